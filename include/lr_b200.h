@@ -1,0 +1,148 @@
+/*
+ * lr_b200.h — C-ABI of liblr_b200.so: the B200 (sm_100a) hot path of joseph-zhong/LipReading.
+ *
+ * The reference has no FFI of its own (it is pure Python calling third-party wheels), so the
+ * boundary is the set of Python call sites listed per entry point below ("replaces: file:line",
+ * paths relative to the reference checkout).  INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add at each site.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer unless the name ends in _host;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates,
+ *     never synchronises, never throws; returns 0 or a negative LR_E* code, text in lr_last_error();
+ *   - tensors are dense row-major with the shapes given in the comments;
+ *   - re-entrant across streams and devices (one process per GPU under data parallelism).
+ */
+#ifndef LR_B200_H_
+#define LR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LR_OK            0
+#define LR_EINVAL       -1   /* bad argument / unsupported shape          */
+#define LR_ECUDA        -2   /* CUDA runtime / driver error at launch     */
+#define LR_EWORKSPACE   -3   /* workspace too small                       */
+#define LR_EARCH        -4   /* device is not sm_100 (tcgen05 paths)      */
+
+#define LR_RNN_TANH 0
+#define LR_RNN_GRU  1
+#define LR_RNN_LSTM 2
+
+#define LR_F32  0
+#define LR_BF16 1
+
+/* -------- library ---------------------------------------------------------------------- */
+int         lr_abi_version(void);
+const char* lr_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t    lr_launch_count(void);
+
+/* -------- a15: CTC alpha/beta + gradient ----------------------------------------------- */
+/* replaces: src/train/ctc_loss.py:85,100 (F.ctc_loss(...cpu()) and its autograd backward).
+ * log_probs (B,T,C) f32 batch-first (the layout VideoEncoder emits; no transpose, no D2H),
+ * targets (B,Lmax) i32 CTC classes (label+1, blank=0), input_lens/target_lens (B) i32.
+ * nll (B) f32 = -log p(target|input), +inf when infeasible.
+ * grad (B,T,C) f32 or NULL: d nll_b / d log_probs with torch's native-CTC convention
+ *   exp(lp) - exp(log(alpha*beta summed per class) + nll - lp), zero for t >= input_len.     */
+size_t lr_ctc_workspace(int B, int T, int C, int Lmax);
+int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lens,
+                   const int32_t* target_lens, int B, int T, int C, int Lmax,
+                   float* nll, float* grad, void* workspace, size_t ws_bytes, void* stream);
+/* out[b,:,:] = in[b,:,:] * scale[b]  (chain rule for the per-sample upstream gradient).      */
+int lr_scale_rows(const float* in, const float* scale, float* out, int B, int64_t row_elems,
+                  void* stream);
+
+/* -------- a14: output_proj + masked log-softmax ------------------------------------------ */
+/* replaces: src/models/lipreader/better_model.py:92-93 (nn.Linear + allennlp masked_log_softmax).
+ * hidden (M,K) f32, weight (C,K) f32, bias (C) f32, log_mask (C) f32 additive term
+ * (log(mask+1e-45)); out log_probs (M,C) f32.                                                */
+int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, const float* bias,
+                           const float* log_mask, float* log_probs, int M, int K, int C,
+                           void* stream);
+/* grad_lp (M,C) upstream; writes d_logits (M,C) = g - softmax*sum(g), d_bias (C) (zeroed by the
+ * call), and d_hidden (M,K) = d_logits @ weight, d_weight (C,K) = d_logits^T @ hidden (zeroed by
+ * the call).                                                                                 */
+int lr_proj_logsoftmax_bwd(const float* grad_lp, const float* log_probs, const float* hidden,
+                           const float* weight, float* d_logits, float* d_hidden,
+                           float* d_weight, float* d_bias, int M, int K, int C, void* stream);
+
+/* -------- a12/a13: (bi)directional recurrent layer, packed-sequence semantics ------------ */
+/* replaces: src/models/lipreader/better_model.py:64-89 (sort -> pack -> nn.{LSTM,GRU,RNN} ->
+ * unpack -> unsort).  gi (B,T,D,G*H) f32 = x @ W_ih^T + b_ih precomputed by the caller (one
+ * GEMM for all T and both directions), w_hh (D,G*H,H), b_hh (D,G*H), lens (B) i32.
+ * out hidden (B,T,D*H) zero beyond each length; h_n/c_n (D,B,H) state at each sample's own last
+ * valid frame; `saved` (B,T,D,S*H) activations kept for backward (S = lr_rnn_saved_per_unit).  */
+int    lr_rnn_saved_per_unit(int mode);
+size_t lr_rnn_workspace(int mode, int B, int T, int H, int D);
+int lr_rnn_fwd(int mode, const float* gi, const float* w_hh, const float* b_hh,
+               const int32_t* lens, int B, int T, int H, int D,
+               float* hidden, float* h_n, float* c_n, float* saved,
+               void* workspace, size_t ws_bytes, void* stream);
+/* d_hidden (B,T,D*H), d_h_n/d_c_n (D,B,H) or NULL -> d_gi (B,T,D,G*H), d_gh (B,T,D,G*H)
+ * (gradient w.r.t. h@W_hh^T+b_hh pre-activations; the caller forms d_w_hh = d_gh^T @ h_prev).
+ * h_prev_all (B,T,D,H) is also written (the h that entered each step) for that GEMM.          */
+int lr_rnn_bwd(int mode, const float* d_hidden, const float* d_h_n, const float* d_c_n,
+               const float* saved, const float* hidden, const float* w_hh, const int32_t* lens,
+               int B, int T, int H, int D, float* d_gi, float* d_gh, float* h_prev_all,
+               void* workspace, size_t ws_bytes, void* stream);
+
+/* -------- a11: collate / pad -------------------------------------------------------------- */
+/* replaces: src/data/data_loader.py:124-137 (_pad of ragged (T_i,68,3) f64 rows to (B,Tmax,F) f32).
+ * src_concat f64 rows back to back, offsets (B+1) i64 in rows, dst (B,Tmax,F) f32 zero padded.  */
+int lr_collate_pad_f64(const double* src_concat, const int64_t* row_offsets, float* dst,
+                       int B, int Tmax, int F, void* stream);
+
+/* -------- a2/a3: rectangle geometry (integer exact) --------------------------------------- */
+/* replaces: src/utils/data/face.py:76-90 (_applyPadding, padding 0.3) and
+ * src/models/face/prnet.py:112-119 (old_size, center, size=int(old_size*1.6)).
+ * rects (N,4) i32 (left,right,top,bottom); out rect_pad (N,4) i32, crop (N,4) i32 = (2*cx,2*cy,
+ * size, 0) with the centre doubled so it stays integral.                                      */
+int lr_rect_geometry(const int32_t* rects, int N, int img_h, int img_w,
+                     int32_t* rect_pad, int32_t* crop, void* stream);
+
+/* -------- a4: /255 + bilinear similarity warp to 256x256 ----------------------------------- */
+/* replaces: src/models/face/prnet.py:137-143 (estimate_transform + image/255. + skimage warp).
+ * frames (N,H,W,3) u8, crop (N,4) i32 from lr_rect_geometry -> out (N,256,256,3) f32 in [0,1].  */
+int lr_warp256(const uint8_t* frames, const int32_t* crop, float* out, int N, int H, int W,
+               void* stream);
+
+/* -------- a6-a9: position-map restore + landmark/vertex gather + translate ---------------- */
+/* replaces: src/models/face/prnet.py:151-156,169,179-180 and src/utils/data/face.py:171-174.
+ * posmap (N,256,256,3) f32 (CNN output * 281.6), crop/rect_pad from lr_rect_geometry,
+ * kpt_idx (68) i32 flat indices row*256+col, face_idx (V) i32 or NULL.
+ * out lmk (N,68,3) f64, vtx (N,V,3) f64 or NULL: x' = (u/s + tx') - left_pad etc.              */
+int lr_posmap_gather(const float* posmap, const int32_t* crop, const int32_t* rect_pad,
+                     const int32_t* kpt_idx, int n_kpt, const int32_t* face_idx, int n_vtx,
+                     double* lmk, double* vtx, int N, void* stream);
+
+/* -------- N2: mouth ROI crop + bilinear resize (extension, no reference code) -------------- */
+/* lmk (N,68,3) f64 face-relative landmarks + rect_pad -> roi from landmarks 48:68
+ * (face.py:21 `_mouth`), fixed aspect out_w:out_h, bilinear -> clips (N,out_h,out_w,3) u8.     */
+int lr_mouth_crop(const uint8_t* frames, const double* lmk, const int32_t* rect_pad,
+                  uint8_t* out, int32_t* roi, int N, int H, int W, int out_h, int out_w,
+                  void* stream);
+
+/* -------- N1: spatio-temporal conv front-end on tcgen05 ------------------------------------ */
+/* extension behind VideoEncoder(frame_processing='conv3d'); oracle = torch.nn.Conv3d fp32.
+ * See lipreading_b200/csrc/conv3d_sm100.cu for the tile geometry.                             */
+int lr_conv3d_supported(void);
+/* u8 NDHWC clip (B,T,H,W,3) -> bf16 space-to-depth, zero-padded (B,T+2,H/2+2,W/2+2,16), /255. */
+int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, void* stream);
+/* Stride-1 conv k=(KT,KH,KW) over a zero-padded channels-last bf16 volume
+ *   x (B,Tp,Hp,Wp,Cin) with Tp=T+KT-1, Hp=H+KH-1, Wp=W+KW-1, w (Cout,KT,KH,KW,Cin) bf16, bias f32
+ * fused bias + ReLU + MaxPool(1,2,2) epilogue; writes the pooled bf16 activation into the
+ * interior of a zero-padded volume y (B,T+2*pt,H/2+2*ph,W/2+2*pw,Cout) ready for the next layer
+ * and the 2-bit pool argmax (u8, B,T,H/2,W/2,Cout) for backward.                               */
+int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
+                  int B, int T, int H, int W, int Cin, int Cout, int KT, int KH, int KW,
+                  int out_pt, int out_ph, int out_pw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LR_B200_H_ */

@@ -1,0 +1,304 @@
+// ctc.cu — CTC alpha/beta dynamic programme with fused gradient.
+//
+// Replaces the reference's `F.ctc_loss(log_probs.transpose(0,1).cpu(), ...)` + autograd backward
+// (src/train/ctc_loss.py:85,100): no transpose, no device->host copy, one kernel for loss+gradient.
+//
+// One CTA per clip.  The clip's (T,C) log-prob block is contiguous in the batch-first layout the
+// encoder emits, so it is pulled into shared memory with ONE bulk-async copy (TMA, UBLKCP) while
+// the other threads expand the label into the 2L+1 lattice classes.  Warp 0 runs the alpha
+// recursion and warp 1 the beta recursion concurrently out of shared memory (the (T,S) lattices
+// never touch HBM when they fit; otherwise they spill to the caller's workspace through the same
+// generic pointers).  All warps then build the gradient rows
+//     g[t,c] = exp(lp[t,c]) - exp(logsum_{s: l'_s = c}(alpha_t(s)+beta_t(s)) + nll - lp[t,c])
+// (torch's native-CTC convention, aten/src/ATen/native/LossCTC.cpp) deterministically: repeated
+// label classes are chained through a per-clip "next occurrence" list, no atomics.
+//
+// HBM traffic is exactly the algorithmic 2*T*C*4 bytes per clip (39 000 B at T=75,C=65).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kCtcThreads = 128;
+constexpr int kCtcWarps = kCtcThreads / 32;
+constexpr size_t kCtcSmemCap = 200 * 1024;
+
+struct CtcPlan {
+  int Smax;
+  int Cpad;
+  size_t off_cls, off_skip, off_nxt, off_head, off_rowbuf, off_misc, off_lp, off_alpha, off_beta;
+  size_t lp_tile_bytes;
+  size_t smem_bytes;
+  int lp_in_smem;
+  int lat_in_smem;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+CtcPlan make_plan(int T, int C, int Lmax) {
+  CtcPlan p;
+  p.Smax = 2 * Lmax + 1;
+  p.Cpad = (C + 31) / 32 * 32;
+  size_t off = 16;  // mbarrier
+  p.off_cls = off;   off += (size_t)p.Smax * 4;
+  p.off_skip = off;  off += (size_t)p.Smax * 4;
+  p.off_nxt = off;   off += (size_t)(Lmax + 1) * 4;
+  p.off_head = off;  off += (size_t)(Lmax + 1) * 4;
+  p.off_rowbuf = off; off += (size_t)kCtcWarps * p.Cpad * 4;
+  p.off_misc = off;  off += 16;
+  off = align_up(off, 16);
+  size_t fixed = off;
+  p.lp_tile_bytes = align_up((size_t)T * C * 4, 16) + 32;
+  size_t lat = (size_t)T * p.Smax * 4;
+  p.lp_in_smem = (fixed + p.lp_tile_bytes) <= kCtcSmemCap;
+  p.lat_in_smem = p.lp_in_smem && (fixed + p.lp_tile_bytes + 2 * lat) <= kCtcSmemCap;
+  p.off_lp = fixed;
+  size_t end = fixed + (p.lp_in_smem ? p.lp_tile_bytes : 0);
+  p.off_alpha = end;
+  p.off_beta = end + lat;
+  if (p.lat_in_smem) end += 2 * lat;
+  p.smem_bytes = end;
+  return p;
+}
+
+__global__ void __launch_bounds__(kCtcThreads)
+ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
+                           const int32_t* __restrict__ in_lens,
+                           const int32_t* __restrict__ tgt_lens, int B, int T, int C, int Lmax,
+                           float* __restrict__ nll_out, float* __restrict__ grad,
+                           float* __restrict__ ws, CtcPlan plan) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  int Tb = in_lens[b];
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  int L = tgt_lens[b];
+  L = L < 0 ? 0 : (L > Lmax ? Lmax : L);
+  const int S = 2 * L + 1;
+  const int Smax = plan.Smax;
+
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  int* cls = reinterpret_cast<int*>(smem_raw + plan.off_cls);
+  int* skip = reinterpret_cast<int*>(smem_raw + plan.off_skip);
+  int* nxt = reinterpret_cast<int*>(smem_raw + plan.off_nxt);
+  int* head = reinterpret_cast<int*>(smem_raw + plan.off_head);
+  float* rowbuf = reinterpret_cast<float*>(smem_raw + plan.off_rowbuf) + warp * plan.Cpad;
+  float* misc = reinterpret_cast<float*>(smem_raw + plan.off_misc);
+
+  const float* lp_g = lp_all + (size_t)b * T * C;
+  const int32_t* tgt = targets + (size_t)b * Lmax;
+
+  // ---- phase 0: bulk-load the clip's log-probs, expand labels --------------------------------
+  const float* lp = lp_g;
+  uint32_t tail_begin = 0, n_valid = (uint32_t)Tb * C;
+  float* lp_s = nullptr;
+  if (plan.lp_in_smem && Tb > 0) {
+    unsigned char* tile = smem_raw + plan.off_lp;
+    uintptr_t g0 = reinterpret_cast<uintptr_t>(lp_g);
+    uintptr_t a0 = g0 & ~(uintptr_t)15;
+    uint32_t shift = (uint32_t)(g0 - a0);
+    // never read past the end of the (B,T,C) tensor: bulk part stops at the last 16-byte boundary
+    uintptr_t tensor_end = reinterpret_cast<uintptr_t>(lp_all + (size_t)B * T * C);
+    uintptr_t want_end = g0 + (uintptr_t)n_valid * 4;
+    uintptr_t a1 = (want_end + 15) & ~(uintptr_t)15;
+    if (a1 > tensor_end) a1 = tensor_end & ~(uintptr_t)15;
+    uint32_t bulk_bytes = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
+    lp_s = reinterpret_cast<float*>(tile + shift);
+    lp = lp_s;
+    // floats covered by the bulk copy, counted from lp_g
+    tail_begin = bulk_bytes > shift ? (bulk_bytes - shift) / 4 : 0;
+    if (tail_begin > n_valid) tail_begin = n_valid;
+    if (tid == 0) {
+      lr_mbar_init(bar, 1);
+      lr_fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (bulk_bytes > 0) {
+        lr_mbar_expect_tx(bar, bulk_bytes);
+        lr_bulk_g2s(tile, reinterpret_cast<const void*>(a0), bulk_bytes, bar);
+      } else {
+        lr_mbar_arrive(bar);
+      }
+    }
+  }
+
+  for (int s = tid; s < S; s += kCtcThreads) {
+    int c = (s & 1) ? tgt[s >> 1] : 0;
+    cls[s] = c;
+  }
+  // next-occurrence chains over label positions (O(L^2) but L <= 256 and off the critical path)
+  for (int j = tid; j < L; j += kCtcThreads) {
+    int cj = tgt[j];
+    int h = 1, n = -1;
+    for (int k = 0; k < j; ++k)
+      if (tgt[k] == cj) { h = 0; break; }
+    for (int k = j + 1; k < L; ++k)
+      if (tgt[k] == cj) { n = k; break; }
+    head[j] = h;
+    nxt[j] = n;
+  }
+  __syncthreads();
+  for (int s = tid; s < S; s += kCtcThreads) {
+    int f = 0;
+    if ((s & 1) && s >= 3 && cls[s] != cls[s - 2]) f |= 1;      // alpha may arrive from s-2
+    if ((s & 1) && s + 2 < S && cls[s + 2] != cls[s]) f |= 2;   // beta may arrive from s+2
+    skip[s] = f;
+  }
+  if (lp_s != nullptr) {
+    lr_mbar_wait(bar, 0);
+    // the <16-byte tail (and anything the clamp cut off) comes in with plain loads
+    for (uint32_t i = tail_begin + tid; i < n_valid; i += kCtcThreads) lp_s[i] = lp_g[i];
+  }
+  __syncthreads();
+
+  float* alpha;
+  float* beta;
+  if (plan.lat_in_smem) {
+    alpha = reinterpret_cast<float*>(smem_raw + plan.off_alpha);
+    beta = reinterpret_cast<float*>(smem_raw + plan.off_beta);
+  } else {
+    alpha = ws + (size_t)b * 2 * T * Smax;
+    beta = alpha + (size_t)T * Smax;
+  }
+
+  // ---- phase 1: alpha on warp 0, beta on warp 1, concurrently ---------------------------------
+  if (Tb > 0) {
+    if (warp == 0) {
+      for (int s = lane; s < S; s += 32)
+        alpha[s] = (s == 0) ? lp[0] : (s == 1 ? lp[cls[1]] : LR_NEG_INF);
+      for (int t = 1; t < Tb; ++t) {
+        __syncwarp();
+        const float* prev = alpha + (size_t)(t - 1) * Smax;
+        float* cur = alpha + (size_t)t * Smax;
+        const float* row = lp + (size_t)t * C;
+        for (int s = lane; s < S; s += 32) {
+          float a0 = prev[s];
+          float a1 = s >= 1 ? prev[s - 1] : LR_NEG_INF;
+          float a2 = (skip[s] & 1) ? prev[s - 2] : LR_NEG_INF;
+          cur[s] = lr_lse3(a0, a1, a2) + row[cls[s]];
+        }
+      }
+    } else if (warp == 1) {
+      float* last = beta + (size_t)(Tb - 1) * Smax;
+      const float* lrow = lp + (size_t)(Tb - 1) * C;
+      for (int s = lane; s < S; s += 32)
+        last[s] = (s == S - 1) ? lrow[0] : (s == S - 2 ? lrow[cls[s]] : LR_NEG_INF);
+      for (int t = Tb - 2; t >= 0; --t) {
+        __syncwarp();
+        const float* nx = beta + (size_t)(t + 1) * Smax;
+        float* cur = beta + (size_t)t * Smax;
+        const float* row = lp + (size_t)t * C;
+        for (int s = lane; s < S; s += 32) {
+          float b0 = nx[s];
+          float b1 = s + 1 < S ? nx[s + 1] : LR_NEG_INF;
+          float b2 = (skip[s] & 2) ? nx[s + 2] : LR_NEG_INF;
+          cur[s] = lr_lse3(b0, b1, b2) + row[cls[s]];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    float nll;
+    if (Tb == 0) {
+      nll = (L == 0) ? 0.f : INFINITY;
+    } else {
+      const float* last = alpha + (size_t)(Tb - 1) * Smax;
+      float l1 = last[S - 1];
+      float l2 = S > 1 ? last[S - 2] : LR_NEG_INF;
+      nll = -lr_lse2(l1, l2);
+    }
+    misc[0] = nll;
+    nll_out[b] = nll;
+  }
+  __syncthreads();
+  if (grad == nullptr) return;
+  const float nll = misc[0];
+  const bool dead = !(nll < INFINITY);  // infeasible alignment (or NaN): gradient defined as 0
+
+  // ---- phase 2: gradient rows, one warp per time step ------------------------------------------
+  float* g_b = grad + (size_t)b * T * C;
+  for (int t = warp; t < T; t += kCtcWarps) {
+    float* g = g_b + (size_t)t * C;
+    if (t >= Tb || dead) {
+      for (int c = lane; c < C; c += 32) g[c] = 0.f;
+      continue;
+    }
+    const float* a = alpha + (size_t)t * Smax;
+    const float* be = beta + (size_t)t * Smax;
+    const float* row = lp + (size_t)t * C;
+    // blank: all even lattice states
+    float m = LR_NEG_INF;
+    for (int s = 2 * lane; s < S; s += 64) m = fmaxf(m, a[s] + be[s]);
+    m = lr_warp_max(m);
+    float sum = 0.f;
+    if (m != LR_NEG_INF)
+      for (int s = 2 * lane; s < S; s += 64) sum += __expf(a[s] + be[s] - m);
+    sum = lr_warp_sum(sum);
+    const float lcab0 = (m == LR_NEG_INF) ? LR_NEG_INF : m + __logf(sum);
+
+    for (int c = lane; c < C; c += 32) rowbuf[c] = __expf(row[c]);
+    __syncwarp();
+    if (lane == 0) {
+      float lp0 = row[0];
+      float occ = (lcab0 == LR_NEG_INF) ? 0.f : __expf(lcab0 + nll - lp0);
+      rowbuf[0] = __expf(lp0) - occ;
+    }
+    for (int j = lane; j < L; j += 32) {
+      if (!head[j]) continue;
+      float acc = a[2 * j + 1] + be[2 * j + 1];
+      for (int k = nxt[j]; k >= 0; k = nxt[k]) acc = lr_lse2(acc, a[2 * k + 1] + be[2 * k + 1]);
+      int c = cls[2 * j + 1];
+      if (c > 0 && c < C) {
+        float lpc = row[c];
+        float occ = (acc == LR_NEG_INF) ? 0.f : __expf(acc + nll - lpc);
+        rowbuf[c] = __expf(lpc) - occ;
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) g[c] = rowbuf[c];
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
+  if (B <= 0 || T <= 0 || C <= 0 || Lmax < 0) return 0;
+  CtcPlan p = make_plan(T, C, Lmax);
+  if (p.lat_in_smem) return 16;
+  return (size_t)B * 2 * T * p.Smax * sizeof(float);
+}
+
+extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
+                              const int32_t* input_lens, const int32_t* target_lens, int B, int T,
+                              int C, int Lmax, float* nll, float* grad, void* workspace,
+                              size_t ws_bytes, void* stream) {
+  LR_CHECK_ARG(log_probs && targets && input_lens && target_lens && nll,
+               "lr_ctc_fwd_bwd: null pointer");
+  LR_CHECK_ARG(B > 0 && T > 0 && C > 1 && Lmax >= 0, "lr_ctc_fwd_bwd: bad shape B=%d T=%d C=%d L=%d",
+               B, T, C, Lmax);
+  if (Lmax == 0) Lmax = 1;  // keep array extents non-zero; target_lens still clamp to 0
+  CtcPlan p = make_plan(T, C, Lmax);
+  if (!p.lat_in_smem) {
+    size_t need = (size_t)B * 2 * T * p.Smax * sizeof(float);
+    if (!workspace || ws_bytes < need) {
+      lr_set_error("lr_ctc_fwd_bwd: workspace %zu < %zu", ws_bytes, need);
+      return LR_EWORKSPACE;
+    }
+  }
+  static thread_local size_t configured = 0;
+  if (p.smem_bytes > 48 * 1024 && p.smem_bytes > configured) {
+    LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_grad_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kCtcSmemCap));
+    configured = kCtcSmemCap;
+  }
+  ctc_alpha_beta_grad_kernel<<<B, kCtcThreads, p.smem_bytes, lr_stream(stream)>>>(
+      log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad,
+      reinterpret_cast<float*>(workspace), p);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}

@@ -1,0 +1,271 @@
+// vision.cu — per-frame geometry kernels of the landmark dataview path (SURVEY §8 rows a2-a4,
+// a6-a9, a11, N2).  All of them are HBM/latency-bound byte and index work: batched over frames,
+// coalesced 128-bit accesses where the layout allows it, grids sized in multiples of 148 SMs.
+//
+// Reference arithmetic restated (file:line in the reference checkout):
+//   _applyPadding        src/utils/data/face.py:76-90        -> rect_geometry_kernel
+//   PRN.process crop box src/models/face/prnet.py:112-119    -> rect_geometry_kernel
+//   estimate_transform / image/255. / warp   prnet.py:137-143 -> warp256_kernel
+//   restore + get_landmarks/get_vertices     prnet.py:151-156,169,179-180
+//   getFace translate    src/utils/data/face.py:171-174      -> posmap_gather_kernel
+//   _collate_fn._pad     src/data/data_loader.py:124-137     -> collate_pad_kernel
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// a2 + a3.  Python's int(0.3*bw) == (3*bw)/10 and int(((r-l)+(b-t))/2*1.6) == (4*k)/5 for every
+// non-negative extent below 2000 / 6000 (checked exhaustively against the float64 restatement in
+// tests/test_vision_oracle.py), so the kernel is integer-exact.
+__global__ void rect_geometry_kernel(const int32_t* __restrict__ rects, int N, int img_h, int img_w,
+                                     int32_t* __restrict__ rect_pad, int32_t* __restrict__ crop) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int4 rc = reinterpret_cast<const int4*>(rects)[i];
+  int l = rc.x, r = rc.y, t = rc.z, b = rc.w;
+  int bw = r - l, bh = b - t;
+  int pw = (3 * bw) / 10, ph = (3 * bh) / 10;
+  int4 o;
+  o.x = max(0, l - pw);
+  o.y = min(img_w, r + pw);
+  o.z = max(0, t - ph);
+  o.w = min(img_h, b + ph);
+  reinterpret_cast<int4*>(rect_pad)[i] = o;
+  int k = bw + bh;
+  int4 c;
+  c.x = r + l;          // 2*cx
+  c.y = b + t;          // 2*cy
+  c.z = (4 * k) / 5;    // size
+  c.w = 0;
+  reinterpret_cast<int4*>(crop)[i] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4.  One thread per output pixel (u fastest => 12-byte stores coalesce into 384 B per warp).
+// Source sampling follows skimage 0.14 `_warp_fast` bilinear, mode='constant', cval=0:
+//   (x,y) = T^-1 (u,v) ; floor/ceil taps ; out-of-image taps contribute 0.
+// The similarity fitted to the three crop corners is an exact axis-aligned scale + shift, so
+//   x = u*size/255 + (cx - size/2),  y = v*size/255 + (cy - size/2)
+// evaluated in fp64 like the reference (fp32 coordinates at x~1000 would already cost 1e-4).
+// Only the <= size^2 window of the frame is ever read (the reference divides the whole frame).
+__global__ void __launch_bounds__(256)
+warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ crop,
+               float* __restrict__ out, int H, int W) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;   // 0..65535
+  const int v = pix >> 8, u = pix & 255;
+  const int4 c = reinterpret_cast<const int4*>(crop)[n];
+  const double size = (double)c.z;
+  const double step = size / 255.0;
+  const double x0 = 0.5 * (double)c.x - 0.5 * size;
+  const double y0 = 0.5 * (double)c.y - 0.5 * size;
+  const double x = (double)u * step + x0;
+  const double y = (double)v * step + y0;
+  const double fx = floor(x), fy = floor(y);
+  const int minc = (int)fx, minr = (int)fy;
+  const int maxc = (int)ceil(x), maxr = (int)ceil(y);
+  const double dc = x - fx, dr = y - fy;
+  const uint8_t* img = frames + (size_t)n * H * W * 3;
+  const bool r0 = minr >= 0 && minr < H, r1 = maxr >= 0 && maxr < H;
+  const bool c0 = minc >= 0 && minc < W, c1 = maxc >= 0 && maxc < W;
+  const uint8_t* p00 = img + ((size_t)minr * W + minc) * 3;
+  const uint8_t* p01 = img + ((size_t)minr * W + maxc) * 3;
+  const uint8_t* p10 = img + ((size_t)maxr * W + minc) * 3;
+  const uint8_t* p11 = img + ((size_t)maxr * W + maxc) * 3;
+  float res[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    double v00 = (r0 && c0) ? (double)p00[ch] / 255.0 : 0.0;
+    double v01 = (r0 && c1) ? (double)p01[ch] / 255.0 : 0.0;
+    double v10 = (r1 && c0) ? (double)p10[ch] / 255.0 : 0.0;
+    double v11 = (r1 && c1) ? (double)p11[ch] / 255.0 : 0.0;
+    double top = (1.0 - dc) * v00 + dc * v01;
+    double bot = (1.0 - dc) * v10 + dc * v11;
+    res[ch] = (float)((1.0 - dr) * top + dr * bot);
+  }
+  float* o = out + ((size_t)n * 65536 + pix) * 3;
+  o[0] = res[0];
+  o[1] = res[1];
+  o[2] = res[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6-a9 fused: for each requested map location, undo the crop similarity, translate into the
+// padded-face frame, emit float64 (the dataview dtype).  The full (256,256,3) "restored" map the
+// reference materialises per frame is never written: only the gathered points are.
+//   z = f32(P_z) / f32(s)   (numpy-1.x value-based casting keeps this division in float32)
+//   x = f64(P_x) * (1/s) + x0 - left_pad ,  y likewise with top_pad
+__global__ void __launch_bounds__(256)
+posmap_gather_kernel(const float* __restrict__ posmap, const int32_t* __restrict__ crop,
+                     const int32_t* __restrict__ rect_pad, const int32_t* __restrict__ idx,
+                     int n_idx, double* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int4 c = reinterpret_cast<const int4*>(crop)[n];
+  const int4 rp = reinterpret_cast<const int4*>(rect_pad)[n];
+  const double size = (double)c.z;
+  const double s = 255.0 / size;
+  const double inv_s = size / 255.0;
+  const float s32 = (float)s;
+  const double x0 = 0.5 * (double)c.x - 0.5 * size;
+  const double y0 = 0.5 * (double)c.y - 0.5 * size;
+  const double left = (double)rp.x, top = (double)rp.z;
+  const float* map = posmap + (size_t)n * 65536 * 3;
+  double* o = out + (size_t)n * n_idx * 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_idx; i += gridDim.x * blockDim.x) {
+    const int flat = idx[i];
+    const float* p = map + (size_t)flat * 3;
+    const float px = p[0], py = p[1], pz = p[2];
+    o[(size_t)i * 3 + 0] = ((double)px * inv_s + x0) - left;
+    o[(size_t)i * 3 + 1] = ((double)py * inv_s + y0) - top;
+    o[(size_t)i * 3 + 2] = (double)(pz / s32);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11.  Ragged float64 rows -> zero-padded (B,Tmax,F) float32.  One CTA row-block per clip.
+__global__ void __launch_bounds__(256)
+collate_pad_kernel(const double* __restrict__ src, const int64_t* __restrict__ offs,
+                   float* __restrict__ dst, int Tmax, int F) {
+  const int b = blockIdx.y;
+  const int64_t r0 = offs[b], r1 = offs[b + 1];
+  const int64_t n_valid = (r1 - r0) * F;
+  const int64_t n_all = (int64_t)Tmax * F;
+  const double* s = src + r0 * F;
+  float* d = dst + (int64_t)b * n_all;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_all;
+       i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = i < n_valid ? (float)s[i] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N2 (extension).  Mouth ROI from landmarks 48:68 and a bilinear resize to out_h x out_w u8.
+// Spec (mirrored by oracle/vision.py:mouth_roi / mouth_crop):
+//   frame coords = landmark + (left_pad, top_pad); bbox of the 20 mouth points;
+//   rw = 1.2 * max(xmax-xmin, (ymax-ymin) * out_w/out_h), rh = rw * out_h/out_w, both >= 2;
+//   x_lo = floor(cx - rw/2), y_lo = floor(cy - rh/2), roi_w = ceil(rw), roi_h = ceil(rh);
+//   sample centre-aligned: sx = (ox+0.5)*roi_w/out_w - 0.5 + x_lo, clamp to the frame (replicate),
+//   fp32 lerp, round-half-even to u8.
+__global__ void mouth_roi_kernel(const double* __restrict__ lmk, const int32_t* __restrict__ rect_pad,
+                                 int32_t* __restrict__ roi, int N, int out_h, int out_w) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const double* p = lmk + (size_t)n * 68 * 3;
+  const int4 rp = reinterpret_cast<const int4*>(rect_pad)[n];
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+  for (int i = 48; i < 68; ++i) {
+    double x = p[i * 3 + 0] + (double)rp.x, y = p[i * 3 + 1] + (double)rp.z;
+    xmin = fmin(xmin, x); xmax = fmax(xmax, x);
+    ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+  }
+  double aspect = (double)out_w / (double)out_h;
+  double rw = 1.2 * fmax(xmax - xmin, (ymax - ymin) * aspect);
+  if (rw < 2.0) rw = 2.0;
+  double rh = rw / aspect;
+  if (rh < 2.0) rh = 2.0;
+  double cx = 0.5 * (xmin + xmax), cy = 0.5 * (ymin + ymax);
+  int4 o;
+  o.x = (int)floor(cx - 0.5 * rw);
+  o.y = (int)floor(cy - 0.5 * rh);
+  o.z = (int)ceil(rw);
+  o.w = (int)ceil(rh);
+  reinterpret_cast<int4*>(roi)[n] = o;
+}
+
+__global__ void __launch_bounds__(256)
+mouth_crop_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi,
+                  uint8_t* __restrict__ out, int H, int W, int out_h, int out_w) {
+  const int n = blockIdx.y;
+  const int4 r = reinterpret_cast<const int4*>(roi)[n];
+  const uint8_t* img = frames + (size_t)n * H * W * 3;
+  uint8_t* o = out + (size_t)n * out_h * out_w * 3;
+  const float sxs = (float)r.z / (float)out_w, sys = (float)r.w / (float)out_h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < out_h * out_w;
+       i += gridDim.x * blockDim.x) {
+    int oy = i / out_w, ox = i - oy * out_w;
+    float sx = __fadd_rn(__fadd_rn(__fmul_rn((float)ox + 0.5f, sxs), -0.5f), (float)r.x);
+    float sy = __fadd_rn(__fadd_rn(__fmul_rn((float)oy + 0.5f, sys), -0.5f), (float)r.y);
+    float fx = floorf(sx), fy = floorf(sy);
+    float ax = sx - fx, ay = sy - fy;
+    int x0 = min(max((int)fx, 0), W - 1), x1 = min(max((int)fx + 1, 0), W - 1);
+    int y0 = min(max((int)fy, 0), H - 1), y1 = min(max((int)fy + 1, 0), H - 1);
+    const uint8_t* p00 = img + ((size_t)y0 * W + x0) * 3;
+    const uint8_t* p01 = img + ((size_t)y0 * W + x1) * 3;
+    const uint8_t* p10 = img + ((size_t)y1 * W + x0) * 3;
+    const uint8_t* p11 = img + ((size_t)y1 * W + x1) * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float top = __fadd_rn(__fmul_rn(1.f - ax, (float)p00[ch]), __fmul_rn(ax, (float)p01[ch]));
+      float bot = __fadd_rn(__fmul_rn(1.f - ax, (float)p10[ch]), __fmul_rn(ax, (float)p11[ch]));
+      float val = __fadd_rn(__fmul_rn(1.f - ay, top), __fmul_rn(ay, bot));
+      val = fminf(fmaxf(rintf(val), 0.f), 255.f);
+      o[(size_t)i * 3 + ch] = (uint8_t)val;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int lr_rect_geometry(const int32_t* rects, int N, int img_h, int img_w,
+                                int32_t* rect_pad, int32_t* crop, void* stream) {
+  LR_CHECK_ARG(rects && rect_pad && crop && N > 0 && img_h > 0 && img_w > 0, "lr_rect_geometry: bad args");
+  rect_geometry_kernel<<<lr_div_up(N, 128), 128, 0, lr_stream(stream)>>>(rects, N, img_h, img_w,
+                                                                         rect_pad, crop);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+extern "C" int lr_warp256(const uint8_t* frames, const int32_t* crop, float* out, int N, int H, int W,
+                          void* stream) {
+  LR_CHECK_ARG(frames && crop && out && N > 0 && H > 0 && W > 0, "lr_warp256: bad args");
+  LR_CHECK_ARG(N <= 65535, "lr_warp256: at most 65535 frames per call");
+  dim3 grid(256, N);
+  warp256_kernel<<<grid, 256, 0, lr_stream(stream)>>>(frames, crop, out, H, W);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+extern "C" int lr_posmap_gather(const float* posmap, const int32_t* crop, const int32_t* rect_pad,
+                                const int32_t* kpt_idx, int n_kpt, const int32_t* face_idx, int n_vtx,
+                                double* lmk, double* vtx, int N, void* stream) {
+  LR_CHECK_ARG(posmap && crop && rect_pad && N > 0 && N <= 65535, "lr_posmap_gather: bad args");
+  LR_CHECK_ARG((kpt_idx && lmk && n_kpt > 0) || (face_idx && vtx && n_vtx > 0),
+               "lr_posmap_gather: nothing to gather");
+  cudaStream_t st = lr_stream(stream);
+  if (kpt_idx && lmk && n_kpt > 0) {
+    dim3 grid(1, N);
+    posmap_gather_kernel<<<grid, 96, 0, st>>>(posmap, crop, rect_pad, kpt_idx, n_kpt, lmk);
+    LR_CHECK_LAUNCH();
+  }
+  if (face_idx && vtx && n_vtx > 0) {
+    dim3 grid(lr_div_up(n_vtx, 256 * 4), N);
+    posmap_gather_kernel<<<grid, 256, 0, st>>>(posmap, crop, rect_pad, face_idx, n_vtx, vtx);
+    LR_CHECK_LAUNCH();
+  }
+  return LR_OK;
+}
+
+extern "C" int lr_collate_pad_f64(const double* src_concat, const int64_t* row_offsets, float* dst,
+                                  int B, int Tmax, int F, void* stream) {
+  LR_CHECK_ARG(src_concat && row_offsets && dst && B > 0 && B <= 65535 && Tmax > 0 && F > 0,
+               "lr_collate_pad_f64: bad args");
+  int gx = lr_div_up((int64_t)Tmax * F, 256 * 4);
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  collate_pad_kernel<<<grid, 256, 0, lr_stream(stream)>>>(src_concat, row_offsets, dst, Tmax, F);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+extern "C" int lr_mouth_crop(const uint8_t* frames, const double* lmk, const int32_t* rect_pad,
+                             uint8_t* out, int32_t* roi, int N, int H, int W, int out_h, int out_w,
+                             void* stream) {
+  LR_CHECK_ARG(frames && lmk && rect_pad && out && roi && N > 0 && N <= 65535 && H > 0 && W > 0 &&
+                   out_h > 0 && out_w > 0,
+               "lr_mouth_crop: bad args");
+  cudaStream_t st = lr_stream(stream);
+  mouth_roi_kernel<<<lr_div_up(N, 128), 128, 0, st>>>(lmk, rect_pad, roi, N, out_h, out_w);
+  LR_CHECK_LAUNCH();
+  dim3 grid(lr_div_up(out_h * out_w, 256), N);
+  mouth_crop_kernel<<<grid, 256, 0, st>>>(frames, roi, out, H, W, out_h, out_w);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}

@@ -1,0 +1,247 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/lr_b200.h).
+
+PyTorch here is plumbing: device memory, the current stream and autograd bookkeeping.  The
+arithmetic of every op below runs in liblr_b200.so; the only library calls are the plain GEMMs
+around the recurrent kernel (x @ W_ih^T and the weight-gradient reductions), which go to cuBLAS.
+"""
+import torch
+
+from . import native as N
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# a15: CTC
+# ------------------------------------------------------------------------------------------------
+class _CTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_probs, targets, input_lens, target_lens):
+        N.require_cuda(log_probs, targets, input_lens, target_lens)
+        lp = N.cont(log_probs, torch.float32)
+        tg = N.cont(targets, torch.int32)
+        il = N.cont(input_lens, torch.int32)
+        tl = N.cont(target_lens, torch.int32)
+        B, T, C = lp.shape
+        Lmax = max(int(tg.shape[1]), 1)
+        if tg.shape[1] == 0:
+            tg = torch.zeros((B, 1), dtype=torch.int32, device=lp.device)
+        nll = torch.empty(B, dtype=torch.float32, device=lp.device)
+        need_grad = log_probs.requires_grad
+        grad = torch.empty_like(lp) if need_grad else None
+        L = N.lib()
+        ws = _ws(L.lr_ctc_workspace(B, T, C, Lmax), lp.device)
+        N.check(L.lr_ctc_fwd_bwd(N.ptr(lp), N.ptr(tg), N.ptr(il), N.ptr(tl), B, T, C, Lmax,
+                                 N.ptr(nll), N.ptr(grad), N.ptr(ws), ws.numel(), N.stream()),
+                "lr_ctc_fwd_bwd")
+        ctx.unit_grad = grad
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        grad = ctx.unit_grad
+        if grad is None:
+            return None, None, None, None
+        g = N.cont(g, torch.float32)
+        out = torch.empty_like(grad)
+        B = grad.shape[0]
+        N.check(N.lib().lr_scale_rows(N.ptr(grad), N.ptr(g), N.ptr(out), B, grad[0].numel(), N.stream()),
+                "lr_scale_rows")
+        return out, None, None, None
+
+
+def ctc_nll(log_probs, targets, input_lens, target_lens):
+    """Per-sample CTC negative log-likelihood.  log_probs (B,T,C) f32 batch-first, targets (B,Lmax)
+    CTC classes (label+1, blank=0), lens (B).  Differentiable w.r.t. log_probs (torch's native-CTC
+    gradient convention).  Replaces F.ctc_loss(..., reduction='none') at src/train/ctc_loss.py:85."""
+    return _CTC.apply(log_probs, targets, input_lens, target_lens)
+
+
+# ------------------------------------------------------------------------------------------------
+# a14: Linear + masked log-softmax
+# ------------------------------------------------------------------------------------------------
+class _ProjLogSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, bias, log_mask):
+        N.require_cuda(hidden, weight, bias, log_mask)
+        shp = hidden.shape
+        h2 = N.cont(hidden.reshape(-1, shp[-1]), torch.float32)
+        w, b, lm = N.cont(weight, torch.float32), N.cont(bias, torch.float32), N.cont(log_mask, torch.float32)
+        M, K = h2.shape
+        C = w.shape[0]
+        out = torch.empty((M, C), dtype=torch.float32, device=h2.device)
+        N.check(N.lib().lr_proj_logsoftmax_fwd(N.ptr(h2), N.ptr(w), N.ptr(b), N.ptr(lm), N.ptr(out),
+                                               M, K, C, N.stream()), "lr_proj_logsoftmax_fwd")
+        ctx.save_for_backward(h2, w, out)
+        ctx.in_shape = shp
+        return out.reshape(shp[:-1] + (C,))
+
+    @staticmethod
+    def backward(ctx, g):
+        h2, w, out = ctx.saved_tensors
+        M, K = h2.shape
+        C = w.shape[0]
+        g2 = N.cont(g.reshape(M, C), torch.float32)
+        d_logits = torch.empty_like(out)
+        d_hidden = torch.empty_like(h2)
+        d_w = torch.empty_like(w)
+        d_b = torch.empty(C, dtype=torch.float32, device=w.device)
+        N.check(N.lib().lr_proj_logsoftmax_bwd(N.ptr(g2), N.ptr(out), N.ptr(h2), N.ptr(w), N.ptr(d_logits),
+                                               N.ptr(d_hidden), N.ptr(d_w), N.ptr(d_b), M, K, C, N.stream()),
+                "lr_proj_logsoftmax_bwd")
+        return d_hidden.reshape(ctx.in_shape), d_w, d_b, None
+
+
+def proj_masked_log_softmax(hidden, weight, bias, log_mask):
+    """log_softmax(hidden @ weight^T + bias + log_mask) fused (better_model.py:92-93)."""
+    return _ProjLogSoftmax.apply(hidden, weight, bias, log_mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# a12/a13: one (bi)directional recurrent layer with packed-sequence semantics
+# ------------------------------------------------------------------------------------------------
+class _RNNLayer(torch.autograd.Function):
+    """inputs: x (B,T,I), lens (B) int32, mode str, then per direction (w_ih, w_hh, b_ih, b_hh)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, mode, *weights):
+        N.require_cuda(x, lens, *weights)
+        D = len(weights) // 4
+        G = N.RNN_GATES[mode]
+        B, T, I = x.shape
+        H = weights[1].shape[1]
+        x2 = N.cont(x.reshape(B * T, I), torch.float32)
+        w_ih = torch.cat([weights[4 * d + 0] for d in range(D)], 0)            # (D*G*H, I)
+        b_ih = torch.cat([weights[4 * d + 2] for d in range(D)], 0)
+        w_hh = torch.stack([weights[4 * d + 1] for d in range(D)], 0).contiguous()   # (D,G*H,H)
+        b_hh = torch.stack([weights[4 * d + 3] for d in range(D)], 0).contiguous()
+        gi = torch.addmm(b_ih, x2, w_ih.t())                                    # plain GEMM -> cuBLAS
+        lens32 = N.cont(lens, torch.int32)
+        dev = x.device
+        hidden = torch.empty((B, T, D * H), dtype=torch.float32, device=dev)
+        h_n = torch.empty((D, B, H), dtype=torch.float32, device=dev)
+        c_n = torch.empty((D, B, H), dtype=torch.float32, device=dev) if mode == "LSTM" else None
+        L = N.lib()
+        S = L.lr_rnn_saved_per_unit(N.RNN_MODES[mode])
+        saved = torch.empty((B, T, D, S * H), dtype=torch.float32, device=dev) if S > 0 else None
+        ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
+        N.check(L.lr_rnn_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T, H, D,
+                             N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.ptr(ws), ws.numel(),
+                             N.stream()), "lr_rnn_fwd")
+        ctx.mode, ctx.dims = mode, (B, T, I, H, D, G)
+        ctx.save_for_backward(x2, lens32, w_ih, w_hh, hidden, saved if saved is not None else torch.empty(0, device=dev))
+        ctx.x_needs_grad = x.requires_grad
+        if mode == "LSTM":
+            return hidden, h_n, c_n
+        return hidden, h_n
+
+    @staticmethod
+    def backward(ctx, d_hidden, d_h_n, d_c_n=None):
+        mode = ctx.mode
+        B, T, I, H, D, G = ctx.dims
+        x2, lens32, w_ih, w_hh, hidden, saved = ctx.saved_tensors
+        dev = x2.device
+        d_hidden = N.cont(d_hidden, torch.float32) if d_hidden is not None else torch.zeros_like(hidden)
+        d_h_n = N.cont(d_h_n, torch.float32) if d_h_n is not None else None
+        d_c_n = N.cont(d_c_n, torch.float32) if d_c_n is not None else None
+        w_hh_t = w_hh.transpose(1, 2).contiguous()                              # (D,H,G*H)
+        d_gi = torch.empty((B, T, D, G * H), dtype=torch.float32, device=dev)
+        d_gh = torch.empty((B, T, D, G * H), dtype=torch.float32, device=dev)
+        h_prev = torch.empty((B, T, D, H), dtype=torch.float32, device=dev)
+        L = N.lib()
+        ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
+        N.check(L.lr_rnn_bwd(N.RNN_MODES[mode], N.ptr(d_hidden), N.ptr(d_h_n), N.ptr(d_c_n),
+                             N.ptr(saved) if saved.numel() else None, N.ptr(hidden), N.ptr(w_hh_t), N.ptr(lens32),
+                             B, T, H, D, N.ptr(d_gi), N.ptr(d_gh), N.ptr(h_prev), N.ptr(ws), ws.numel(),
+                             N.stream()), "lr_rnn_bwd")
+        # weight-gradient reductions over B*T: plain GEMMs -> cuBLAS
+        d_gi2 = d_gi.reshape(B * T, D * G * H)
+        d_w_ih = d_gi2.t() @ x2                                                 # (D*G*H, I)
+        d_b_ih = d_gi2.sum(0)
+        d_gh3 = d_gh.reshape(B * T, D, G * H)
+        h_prev3 = h_prev.reshape(B * T, D, H)
+        grads = []
+        for d in range(D):
+            d_w_hh = d_gh3[:, d].t() @ h_prev3[:, d]                            # (G*H, H)
+            d_b_hh = d_gh3[:, d].sum(0)
+            grads += [d_w_ih[d * G * H:(d + 1) * G * H], d_w_hh, d_b_ih[d * G * H:(d + 1) * G * H], d_b_hh]
+        d_x = (d_gi2 @ w_ih).reshape(B, T, I) if ctx.x_needs_grad else None
+        return (d_x, None, None) + tuple(grads)
+
+
+def rnn_layer(x, lens, mode, weights):
+    """weights: flat list per direction [w_ih, w_hh, b_ih, b_hh] (+ the reverse direction's four).
+    Returns (hidden (B,T,D*H), h_n (D,B,H)[, c_n])."""
+    return _RNNLayer.apply(x, lens, mode, *weights)
+
+
+# ------------------------------------------------------------------------------------------------
+# vision ops (no autograd)
+# ------------------------------------------------------------------------------------------------
+def rect_geometry(rects, img_h, img_w):
+    """rects (N,4) int32 (left,right,top,bottom) -> rect_pad (N,4), crop (N,4)=(2cx,2cy,size,0).
+    face.py:76-90 + prnet.py:112-119."""
+    N.require_cuda(rects)
+    r = N.cont(rects, torch.int32)
+    n = r.shape[0]
+    rect_pad = torch.empty_like(r)
+    crop = torch.empty_like(r)
+    N.check(N.lib().lr_rect_geometry(N.ptr(r), n, img_h, img_w, N.ptr(rect_pad), N.ptr(crop), N.stream()),
+            "lr_rect_geometry")
+    return rect_pad, crop
+
+
+def warp256(frames, crop):
+    """frames (N,H,W,3) u8, crop (N,4) -> (N,256,256,3) f32 in [0,1] (prnet.py:137-143)."""
+    N.require_cuda(frames, crop)
+    f = N.cont(frames, torch.uint8)
+    n, H, W, _ = f.shape
+    out = torch.empty((n, 256, 256, 3), dtype=torch.float32, device=f.device)
+    N.check(N.lib().lr_warp256(N.ptr(f), N.ptr(N.cont(crop, torch.int32)), N.ptr(out), n, H, W, N.stream()),
+            "lr_warp256")
+    return out
+
+
+def posmap_gather(posmap, crop, rect_pad, kpt_idx, face_idx=None):
+    """posmap (N,256,256,3) f32 -> landmarks (N,68,3) f64 [, vertices (N,V,3) f64], face-relative
+    (prnet.py:151-156,169,179-180 + face.py:171-174)."""
+    N.require_cuda(posmap, crop, rect_pad, kpt_idx, face_idx)
+    pm = N.cont(posmap, torch.float32)
+    n = pm.shape[0]
+    k = N.cont(kpt_idx, torch.int32)
+    lmk = torch.empty((n, k.numel(), 3), dtype=torch.float64, device=pm.device)
+    vtx = None
+    fi = None
+    if face_idx is not None:
+        fi = N.cont(face_idx, torch.int32)
+        vtx = torch.empty((n, fi.numel(), 3), dtype=torch.float64, device=pm.device)
+    N.check(N.lib().lr_posmap_gather(N.ptr(pm), N.ptr(N.cont(crop, torch.int32)), N.ptr(N.cont(rect_pad, torch.int32)),
+                                     N.ptr(k), k.numel(), N.ptr(fi), fi.numel() if fi is not None else 0,
+                                     N.ptr(lmk), N.ptr(vtx), n, N.stream()), "lr_posmap_gather")
+    return (lmk, vtx) if face_idx is not None else lmk
+
+
+def mouth_crop(frames, lmk, rect_pad, out_h=50, out_w=100):
+    """N2 extension: (N,H,W,3) u8 + landmarks -> (N,out_h,out_w,3) u8 mouth clips, roi (N,4)."""
+    N.require_cuda(frames, lmk, rect_pad)
+    f = N.cont(frames, torch.uint8)
+    n, H, W, _ = f.shape
+    out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=f.device)
+    roi = torch.empty((n, 4), dtype=torch.int32, device=f.device)
+    N.check(N.lib().lr_mouth_crop(N.ptr(f), N.ptr(N.cont(lmk, torch.float64)), N.ptr(N.cont(rect_pad, torch.int32)),
+                                  N.ptr(out), N.ptr(roi), n, H, W, out_h, out_w, N.stream()), "lr_mouth_crop")
+    return out, roi
+
+
+def collate_pad(src_concat, row_offsets, B, Tmax, F):
+    """Ragged f64 rows (sum T_i, F) + offsets (B+1) i64 -> (B,Tmax,F) f32 zero padded
+    (data_loader.py:124-137)."""
+    N.require_cuda(src_concat, row_offsets)
+    s = N.cont(src_concat, torch.float64)
+    o = N.cont(row_offsets, torch.int64)
+    dst = torch.empty((B, Tmax, F), dtype=torch.float32, device=s.device)
+    N.check(N.lib().lr_collate_pad_f64(N.ptr(s), N.ptr(o), N.ptr(dst), B, Tmax, F, N.stream()),
+            "lr_collate_pad_f64")
+    return dst

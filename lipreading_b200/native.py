@@ -1,0 +1,101 @@
+"""ctypes binding of liblr_b200.so (the C-ABI in include/lr_b200.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblr_b200.so")
+
+LR_RNN_TANH, LR_RNN_GRU, LR_RNN_LSTM = 0, 1, 2
+RNN_MODES = {"RNN": LR_RNN_TANH, "GRU": LR_RNN_GRU, "LSTM": LR_RNN_LSTM}
+RNN_GATES = {"RNN": 1, "GRU": 3, "LSTM": 4}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp, _i, _sz, _i64, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64, ctypes.c_uint64
+
+# name -> (restype, argtypes); mirrors include/lr_b200.h one to one.
+SIGNATURES = {
+    "lr_abi_version": (_i, []),
+    "lr_last_error": (ctypes.c_char_p, []),
+    "lr_launch_count": (_u64, []),
+    "lr_ctc_workspace": (_sz, [_i, _i, _i, _i]),
+    "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "lr_scale_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
+    "lr_proj_logsoftmax_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lr_proj_logsoftmax_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lr_rnn_saved_per_unit": (_i, [_i]),
+    "lr_rnn_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "lr_rnn_fwd": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lr_rnn_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lr_collate_pad_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lr_rect_geometry": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "lr_warp256": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lr_posmap_gather": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "lr_mouth_crop": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises NativeError when the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "liblr_b200.so not built (%s). Run `python -m lipreading_b200.build` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % LIB_PATH)
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)       # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def register(name, restype, argtypes):
+    SIGNATURES[name] = (restype, argtypes)
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.restype, fn.argtypes = restype, argtypes
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError("%s failed (%d): %s" % (what, rc, lib().lr_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().lr_launch_count())
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NativeError("lipreading_b200 ops run on CUDA tensors only (got %s); there is no CPU path" % t.device)
+
+
+def cont(t, dtype=None):
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()

@@ -1,0 +1,190 @@
+"""-m gpu parity tests of the sequence half: CUDA path (through the C-ABI) vs the CPU oracle.
+
+Tolerances (fp32 path): log-probs 1e-4 abs, CTC loss 1e-4 abs, gradients 1e-4 rel to
+the gradient's max magnitude."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sequence as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_labels(g, B, Lmax, lo=1, hi=None, nclass=64, repeat_p=0.3):
+    hi = hi or Lmax
+    lens = torch.randint(lo, hi + 1, (B,), generator=g)
+    lab = torch.zeros(B, Lmax, dtype=torch.long)
+    for b in range(B):
+        seq = torch.randint(4, nclass, (int(lens[b]),), generator=g)
+        for i in range(1, len(seq)):                      # force some repeats (skip-transition rule)
+            if torch.rand(1, generator=g) < repeat_p:
+                seq[i] = seq[i - 1]
+        lab[b, : len(seq)] = seq
+    return lab, lens
+
+
+def _relerr(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("B,T,C,Lmax", [(7, 20, 65, 8), (3, 75, 65, 30), (2, 300, 65, 120), (1, 5, 65, 1)])
+def test_ctc_nll_and_grad(native_lib, cuda, B, T, C, Lmax):
+    from lipreading_b200 import functional as LF
+    g = torch.Generator().manual_seed(123456 + B * T)
+    lp = torch.randn(B, T, C, generator=g).log_softmax(-1)
+    lab, tl = _rand_labels(g, B, Lmax, hi=min(Lmax, T // 2))
+    il = torch.randint(max(T // 2, int(tl.max()) * 2), T + 1, (B,), generator=g).sort().values
+    tgt = lab + 1
+    lp_ref = lp.clone().requires_grad_(True)
+    nll_ref = O.ctc_nll_torch(lp_ref, tgt, il, tl)
+    w = torch.rand(B, generator=g) + 0.5
+    (nll_ref * w).sum().backward()
+
+    lp_d = lp.to(cuda).requires_grad_(True)
+    nll = LF.ctc_nll(lp_d, tgt.to(cuda), il.to(cuda), tl.to(cuda))
+    (nll * w.to(cuda)).sum().backward()
+    assert torch.allclose(nll.cpu(), nll_ref.detach(), atol=1e-4, rtol=1e-6), (nll.cpu(), nll_ref)
+    assert _relerr(lp_d.grad.cpu(), lp_ref.grad) < 1e-4
+    # independent restatement (published recursion, float64) on sample 0
+    n0, g0 = O.ctc_alpha_beta(lp[0, : int(il[0])].numpy(), tgt[0, : int(tl[0])].numpy())
+    assert abs(float(nll[0]) - n0) < 1e-4 * max(1.0, abs(n0))
+    got = (lp_d.grad[0, : int(il[0])].cpu() / w[0]).numpy()
+    assert np.abs(got - g0).max() < 1e-4
+
+
+def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda):
+    from lipreading_b200 import functional as LF
+    g = torch.Generator().manual_seed(1)
+    lp = torch.randn(2, 6, 65, generator=g).log_softmax(-1).to(cuda).requires_grad_(True)
+    tgt = torch.randint(5, 60, (2, 10), generator=g).to(cuda)
+    nll = LF.ctc_nll(lp, tgt, torch.tensor([6, 6], device=cuda), torch.tensor([10, 2], device=cuda))
+    assert torch.isinf(nll[0]) and torch.isfinite(nll[1])
+    nll[1].backward()
+    assert torch.isfinite(lp.grad).all() and float(lp.grad[0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,K", [(300, 512), (75, 256), (1000, 1400)])
+def test_proj_masked_log_softmax(native_lib, cuda, M, K):
+    from lipreading_b200 import functional as LF
+    g = torch.Generator().manual_seed(7)
+    c2i = O.build_char2idx()
+    C = len(c2i) + 1
+    h = torch.randn(M, K, generator=g)
+    w = torch.randn(C, K, generator=g) / K ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    lm = O.log_mask_vector(len(c2i), c2i)
+    up = torch.randn(M, C, generator=g)
+    hr, wr, br = h.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = O.masked_log_softmax(hr @ wr.t() + br, lm)
+    (ref * up).sum().backward()
+    hd, wd, bd = [t.to(cuda).requires_grad_(True) for t in (h, w, b)]
+    out = LF.proj_masked_log_softmax(hd, wd, bd, lm.to(cuda))
+    (out * up.to(cuda)).sum().backward()
+    assert float((out.cpu() - ref.detach()).abs().max()) < 1e-4
+    assert _relerr(hd.grad.cpu(), hr.grad) < 1e-4
+    assert _relerr(wd.grad.cpu(), wr.grad) < 1e-4
+    assert _relerr(bd.grad.cpu(), br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("rnn_type", ["GRU", "LSTM", "RNN"])
+@pytest.mark.parametrize("bidirectional", [True, False])
+@pytest.mark.parametrize("B,T,I,H", [(5, 9, 12, 8), (70, 21, 204, 36)])
+def test_rnn_layer_matches_packed_torch(native_lib, cuda, rnn_type, bidirectional, B, T, I, H):
+    from lipreading_b200 import functional as LF
+    g = torch.Generator().manual_seed(99)
+    ref = getattr(torch.nn, rnn_type)(I, H, bidirectional=bidirectional, batch_first=True)
+    weights = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    x = torch.randn(B, T, I, generator=g)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    for b in range(B):
+        x[b, int(lens[b]):] = 0
+    D = 2 if bidirectional else 1
+    up_h = torch.randn(B, T, D * H, generator=g)
+    up_f = torch.randn(D, B, H, generator=g)
+
+    wr = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    xr = x.clone().requires_grad_(True)
+    # differentiable packed reference with these leaves
+    m = getattr(torch.nn, rnn_type)(I, H, bidirectional=bidirectional, batch_first=True)
+    out_r, fin_r = torch.func.functional_call(m, wr, (torch.nn.utils.rnn.pack_padded_sequence(
+        xr, lens, batch_first=True, enforce_sorted=False),))
+    out_r, _ = torch.nn.utils.rnn.pad_packed_sequence(out_r, batch_first=True, total_length=T)
+    hn_r = fin_r[0] if rnn_type == "LSTM" else fin_r
+    loss_r = (out_r * up_h).sum() + (hn_r * up_f).sum()
+    if rnn_type == "LSTM":
+        loss_r = loss_r + (fin_r[1] * up_f.flip(0)).sum()
+    loss_r.backward()
+
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    flat = [weights[n + s].to(cuda).requires_grad_(True) for s in (["", "_reverse"] if bidirectional else [""]) for n in names]
+    xd = x.to(cuda).requires_grad_(True)
+    res = LF.rnn_layer(xd, lens.to(cuda), rnn_type, flat)
+    loss = (res[0] * up_h.to(cuda)).sum() + (res[1] * up_f.to(cuda)).sum()
+    if rnn_type == "LSTM":
+        loss = loss + (res[2] * up_f.flip(0).to(cuda)).sum()
+    loss.backward()
+
+    assert float((res[0].cpu() - out_r.detach()).abs().max()) < 2e-5
+    assert float((res[1].cpu() - hn_r.detach()).abs().max()) < 2e-5
+    if rnn_type == "LSTM":
+        assert float((res[2].cpu() - fin_r[1].detach()).abs().max()) < 2e-5
+    assert _relerr(xd.grad.cpu(), xr.grad) < 1e-4
+    i = 0
+    for s in (["", "_reverse"] if bidirectional else [""]):
+        for n in names:
+            assert _relerr(flat[i].grad.cpu(), wr[n + s].grad) < 1e-4, n + s
+            i += 1
+    # and the masking formulation of the oracle agrees with the packed one
+    om, _ = O.rnn_masked(x, lens, weights, rnn_type, bidirectional)
+    assert float((om - out_r.detach()).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("rnn_type,H,bi", [("GRU", 32, True), ("LSTM", 24, True), ("LSTM", 20, False)])
+def test_video_encoder_forward_matches_oracle(native_lib, cuda, rnn_type, H, bi):
+    from lipreading_b200.model import VideoEncoder
+    c2i = O.build_char2idx()
+    torch.manual_seed(123456)
+    enc = VideoEncoder(204, H, rnn_type=rnn_type, bidirectional=bi, enable_ctc=True,
+                       vocab_size=len(c2i), char2idx=c2i, device=cuda).to(cuda)
+    g = torch.Generator().manual_seed(5)
+    B, T = 6, 17
+    lens = torch.randint(5, T, (B,), generator=g).sort().values          # max < T: exercises trimming
+    frames = torch.randn(B, T, 68, 3, generator=g)
+    for b in range(B):
+        frames[b, int(lens[b]):] = 0
+    state = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    lp_r, h_r, fin_r = O.encoder_forward(state, frames, lens, rnn_type, bi, c2i)
+    lp, h, fin = enc(frames.to(cuda), lens.to(cuda))
+    assert lp.shape == lp_r.shape and h.shape == h_r.shape
+    assert float((lp.cpu() - lp_r).abs().max()) < 1e-4
+    assert float((h.cpu() - h_r).abs().max()) < 1e-4
+    if rnn_type == "LSTM":
+        assert float((fin[0].cpu() - fin_r[0]).abs().max()) < 1e-4 and float((fin[1].cpu() - fin_r[1]).abs().max()) < 1e-4
+    else:
+        assert float((fin.cpu() - fin_r).abs().max()) < 1e-4
+    # state_dict keys are the torch-default ones a reference checkpoint carries
+    assert set(state) == {"rnn." + k for k in getattr(torch.nn, rnn_type)(204, H, bidirectional=bi).state_dict()} | {
+        "output_proj.weight", "output_proj.bias"}
+
+
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_ctc_wrapper_quirk_matches_oracle(native_lib, cuda, reduction):
+    from lipreading_b200.ctc import ctc_loss
+    g = torch.Generator().manual_seed(11)
+    B, T, C = 9, 30, 65
+    fl = torch.tensor([12, 12, 12, 20, 20, 25, 30, 30, 30])
+    lab, ll = _rand_labels(g, B, 6, lo=2)
+    lp = torch.randn(B, T, C, generator=g).log_softmax(-1)
+    lp_r = lp.clone().requires_grad_(True)
+    ref = O.ctc_loss_wrapper(lp_r, lab, fl, ll, reduction)
+    ref.backward()
+    lp_d = lp.to(cuda).requires_grad_(True)
+    got = ctc_loss(lp_d, lab.to(cuda), fl.to(cuda), ll.to(cuda), reduction, cuda)
+    got.backward()
+    assert abs(float(got) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    assert _relerr(lp_d.grad.cpu(), lp_r.grad) < 1e-4
+    # labels too long -> None, like the reference
+    assert ctc_loss(lp_d, torch.zeros(B, 300, dtype=torch.long, device=cuda), fl, torch.full((B,), 300), reduction, cuda) is None
