@@ -128,19 +128,31 @@ int lr_mouth_crop(const uint8_t* frames, const double* lmk, const int32_t* rect_
                   void* stream);
 
 /* -------- N1: spatio-temporal conv front-end on tcgen05 ------------------------------------ */
-/* extension behind VideoEncoder(frame_processing='conv3d'); oracle = torch.nn.Conv3d fp32.
- * See lipreading_b200/csrc/conv3d_sm100.cu for the tile geometry.                             */
+/* extension behind VideoEncoder(frame_processing='conv3d'); oracle = torch.nn.functional.conv3d
+ * fp32 (oracle/conv3d.py).  See lipreading_b200/csrc/conv3d_sm100.cu for the tile geometry.     */
 int lr_conv3d_supported(void);
-/* u8 NDHWC clip (B,T,H,W,3) -> bf16 space-to-depth, zero-padded (B,T+2,H/2+2,W/2+2,16), /255. */
-int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, void* stream);
-/* Stride-1 conv k=(KT,KH,KW) over a zero-padded channels-last bf16 volume
- *   x (B,Tp,Hp,Wp,Cin) with Tp=T+KT-1, Hp=H+KH-1, Wp=W+KW-1, w (Cout,KT,KH,KW,Cin) bf16, bias f32
- * fused bias + ReLU + MaxPool(1,2,2) epilogue; writes the pooled bf16 activation into the
- * interior of a zero-padded volume y (B,T+2*pt,H/2+2*ph,W/2+2*pw,Cout) ready for the next layer
- * and the 2-bit pool argmax (u8, B,T,H/2,W/2,Cout) for backward.                               */
+/* u8 NDHWC clip (B,T,H,W,3) -> /255 -> 2x2 space-to-depth -> zero-padded bf16 volume
+ * (B,T+2,H/2+2,Wp,16), interior at (1,1,1); the caller zero-fills the volume once.             */
+int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, int Wp,
+                void* stream);
+/* Stride-1 "same" conv k=(KT,KH,KW) as a shifted-window implicit GEMM on tcgen05.
+ *   x : zero-padded channel-grouped bf16 volume [CG][B][T+KT-1][H+KH-1][Wp][Cin], Wp a power of
+ *       two >= W+KW-1, Cin in {16,32,64} per group;
+ *   w : bf16 [Cout][CG][KT][KH][KW][Cin]; bias f32 (Cout) or NULL; Cout in {32,64,96,128};
+ *   epi_mode 0: bias + ReLU + MaxPool(1,2,2) -> bf16 written at offset (o_t,o_y,o_x) inside the
+ *               output volume (B,oTp,oHp,oWp,Cout) [the next layer's padded input], plus one
+ *               arg-max byte per pooled element (0..3, 4 = ReLU-dead) into argmax (may be NULL);
+ *   epi_mode 1: plain bf16 store of the valid (t,y,x) positions (used for dgrad).
+ *   J = accumulators (consecutive frames) per CTA work item, 0 = choose.                        */
 int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
-                  int B, int T, int H, int W, int Cin, int Cout, int KT, int KH, int KW,
-                  int out_pt, int out_ph, int out_pw, void* stream);
+                  int B, int T, int H, int W, int Wp, int Cin, int CG, int Cout, int KT, int KH,
+                  int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
+                  int J, void* stream);
+/* Backward of ReLU+MaxPool(1,2,2): d_pooled (B,T,H/2,W/2,C) bf16 + argmax -> gradient w.r.t. the
+ * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
+ * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass.                               */
+int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, int B, int T, int H, int W,
+              int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw, void* stream);
 
 #ifdef __cplusplus
 }

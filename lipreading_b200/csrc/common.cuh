@@ -73,12 +73,12 @@ __device__ __forceinline__ float lr_warp_sum(float v) {
 __device__ __forceinline__ float lr_lse2(float a, float b) {
   float m = fmaxf(a, b);
   if (m == LR_NEG_INF) return LR_NEG_INF;
-  return m + __logf(__expf(a - m) + __expf(b - m));
+  return m + logf(expf(a - m) + expf(b - m));
 }
 __device__ __forceinline__ float lr_lse3(float a, float b, float c) {
   float m = fmaxf(a, fmaxf(b, c));
   if (m == LR_NEG_INF) return LR_NEG_INF;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
 // ---- mbarrier / bulk-async (TMA) primitives ---------------------------------------------
@@ -103,7 +103,8 @@ __device__ __forceinline__ void lr_mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void lr_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = lr_smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  const long long t0 = clock64();
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -112,9 +113,10 @@ __device__ __forceinline__ void lr_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    if (clock64() - t0 > 4000000000LL) break;     // ~2 s at 2 GHz
   }
-  printf("lr_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-         threadIdx.x);
+  printf("lr_b200: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+         blockIdx.y, threadIdx.x, addr, parity);
   __trap();
 }
 // 1-D bulk copy global -> shared (SASS: UBLKCP). 16-byte aligned src/dst/size.

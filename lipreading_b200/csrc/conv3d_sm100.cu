@@ -1,0 +1,558 @@
+// conv3d_sm100.cu — spatio-temporal conv front-end on tcgen05 / TMEM / TMA.
+//
+// North-star extension (the reference has no Conv3d; oracle = torch.nn.functional.conv3d fp32).
+//
+// Formulation: "shifted-window implicit GEMM over the zero-padded channels-last volume".
+//   The activation lives in HBM as a zero-padded NDHWC bf16 volume X[B][Tp][Hp][Wp][Cin] with
+//   Wp a power of two, i.e. a 2-D matrix X2D[rows = B*Tp*Hp*Wp][Cin].  For a stride-1 conv the
+//   A-operand row of output pixel (t,y,x) and tap (kt,ky,kx) is X2D[p(t,y,x) + kt*Hp*Wp + ky*Wp + kx]:
+//   every tap is a pure ROW SHIFT.  So a CTA
+//     1. TMA-loads, once per work item, the KT+J-1 plane "chunks" (128 + halo rows x Cin, hardware
+//        swizzled, K-major) that cover J consecutive output frames of one 128-position tile;
+//     2. streams the per-tap weight tiles [Cout x Cin] through a small TMA ring;
+//     3. issues, per tap, J x Cin/16 tcgen05.mma (M=128, N=Cout, K=16) whose A descriptors simply
+//        start (ky*Wp+kx) rows into the resident chunk — the input is read from L2 once, not once
+//        per tap, and the weights once per J tiles;
+//     4. keeps the J accumulators (128 lanes x Cout fp32 columns each) in TMEM;
+//     5. drains them with tcgen05.ld in a 4-warp epilogue that fuses bias + ReLU + MaxPool(1,2,2)
+//        (+ pool-argmax bytes for backward) and writes the pooled bf16 tile straight into the
+//        interior of the NEXT layer's zero-padded volume.
+//   The tile is 128/Wp full padded rows; positions x >= W and y >= H are junk lanes whose results
+//   are never stored (their windows wrap across rows, which is harmless).
+// The same kernel run on the un-pooled output gradient with flipped/transposed weights is dgrad.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
+// lane), warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxChunks = 16;   // (J + KT - 1) * channel groups
+constexpr int kWStages = 4;
+
+struct ConvParams {
+  int B, T, H, W;              // valid (un-padded) extents, same for input and conv output
+  int Tp, Hp, Wp;              // padded input extents
+  int KT, KH, KW;
+  int Cin;                     // channels per group row: 16, 32 or 64 (32/64/128-byte rows)
+  int CG;                      // channel groups (input stored group-major: CG volumes)
+  int Cout;                    // N, multiple of 32, <= 128
+  int R;                       // tile rows = 128 / Wp
+  int J;                       // accumulators (consecutive frames) per work item
+  int n_ytiles, n_tgroups, n_items;
+  int CH;                      // chunk rows
+  int chunk_bytes;             // 1024-aligned
+  int wtile_bytes;             // 1024-aligned
+  int tmem_cols;
+  int epi_mode;                // 0: bias+ReLU+pool(1,2,2) ; 1: plain store of valid positions
+  int has_bias;
+  int oTp, oHp, oWp, o_t, o_y, o_x;   // output volume geometry / interior offset
+  long long rows_per_group;    // B*Tp*Hp*Wp
+  const float* bias;
+  __nv_bfloat16* y;
+  uint8_t* argmax;
+  uint32_t idesc;
+  uint32_t desc_hi;            // SBO | version | layout type (upper 32 bits of the smem descriptor)
+  int row_bytes;
+  int smem_off_w, smem_off_stage, smem_off_bar;
+  int stage_pitch;             // bytes per staging row
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(lr_smem_u32(dst)), "l"(map), "r"(lr_smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   lr_smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   lr_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t desc_hi) {
+  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);   // start address, LBO = 1 (unused)
+  return ((uint64_t)desc_hi << 32) | lo;
+}
+
+// barrier block layout (uint64 each)
+enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_ACC_FULL, BAR_ACC_EMPTY, BAR_W_FULL, BAR_W_EMPTY = BAR_W_FULL + kWStages,
+       BAR_COUNT = BAR_W_EMPTY + kWStages };
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                      const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_smem = base;
+  uint8_t* w_smem = base + p.smem_off_w;
+  uint8_t* stage = base + p.smem_off_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.smem_off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_taps = p.KT * p.KH * p.KW;
+  const int ksteps = p.Cin / 16;
+
+  if (threadIdx.x == 0) {
+    lr_mbar_init(&bars[BAR_A_FULL], 1);
+    lr_mbar_init(&bars[BAR_A_EMPTY], 1);
+    lr_mbar_init(&bars[BAR_ACC_FULL], 1);
+    lr_mbar_init(&bars[BAR_ACC_EMPTY], 4);
+    for (int s = 0; s < kWStages; ++s) {
+      lr_mbar_init(&bars[BAR_W_FULL + s], 1);
+      lr_mbar_init(&bars[BAR_W_EMPTY + s], 1);
+    }
+    lr_fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t wn = 0;   // global weight-stage counter
+      int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int b = item / (p.n_tgroups * p.n_ytiles);
+        const int rem = item - b * (p.n_tgroups * p.n_ytiles);
+        const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
+        const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
+        const int n_chunks = jn + p.KT - 1;
+        lr_mbar_wait(&bars[BAR_A_EMPTY], (it & 1) ^ 1);
+        lr_mbar_expect_tx(&bars[BAR_A_FULL], (uint32_t)(n_chunks * p.CG * p.CH * p.row_bytes));
+        for (int g = 0; g < p.CG; ++g)
+          for (int c = 0; c < n_chunks; ++c) {
+            long long row0 = (long long)g * p.rows_per_group +
+                             (((long long)b * p.Tp + (t0 + c)) * p.Hp + y0) * p.Wp;
+            tma_load_2d(a_smem + (size_t)(g * (p.J + p.KT - 1) + c) * p.chunk_bytes, &map_x, 0, (int)row0,
+                        &bars[BAR_A_FULL]);
+          }
+        for (int g = 0; g < p.CG; ++g)
+          for (int tap = 0; tap < n_taps; ++tap, ++wn) {
+            const int s = wn % kWStages;
+            lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / kWStages) & 1) ^ 1);
+            lr_mbar_expect_tx(&bars[BAR_W_FULL + s], (uint32_t)(p.Cout * p.row_bytes));
+            tma_load_2d(w_smem + (size_t)s * p.wtile_bytes, &map_w, (g * n_taps + tap) * p.Cin, 0,
+                        &bars[BAR_W_FULL + s]);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t wn = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int rem = item % (p.n_tgroups * p.n_ytiles);
+        const int tg = rem / p.n_ytiles;
+        const int t0 = tg * p.J, jn = min(p.J, p.T - t0);
+        lr_mbar_wait(&bars[BAR_ACC_EMPTY], (it & 1) ^ 1);
+        lr_mbar_wait(&bars[BAR_A_FULL], it & 1);
+        tc_fence_after();
+        bool first = true;
+        for (int g = 0; g < p.CG; ++g) {
+          int tap = 0;
+          for (int kt = 0; kt < p.KT; ++kt)
+            for (int ky = 0; ky < p.KH; ++ky)
+              for (int kx = 0; kx < p.KW; ++kx, ++tap, ++wn) {
+                const int s = wn % kWStages;
+                lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / kWStages) & 1);
+                tc_fence_after();
+                const uint32_t w_addr = lr_smem_u32(w_smem + (size_t)s * p.wtile_bytes);
+                const uint32_t shift = (uint32_t)((ky * p.Wp + kx) * p.row_bytes);
+                for (int j = 0; j < jn; ++j) {
+                  const uint32_t a_addr =
+                      lr_smem_u32(a_smem + (size_t)(g * (p.J + p.KT - 1) + j + kt) * p.chunk_bytes) + shift;
+                  const uint32_t d = tmem_base + (uint32_t)(j * p.Cout);
+                  for (int ks = 0; ks < ksteps; ++ks)
+                    umma_bf16(d, make_desc(a_addr + ks * 32, p.desc_hi), make_desc(w_addr + ks * 32, p.desc_hi),
+                              p.idesc, (first && ks == 0) ? 0u : 1u);
+                }
+                first = false;
+                umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
+              }
+        }
+        umma_commit(&bars[BAR_A_EMPTY]);
+        umma_commit(&bars[BAR_ACC_FULL]);
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int etid = (warp - 2) * 32 + lane;      // 0..127 among epilogue threads
+    const int row = q * 32 + lane;                // accumulator row (tile position) held by this thread
+    const int PW = p.W >> 1;
+    const int cgroups = p.Cout >> 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int b = item / (p.n_tgroups * p.n_ytiles);
+      const int rem = item - b * (p.n_tgroups * p.n_ytiles);
+      const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
+      const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
+      lr_mbar_wait(&bars[BAR_ACC_FULL], it & 1);
+      tc_fence_after();
+      for (int j = 0; j < jn; ++j) {
+        const int t = t0 + j;
+        // TMEM -> registers -> (bias, ReLU) -> bf16 staging tile [128][Cout]
+        for (int cc = 0; cc < p.Cout; cc += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.Cout + cc), v);
+          uint32_t packed[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float f0 = __uint_as_float(v[2 * i]), f1 = __uint_as_float(v[2 * i + 1]);
+            if (p.has_bias) { f0 += p.bias[cc + 2 * i]; f1 += p.bias[cc + 2 * i + 1]; }
+            if (p.epi_mode == 0) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            packed[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(stage + (size_t)row * p.stage_pitch + cc * 2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+        named_bar_sync(1, 128);
+        if (p.epi_mode == 0) {
+          // MaxPool(1,2,2) over the staged tile; 8 channels (16 B) per thread-item
+          const int n_out = (p.R >> 1) * PW * cgroups;
+          for (int idx = etid; idx < n_out; idx += 128) {
+            const int cg = idx % cgroups;
+            const int pp = idx / cgroups;
+            const int px = pp % PW, py = pp / PW;
+            const int gy = (y0 >> 1) + py;
+            if (gy >= (p.H >> 1)) continue;
+            const int r00 = (2 * py) * p.Wp + 2 * px;
+            uint4 q4[4];
+            q4[0] = *reinterpret_cast<const uint4*>(stage + (size_t)r00 * p.stage_pitch + cg * 16);
+            q4[1] = *reinterpret_cast<const uint4*>(stage + (size_t)(r00 + 1) * p.stage_pitch + cg * 16);
+            q4[2] = *reinterpret_cast<const uint4*>(stage + (size_t)(r00 + p.Wp) * p.stage_pitch + cg * 16);
+            q4[3] = *reinterpret_cast<const uint4*>(stage + (size_t)(r00 + p.Wp + 1) * p.stage_pitch + cg * 16);
+            const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q4[0]);
+            const __nv_bfloat16* e1 = reinterpret_cast<const __nv_bfloat16*>(&q4[1]);
+            const __nv_bfloat16* e2 = reinterpret_cast<const __nv_bfloat16*>(&q4[2]);
+            const __nv_bfloat16* e3 = reinterpret_cast<const __nv_bfloat16*>(&q4[3]);
+            __align__(16) __nv_bfloat16 outv[8];
+            __align__(8) uint8_t am[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float m = __bfloat162float(e0[e]);
+              int a = 0;
+              float c1 = __bfloat162float(e1[e]), c2 = __bfloat162float(e2[e]), c3 = __bfloat162float(e3[e]);
+              if (c1 > m) { m = c1; a = 1; }
+              if (c2 > m) { m = c2; a = 2; }
+              if (c3 > m) { m = c3; a = 3; }
+              outv[e] = __float2bfloat16(m);
+              am[e] = (uint8_t)(m > 0.f ? a : 4);
+            }
+            const size_t opix = (((size_t)b * p.oTp + (t + p.o_t)) * p.oHp + (gy + p.o_y)) * p.oWp + (px + p.o_x);
+            *reinterpret_cast<uint4*>(p.y + opix * p.Cout + cg * 8) = *reinterpret_cast<const uint4*>(outv);
+            if (p.argmax) {
+              const size_t apix = (((size_t)b * p.T + t) * (p.H >> 1) + gy) * PW + px;
+              *reinterpret_cast<uint2*>(p.argmax + apix * p.Cout + cg * 8) = *reinterpret_cast<const uint2*>(am);
+            }
+          }
+        } else {
+          const int n_out = 128 * cgroups;
+          for (int idx = etid; idx < n_out; idx += 128) {
+            const int cg = idx % cgroups;
+            const int r = idx / cgroups;
+            const int yl = r / p.Wp, x = r - yl * p.Wp;
+            const int gy = y0 + yl;
+            if (x >= p.W || gy >= p.H) continue;
+            const size_t opix = (((size_t)b * p.oTp + (t + p.o_t)) * p.oHp + (gy + p.o_y)) * p.oWp + (x + p.o_x);
+            *reinterpret_cast<uint4*>(p.y + opix * p.Cout + cg * 8) =
+                *reinterpret_cast<const uint4*>(stage + (size_t)r * p.stage_pitch + cg * 16);
+          }
+        }
+        named_bar_sync(1, 128);     // staging tile is reused by the next accumulator
+      }
+      tc_fence_before();
+      if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---- clip preparation: u8 NDHWC -> /255 -> 2x2 space-to-depth -> zero-padded bf16 volume -------
+// out (B, T+2, H/2+2, Wp, 16): channel = (dy*2+dx)*3 + c for c<3, 12..15 = 0; interior at (1,1,1).
+__global__ void __launch_bounds__(256)
+clip_s2d_kernel(const uint8_t* __restrict__ clip, __nv_bfloat16* __restrict__ out, int B, int T, int H,
+                int W, int Wp) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const long long total = (long long)B * T * H2 * W2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W2);
+    long long r = i / W2;
+    int Y = (int)(r % H2);
+    r /= H2;
+    int t = (int)(r % T);
+    int b = (int)(r / T);
+    const uint8_t* src = clip + ((((size_t)b * T + t) * H + 2 * Y) * W + 2 * X) * 3;
+    __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[(dy * 2 + dx) * 3 + c] = __float2bfloat16((float)src[((size_t)dy * W + dx) * 3 + c] / 255.0f);
+#pragma unroll
+    for (int c = 12; c < 16; ++c) v[c] = __float2bfloat16(0.f);
+    size_t opix = (((size_t)b * (T + 2) + (t + 1)) * (H2 + 2) + (Y + 1)) * Wp + (X + 1);
+    uint4* dst = reinterpret_cast<uint4*>(out + opix * 16);
+    dst[0] = reinterpret_cast<const uint4*>(v)[0];
+    dst[1] = reinterpret_cast<const uint4*>(v)[1];
+  }
+}
+
+// ---- backward helper: route pooled gradients through the stored argmax (ReLU'd max-pool) --------
+// d_pooled (B,T,H/2,W/2,C) bf16 + argmax u8 -> d_conv_out written into the interior of the
+// zero-padded, channel-grouped volume the dgrad/wgrad passes read:
+//   out[g][b][t+pt][y+ph][x+pw][c % Cg], g = c / Cg.  Every interior element is written (0 where it
+// is not the arg-max or the unit was ReLU-dead), borders stay zero from allocation.
+__global__ void __launch_bounds__(256)
+unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restrict__ argmax,
+              __nv_bfloat16* __restrict__ out, int B, int T, int H, int W, int C, int Cg, int Tp, int Hp,
+              int Wp, int pt, int ph, int pw) {
+  const int PH = H >> 1, PW = W >> 1;
+  const int c8 = C >> 3;
+  const long long total = (long long)B * T * H * W * c8;     // one thread per (full-res pixel, 8 ch)
+  const long long rows_per_group = (long long)B * Tp * Hp * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % c8);
+    long long r = i / c8;
+    int x = (int)(r % W); r /= W;
+    int y = (int)(r % H); r /= H;
+    int t = (int)(r % T);
+    int b = (int)(r / T);
+    __align__(16) __nv_bfloat16 v[8];
+    const int py = y >> 1, px = x >> 1;
+    const bool inside = py < PH && px < PW;
+    const int which = (y & 1) * 2 + (x & 1);
+    if (inside) {
+      const size_t pp = ((((size_t)b * T + t) * PH + py) * PW + px) * C + cg * 8;
+      uint4 g = *reinterpret_cast<const uint4*>(d_pooled + pp);
+      uint2 a = *reinterpret_cast<const uint2*>(argmax + pp);
+      const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&g);
+      const uint8_t* ae = reinterpret_cast<const uint8_t*>(&a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (ae[e] == which) ? ge[e] : __float2bfloat16(0.f);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16(0.f);
+    }
+    const int c0 = cg * 8;
+    const int g = c0 / Cg, cl = c0 - g * Cg;
+    const size_t opix = (size_t)g * rows_per_group + (((size_t)b * Tp + (t + pt)) * Hp + (y + ph)) * Wp + (x + pw);
+    *reinterpret_cast<uint4*>(out + opix * Cg + cl) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                uint32_t box_outer, int row_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { lr_set_error("cuTensorMapEncodeTiled entry point not available"); return LR_ECUDA; }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                        : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { lr_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LR_ECUDA; }
+  return LR_OK;
+}
+
+}  // namespace
+
+extern "C" int lr_conv3d_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, int Wp,
+                           void* stream) {
+  LR_CHECK_ARG(clip && out_bf16 && B > 0 && T > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0,
+               "lr_clip_s2d: H and W must be even");
+  LR_CHECK_ARG(Wp >= W / 2 + 2, "lr_clip_s2d: Wp too small");
+  long long total = (long long)B * T * (H / 2) * (W / 2);
+  int grid = lr_div_up(total, 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  clip_s2d_kernel<<<grid, 256, 0, lr_stream(stream)>>>(clip, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, T,
+                                                       H, W, Wp);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, int B, int T, int H, int W,
+                         int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw, void* stream) {
+  LR_CHECK_ARG(d_pooled && argmax && out && C % 8 == 0 && Cg % 8 == 0 && C % Cg == 0, "lr_unpool: bad args");
+  long long total = (long long)B * T * H * W * (C / 8);
+  int grid = lr_div_up(total, 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  unpool_kernel<<<grid, 256, 0, lr_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(d_pooled), argmax,
+                                                     reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, C, Cg,
+                                                     Tp, Hp, Wp, pt, ph, pw);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+// x: zero-padded, channel-grouped bf16 volume [CG][B][Tp][Hp][Wp][Cin] with Tp=T+KT-1, Hp=H+KH-1,
+// Wp = power of two >= W+KW-1.  w: [Cout][CG][KT][KH][KW][Cin] bf16 (K-major per output channel).
+extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
+                             int B, int T, int H, int W, int Wp, int Cin, int CG, int Cout, int KT, int KH,
+                             int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
+                             int J, void* stream) {
+  LR_CHECK_ARG(x && w && y, "lr_conv3d_fwd: null pointer");
+  LR_CHECK_ARG(Cin == 16 || Cin == 32 || Cin == 64, "lr_conv3d_fwd: Cin per group must be 16/32/64 (got %d)", Cin);
+  LR_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 128, "lr_conv3d_fwd: Cout must be 32..128, %%32 (got %d)", Cout);
+  LR_CHECK_ARG(Wp == 8 || Wp == 16 || Wp == 32 || Wp == 64 || Wp == 128, "lr_conv3d_fwd: Wp must be 8..128 pow2");
+  LR_CHECK_ARG(Wp >= W + KW - 1, "lr_conv3d_fwd: Wp < W+KW-1");
+  LR_CHECK_ARG(KT >= 1 && KH >= 1 && KW >= 1 && CG >= 1 && B > 0 && T > 0 && H > 0 && W > 0, "lr_conv3d_fwd: bad shape");
+  LR_CHECK_ARG(epi_mode == 0 || epi_mode == 1, "lr_conv3d_fwd: bad epilogue mode");
+  if (!lr_conv3d_supported()) { lr_set_error("lr_conv3d_fwd needs an sm_100 device"); return LR_EARCH; }
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.T = T; p.H = H; p.W = W;
+  p.Tp = T + KT - 1; p.Hp = H + KH - 1; p.Wp = Wp;
+  p.KT = KT; p.KH = KH; p.KW = KW; p.Cin = Cin; p.CG = CG; p.Cout = Cout;
+  p.R = 128 / Wp;
+  LR_CHECK_ARG(epi_mode == 1 || (p.R % 2 == 0), "lr_conv3d_fwd: pooling needs an even number of tile rows");
+  p.CH = 128 + (KH - 1) * Wp + (KW - 1);
+  LR_CHECK_ARG(p.CH <= 256, "lr_conv3d_fwd: halo too large for one TMA box (CH=%d)", p.CH);
+  p.row_bytes = Cin * 2;
+  p.chunk_bytes = (p.CH * p.row_bytes + 1023) / 1024 * 1024;
+  p.wtile_bytes = (Cout * p.row_bytes + 1023) / 1024 * 1024;
+  p.stage_pitch = Cout * 2 + 16;
+  const int stage_bytes = 128 * p.stage_pitch;
+  const int smem_cap = 227 * 1024 - 1024;     // minus alignment slack
+  int fixed = kWStages * p.wtile_bytes + stage_bytes + 256;
+  // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
+  int Jmax = 512 / Cout;
+  if (J <= 0 || J > Jmax) J = Jmax;
+  while (J > 1 && ((J + KT - 1) * CG > kMaxChunks || (J + KT - 1) * CG * p.chunk_bytes + fixed > smem_cap)) --J;
+  LR_CHECK_ARG((J + KT - 1) * CG * p.chunk_bytes + fixed <= smem_cap && (J + KT - 1) * CG <= kMaxChunks,
+               "lr_conv3d_fwd: tile does not fit shared memory");
+  if (J > T) J = T;
+  p.J = J;
+  p.n_ytiles = lr_div_up(H, p.R);
+  p.n_tgroups = lr_div_up(T, J);
+  p.n_items = B * p.n_ytiles * p.n_tgroups;
+  int cols = 32;
+  while (cols < J * Cout) cols <<= 1;
+  p.tmem_cols = cols;
+  p.epi_mode = epi_mode;
+  p.has_bias = bias != nullptr;
+  p.bias = bias;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.argmax = argmax;
+  p.oTp = oTp; p.oHp = oHp; p.oWp = oWp; p.o_t = o_t; p.o_y = o_y; p.o_x = o_x;
+  p.rows_per_group = (long long)B * p.Tp * p.Hp * p.Wp;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t layout = p.row_bytes == 32 ? 6u : (p.row_bytes == 64 ? 4u : 2u);
+  const uint32_t sbo = (uint32_t)(8 * p.row_bytes) >> 4;
+  p.desc_hi = sbo | (1u << 14) | (layout << 29);
+  p.smem_off_w = (J + KT - 1) * CG * p.chunk_bytes;
+  p.smem_off_stage = p.smem_off_w + kWStages * p.wtile_bytes;
+  p.smem_off_bar = p.smem_off_stage + stage_bytes;
+  const size_t smem_bytes = (size_t)p.smem_off_bar + 256 + 1024;
+
+  CUtensorMap map_x, map_w;
+  int rc = make_map_2d(&map_x, x, (uint64_t)Cin, (uint64_t)p.rows_per_group * CG, (uint32_t)Cin, (uint32_t)p.CH,
+                       p.row_bytes);
+  if (rc != LR_OK) return rc;
+  rc = make_map_2d(&map_w, w, (uint64_t)CG * KT * KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cin, (uint32_t)Cout,
+                   p.row_bytes);
+  if (rc != LR_OK) return rc;
+
+  LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes));
+  int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  conv3d_tcgen05_kernel<<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, map_w, p);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}

@@ -235,16 +235,16 @@ ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __re
     m = lr_warp_max(m);
     float sum = 0.f;
     if (m != LR_NEG_INF)
-      for (int s = 2 * lane; s < S; s += 64) sum += __expf(a[s] + be[s] - m);
+      for (int s = 2 * lane; s < S; s += 64) sum += expf(a[s] + be[s] - m);
     sum = lr_warp_sum(sum);
-    const float lcab0 = (m == LR_NEG_INF) ? LR_NEG_INF : m + __logf(sum);
+    const float lcab0 = (m == LR_NEG_INF) ? LR_NEG_INF : m + logf(sum);
 
-    for (int c = lane; c < C; c += 32) rowbuf[c] = __expf(row[c]);
+    for (int c = lane; c < C; c += 32) rowbuf[c] = expf(row[c]);
     __syncwarp();
     if (lane == 0) {
       float lp0 = row[0];
-      float occ = (lcab0 == LR_NEG_INF) ? 0.f : __expf(lcab0 + nll - lp0);
-      rowbuf[0] = __expf(lp0) - occ;
+      float occ = (lcab0 == LR_NEG_INF) ? 0.f : expf(lcab0 + nll - lp0);
+      rowbuf[0] = expf(lp0) - occ;
     }
     for (int j = lane; j < L; j += 32) {
       if (!head[j]) continue;
@@ -253,8 +253,8 @@ ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __re
       int c = cls[2 * j + 1];
       if (c > 0 && c < C) {
         float lpc = row[c];
-        float occ = (acc == LR_NEG_INF) ? 0.f : __expf(acc + nll - lpc);
-        rowbuf[c] = __expf(lpc) - occ;
+        float occ = (acc == LR_NEG_INF) ? 0.f : expf(acc + nll - lpc);
+        rowbuf[c] = expf(lpc) - occ;
       }
     }
     __syncwarp();

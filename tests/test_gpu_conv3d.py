@@ -1,0 +1,114 @@
+"""-m gpu parity tests of the tcgen05 conv front-end vs the fp32 conv3d oracle (oracle/conv3d.py).
+
+Operands are bf16 on both sides (the oracle rounds where the CUDA path stores bf16), accumulation is
+fp32 on both sides, so the bar is the bf16 output rounding: |err| <= 2^-7 relative to the tensor's
+max (one bf16 ulp at the top of the range) for activations, 2e-2 for gradients that went through
+two bf16 stages."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import conv3d as OC
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _padded(x_ndhwc, pad, Wp):
+    """(B,T,H,W,C) -> zero padded (B,T+2pt,H+2ph,Wp,C) with the interior at (pt,ph,pw)."""
+    B, T, H, W, C = x_ndhwc.shape
+    out = torch.zeros((B, T + 2 * pad[0], H + 2 * pad[1], Wp, C), dtype=x_ndhwc.dtype, device=x_ndhwc.device)
+    out[:, pad[0]:pad[0] + T, pad[1]:pad[1] + H, pad[2]:pad[2] + W] = x_ndhwc
+    return out
+
+
+@pytest.mark.parametrize("Cin,CG,Cout,K,H,W,Wp,T,B", [
+    (32, 1, 64, (3, 5, 5), 25, 12, 16, 7, 2),      # conv2 geometry
+    (64, 1, 96, (3, 3, 3), 12, 6, 8, 6, 3),        # conv3 geometry
+    (16, 1, 32, (3, 3, 3), 50, 25, 32, 5, 1),      # conv1 (space-to-depth) geometry
+    (32, 3, 64, (3, 3, 3), 12, 6, 8, 5, 2),        # grouped input channels (conv3 dgrad geometry)
+    (64, 1, 32, (3, 5, 5), 25, 12, 16, 4, 1),      # conv2 dgrad geometry
+    (32, 1, 32, (1, 1, 1), 8, 8, 8, 3, 1),         # 1x1x1: no shifts at all
+    (32, 1, 32, (1, 1, 3), 8, 6, 8, 3, 1),         # x shifts only
+    (32, 1, 32, (1, 3, 1), 8, 8, 8, 3, 1),         # y shifts only
+])
+def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, T, B):
+    from lipreading_b200.conv_frontend import conv3d_native
+    g = torch.Generator().manual_seed(1234)
+    C = Cin * CG
+    pad = tuple((k - 1) // 2 for k in K)
+    x = torch.randn(B, T, H, W, C, generator=g).to(BF)
+    w = (torch.randn(Cout, C, *K, generator=g) / (C * K[0] * K[1] * K[2]) ** 0.5).to(BF)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float(), None, padding=pad).permute(0, 2, 3, 4, 1)
+    xd = x.to(cuda)
+    # channel-grouped padded volume [CG][B][Tp][Hp][Wp][Cin]
+    vol = torch.stack([_padded(xd[..., gi * Cin:(gi + 1) * Cin], pad, Wp) for gi in range(CG)], 0).contiguous()
+    # weights [Cout][CG][taps][Cin]
+    wk = w.to(cuda).permute(0, 2, 3, 4, 1).reshape(Cout, -1, CG, Cin).permute(0, 2, 1, 3).contiguous()
+    y = torch.full((B, T, H, W, Cout), float("nan"), dtype=BF, device=cuda)
+    conv3d_native(vol, wk, None, y, None, B, T, H, W, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0))
+    torch.cuda.synchronize()
+    err = (y.float().cpu() - ref).abs().max() / ref.abs().max()
+    assert torch.isfinite(y.float()).all()
+    assert float(err) < 2 ** -7, float(err)
+
+
+@pytest.mark.parametrize("J", [0, 1, 2])
+def test_conv3d_relu_pool_epilogue(native_lib, cuda, J):
+    from lipreading_b200.conv_frontend import conv3d_native
+    g = torch.Generator().manual_seed(77)
+    B, T, H, W, Cin, Cout, K, Wp = 2, 5, 25, 12, 32, 64, (3, 5, 5), 16
+    x = torch.randn(B, T, H, W, Cin, generator=g).to(BF)
+    w = (torch.randn(Cout, Cin, *K, generator=g) / (Cin * 75) ** 0.5).to(BF)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    conv = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float(), bias, padding=(1, 2, 2))
+    act = F.relu(conv).to(BF).float()
+    ref, idx = F.max_pool3d(act, (1, 2, 2), return_indices=True)
+    ref = ref.permute(0, 2, 3, 4, 1)                                       # B,T,12,6,C
+    vol = _padded(x.to(cuda), (1, 2, 2), Wp).unsqueeze(0).contiguous()
+    wk = w.to(cuda).permute(0, 2, 3, 4, 1).contiguous()
+    PH, PW = H // 2, W // 2
+    out = torch.zeros((B, T + 2, PH + 2, 8, Cout), dtype=BF, device=cuda)   # next layer's padded volume
+    am = torch.full((B, T, PH, PW, Cout), 255, dtype=torch.uint8, device=cuda)
+    conv3d_native(vol, wk, bias.to(cuda), out, am, B, T, H, W, Wp, Cin, 1, Cout, K, 0, (T + 2, PH + 2, 8), (1, 1, 1), J)
+    torch.cuda.synchronize()
+    got = out[:, 1:1 + T, 1:1 + PH, 1:1 + PW].float().cpu()
+    assert float((got - ref).abs().max() / ref.abs().max()) < 2 ** -7
+    # borders untouched
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, :, 0].abs().max()) == 0 and float(out[:, :, :, 0].abs().max()) == 0
+    assert float(out[:, :, :, 1 + PW:].abs().max()) == 0
+    # arg-max bytes: value at the recorded position equals the pooled max (ties may pick either)
+    am = am.cpu()
+    assert int(am.max()) <= 4
+    a = act.permute(0, 2, 3, 4, 1)                                         # B,T,H,W,C
+    dead = am == 4
+    assert bool(((ref <= 0) == dead).all())
+    yy = (torch.arange(PH) * 2).view(1, 1, PH, 1, 1) + (am.clamp(max=3) // 2)
+    xx = (torch.arange(PW) * 2).view(1, 1, 1, PW, 1) + (am.clamp(max=3) % 2)
+    bb = torch.arange(B).view(B, 1, 1, 1, 1).expand_as(am)
+    tt = torch.arange(T).view(1, T, 1, 1, 1).expand_as(am)
+    cc = torch.arange(Cout).view(1, 1, 1, 1, Cout).expand_as(am)
+    picked = a[bb, tt, yy, xx, cc]
+    assert bool((picked[~dead] == ref[~dead]).all())
+
+
+def test_conv_stack_forward_backward_matches_oracle(native_lib, cuda):
+    from lipreading_b200.conv_frontend import ConvFrontEnd, feature_dim
+    torch.manual_seed(123456)
+    B, T, H, W = 2, 6, 100, 50
+    front = ConvFrontEnd((H, W)).to(cuda)
+    assert front.out_features == feature_dim(H, W) == 1728
+    clip = torch.randint(0, 256, (B, T, H, W, 3), dtype=torch.uint8)
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in front.state_dict().items()}
+    feat_ref, _ = OC.stcnn_forward(clip, params, quantize=True)
+    up = torch.randn(feat_ref.shape)
+    (feat_ref * up).sum().backward()
+    feat = front(clip.to(cuda))
+    (feat * up.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    assert feat.shape == (B, T, 1728)
+    assert float((feat.cpu() - feat_ref.detach()).abs().max() / feat_ref.abs().max()) < 2 ** -6
+    for name, p in front.named_parameters():
+        r = params[name].grad
+        err = float((p.grad.cpu() - r).abs().max() / (r.abs().max() + 1e-12))
+        assert err < 3e-2, (name, err)
