@@ -1,0 +1,170 @@
+"""Dataview -> dataset -> padded batches, with the reference's on-disk formats and semantics
+(src/data/data_loader.py:29-290).
+
+Formats kept: `<datasets>/<name>/<video_id>/{s_e,face_lmk_seq,cap}.npy` in, pickle cache
+`<pickles>/<name>/{sentence,non-sentence}/<split>/{char2idx,frames,captions}.pkl` out.
+`collate_gpu` is the device version of `_collate_fn` (one H2D of the ragged rows + the pad kernel)."""
+import glob
+import json
+import os
+import pickle
+
+import numpy as np
+import torch
+import torch.utils.data as _data
+
+from . import workspace as _ws
+from .vocab import BOS, EOS, MARKERS2ID, UNK, build_char2idx
+
+_log = _ws.getLogger("data_loader")
+
+
+def gen_vid_ids(dataset_name, rand=None):
+    dataset_dir = _ws.getRelDatasetsPath(dataset_name)
+    vid_ids = sorted(glob.glob(os.path.join(dataset_dir, "*/")))
+    assert len(vid_ids) > 0, f"No video ids found: '{dataset_dir}'"
+    (rand if rand is not None else np.random).shuffle(vid_ids)
+    return vid_ids
+
+
+def split_dataset(dataset_name, train_split=0.8, rand=None):
+    """Split by video (data_loader.py:49-62): train | val | test with val = half of the remainder."""
+    vid_ids = gen_vid_ids(dataset_name, rand=rand)
+    n_train = int(train_split * len(vid_ids))
+    n_val = n_train + (len(vid_ids) - n_train) // 2
+    return vid_ids[:n_train], vid_ids[n_train:n_val], vid_ids[n_val:]
+
+
+def filter_occlusions(frames, captions, start_ends, fps=29.97, threshold=0.8):
+    """Keep a caption iff >= threshold of its time window produced landmarks and the frame count
+    exceeds len(caption)+2 (room for BOS/EOS) (data_loader.py:80-91)."""
+    keep_f, keep_c = [], []
+    for f, c, (start, end) in zip(frames, captions, start_ends):
+        if (end - start) * fps * threshold <= len(f) and len(c) + 2 < len(f):
+            keep_f.append(f)
+            keep_c.append(c)
+    return keep_f, keep_c
+
+
+def sort_by_seqlen(frames, captions):
+    """Ascending frame count (np.argsort default kind, like the reference :93-98)."""
+    order = np.argsort([x.shape[0] for x in frames])
+    f = np.empty(len(frames), dtype=object)
+    for i, x in enumerate(frames):
+        f[i] = x
+    return f[order], np.array(captions)[order]
+
+
+def build_vocab(dataset_name, labels):
+    path = os.path.join(_ws.getRelRawPath(dataset_name), labels)
+    try:
+        with open(path) as fh:
+            chars = str("".join(json.load(fh)))
+    except Exception:
+        chars = None
+        _log.warning("Could not open '%s'...\n\tUsing hardcoded labels", path)
+    return build_char2idx(chars)
+
+
+def parse_caption(cap, char2idx):
+    ids = [MARKERS2ID[BOS]] + [char2idx.get(ch, MARKERS2ID[UNK]) for ch in cap] + [MARKERS2ID[EOS]]
+    assert len(ids) > 2
+    return np.array(ids)
+
+
+def _pad(seqs, dtype):
+    lens = torch.LongTensor([len(x) for x in seqs])
+    out = torch.zeros((len(seqs), int(lens.max())) + tuple(np.shape(seqs[0])[1:]), dtype=dtype)
+    for i, s in enumerate(seqs):
+        out[i, : lens[i]] = torch.as_tensor(np.asarray(s)).to(dtype)
+    return out, lens
+
+
+def _collate_fn(batch):
+    """Host collate, same output contract as the reference (:117-152)."""
+    assert all(len(x) == 2 for x in batch)
+    frames, captions = zip(*batch)
+    src, src_lens = _pad(frames, torch.float32)
+    tgt, tgt_lens = _pad(captions, torch.long)
+    return src, src_lens, tgt, tgt_lens
+
+
+def collate_gpu(batch, device):
+    """Same contract, frames padded on the device by lr_collate_pad_f64: the ragged float64 rows go up
+    in one pinned copy and are cast + zero-padded by the kernel."""
+    from . import functional as LF
+    frames, captions = zip(*batch)
+    lens = torch.LongTensor([len(x) for x in frames])
+    feat = int(np.prod(np.shape(frames[0])[1:]))
+    rows = np.concatenate([np.asarray(f, dtype=np.float64).reshape(len(f), feat) for f in frames], 0)
+    src = torch.from_numpy(rows).pin_memory().to(device, non_blocking=True)
+    offs = torch.zeros(len(frames) + 1, dtype=torch.int64)
+    offs[1:] = lens.cumsum(0)
+    out = LF.collate_pad(src, offs.to(device), len(frames), int(lens.max()), feat)
+    tgt, tgt_lens = _pad(captions, torch.long)
+    return out.reshape((len(frames), int(lens.max())) + tuple(np.shape(frames[0])[1:])), lens, tgt, tgt_lens
+
+
+class FrameCaptionDataset(_data.Dataset):
+    """Rows = (landmark sequence (T,68,3), parsed caption ids) (data_loader.py:154-257)."""
+
+    def __init__(self, dataset_name, split_name, vid_ids, labels="labels.json", start_end="s_e",
+                 threshold=0.8, fps=29.97, cap="cap", frame_type="face_lmk_seq", sentence_dataset=False,
+                 in_ext=".npy", out_ext=".pkl", refresh=False):
+        super().__init__()
+        assert all(os.path.isdir(x) for x in vid_ids)
+        assert frame_type in ("face_lmk_seq", "face_vtx_seq")
+        assert not sentence_dataset, "--sentence_dataset needs spaCy (out of scope, SURVEY §2 row 6)"
+        pickle_dir = _ws.getRelPicklesPath(dataset_name, "non-sentence", split_name)
+        if refresh or not os.path.isdir(pickle_dir):
+            self.char2idx, self.frames, self.captions = self.construct_dataset(
+                dataset_name, pickle_dir, vid_ids, labels=labels, start_end=start_end, cap=cap,
+                frame_type=frame_type, in_ext=in_ext, out_ext=out_ext, fps=fps, threshold=threshold)
+        else:
+            self.char2idx, self.frames, self.captions = load_dataset(pickle_dir, out_ext)
+        assert len(self.frames) == len(self.captions) > 0
+        self.idx2char = {v: k for k, v in self.char2idx.items()}
+        self.num_elements = len(self.captions)
+        self.frame_type = frame_type
+
+    def __len__(self):
+        return self.num_elements
+
+    def __getitem__(self, index):
+        frames = self.frames[index]
+        assert len(frames.shape) == 3
+        return frames, parse_caption(self.captions[index], self.char2idx)
+
+    def parse_caption(self, cap):
+        return parse_caption(cap, self.char2idx)
+
+    @staticmethod
+    def construct_dataset(dataset_name, pickle_dir, vid_ids, labels="labels.json", start_end="s_e", cap="cap",
+                          frame_type="face_lmk_seq", in_ext=".npy", out_ext=".pkl", fps=29.97, threshold=0.8):
+        def col(name):
+            paths = [os.path.join(v, name + in_ext) for v in vid_ids]
+            assert all(os.path.isfile(p) for p in paths)
+            return [np.load(p, allow_pickle=True) for p in paths]     # object arrays need allow_pickle
+        frames = [x for arr in col(frame_type) for x in arr]
+        captions = [str(x) for arr in col(cap) for x in arr]
+        start_ends = [x for arr in col(start_end) for x in arr]
+        assert len(frames) == len(captions) == len(start_ends)
+        assert all(len(x.shape) == 3 for x in frames)
+        frames, captions = filter_occlusions(frames, captions, start_ends, fps=fps, threshold=threshold)
+        frames, captions = sort_by_seqlen(frames, captions)
+        char2idx = build_vocab(dataset_name, labels)
+        _ws.mkdirP(pickle_dir)
+        for name, obj in (("char2idx", char2idx), ("frames", frames), ("captions", captions)):
+            with open(os.path.join(pickle_dir, name + out_ext), "wb") as fh:
+                pickle.dump(obj, fh)
+        return char2idx, frames, captions
+
+
+def load_dataset(pickle_dir, out_ext=".pkl"):
+    out = []
+    for name in ("char2idx", "frames", "captions"):
+        path = os.path.join(pickle_dir, name + out_ext)
+        assert os.path.isfile(path), "File not found: '{}'".format(path)
+        with open(path, "rb") as fh:
+            out.append(pickle.load(fh))
+    return tuple(out)

@@ -71,11 +71,10 @@ def rnn_packed(x, lens, weights, rnn_type, bidirectional):
     H = weights["weight_hh_l0"].shape[1]
     I = weights["weight_ih_l0"].shape[1]
     rnn = getattr(torch.nn, rnn_type)(I, H, num_layers=1, bidirectional=bidirectional, batch_first=True)
-    rnn.load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()})
     sorted_lens, perm = lens.sort(0, descending=True)
     _, inv = perm.sort(0)
     packed = torch.nn.utils.rnn.pack_padded_sequence(x.index_select(0, perm), sorted_lens.cpu(), batch_first=True)
-    out, final = rnn(packed)
+    out, final = torch.func.functional_call(rnn, {k: torch.as_tensor(v) for k, v in weights.items()}, (packed,))
     out, _ = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True)
     out = out.index_select(0, inv)
     if isinstance(final, tuple):
@@ -262,7 +261,7 @@ def ctc_loss_wrapper(log_probs, labels, frame_lens, label_lens, reduction, per_s
         else:
             total = total + nll.sum()
         prev = cut
-    if isinstance(total, int) or float(total) == 0:
+    if isinstance(total, int) or float(total.detach()) == 0:
         return None
     return total / count if reduction == "mean" else total
 

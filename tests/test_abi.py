@@ -1,0 +1,51 @@
+"""CPU tests of the C-ABI boundary: the library builds for sm_100a, loads without a GPU, and
+exports exactly the symbols include/lr_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "lr_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(lr_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported_and_bound(native_lib):
+    from lipreading_b200 import native
+    import lipreading_b200.conv_frontend  # noqa: F401  (registers the conv entry points)
+    names = _declared()
+    assert len(names) >= 20
+    raw = ctypes.CDLL(native.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), "declared in lr_b200.h but not exported: " + n
+        assert n in native.SIGNATURES, "exported but not bound in native.py: " + n
+    assert native_lib.lr_abi_version() == 1
+    assert native_lib.lr_last_error() is not None
+
+
+def test_workspace_queries_need_no_gpu(native_lib):
+    assert native_lib.lr_ctc_workspace(256, 75, 65, 30) == 16            # lattices fit shared memory
+    assert native_lib.lr_ctc_workspace(4, 400, 65, 256) == 4 * 2 * 400 * 513 * 4
+    assert native_lib.lr_rnn_workspace(1, 256, 75, 256, 2) == 3 * 2 * 256 * 256 * 4
+    assert [native_lib.lr_rnn_saved_per_unit(m) for m in (0, 1, 2)] == [0, 4, 5]
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    from lipreading_b200 import functional as LF, native
+    with pytest.raises(native.NativeError):
+        LF.ctc_nll(torch.zeros(1, 4, 5).log_softmax(-1), torch.ones(1, 2, dtype=torch.int32),
+                   torch.tensor([4]), torch.tensor([2]))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lipreading_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

@@ -54,9 +54,9 @@ def test_ctc_nll_and_grad(native_lib, cuda, B, T, C, Lmax):
     assert torch.allclose(nll.cpu(), nll32, atol=1e-3, rtol=1e-5)
     # independent restatement (published recursion, float64) on sample 0
     n0, g0 = O.ctc_alpha_beta(lp[0, : int(il[0])].numpy(), tgt[0, : int(tl[0])].numpy())
-    assert abs(float(nll[0]) - n0) < 1e-4 * max(1.0, abs(n0))
+    assert abs(float(nll[0].detach()) - n0) < 1e-4 * max(1.0, abs(n0))
     got = (lp_d.grad[0, : int(il[0])].cpu() / w[0]).numpy()
-    assert np.abs(got - g0).max() < 1e-4
+    assert np.abs(got - g0).max() < (1e-4 if T <= 100 else 3e-4)
 
 
 def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda):
