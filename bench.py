@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the north-star training step on synthetic clips.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port) on host cores
+
+One "step" = one CTC-only training step of the hot path on one batch of synthetic video:
+    u8 clips (B,75,100,50,3) -> STCNN conv front-end (tcgen05) -> BiGRU-256 -> Linear+masked
+    log-softmax -> CTC loss -> backward -> [NCCL grad all-reduce] -> clip 50 -> Adam
+with B = 256 clips per GPU (BASELINE.json configs[2]/[3]; weak scaling: per-GPU batch fixed).
+`value` = frames/s with the batch resident in HBM; `e2e` = the same step through the public API
+(`lipreading_b200.trainer.train_ctc`) fed from pinned host memory (H2D of every batch inside the
+timed region, loss read back every step).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES, H_FRAME, W_FRAME = 75, 100, 50
+SEED = 123456
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--rnn", default="GRU")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="clips per step of the CPU baseline sample")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel micro rooflines")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def synth_batch(B, seed, char2idx, L_lo=10, L_hi=30):
+    """Seeded synthetic batch of the dataview/clip shape: u8 clips + BOS/EOS-wrapped labels."""
+    g = torch.Generator().manual_seed(seed)
+    clips = torch.randint(0, 256, (B, T_FRAMES, H_FRAME, W_FRAME, 3), dtype=torch.uint8, generator=g)
+    lens = torch.full((B,), T_FRAMES, dtype=torch.long)
+    L = torch.randint(L_lo, L_hi + 1, (B,), generator=g)
+    chars = torch.zeros(B, int(L.max()) + 2, dtype=torch.long)
+    for b in range(B):
+        n = int(L[b])
+        chars[b, 0] = char2idx["<BOS>"]
+        chars[b, 1:1 + n] = torch.randint(4, 64, (n,), generator=g)
+        chars[b, 1 + n] = char2idx["<EOS>"]
+    return clips, lens, chars, L + 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path: the oracle port of the same step (torch CPU fp32: conv3d -> nn.GRU packed -> CTC)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(hidden, rnn, char2idx):
+    from oracle import conv3d as OC
+    from oracle import sequence as O
+    torch.manual_seed(SEED)
+    convs = torch.nn.ModuleDict({"conv1": torch.nn.Conv3d(3, 32, (3, 5, 5), (1, 2, 2), (1, 2, 2)),
+                                 "conv2": torch.nn.Conv3d(32, 64, (3, 5, 5), 1, (1, 2, 2)),
+                                 "conv3": torch.nn.Conv3d(64, 96, (3, 3, 3), 1, (1, 1, 1))})
+    rnn_m = getattr(torch.nn, rnn)(1728, hidden, bidirectional=True, batch_first=True)
+    proj = torch.nn.Linear(2 * hidden, len(char2idx) + 1)
+    params = list(convs.parameters()) + list(rnn_m.parameters()) + list(proj.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4)
+    log_mask = O.log_mask_vector(len(char2idx), char2idx)
+
+    def step(batch):
+        clips, lens, chars, char_lens = batch
+        cp = {k + "." + n: p for k, m in convs.items() for n, p in m.named_parameters()}
+        feat, _ = OC.stcnn_forward(clips, cp, quantize=False)
+        weights = dict(rnn_m.named_parameters())
+        hidden_states, _ = O.rnn_packed(feat, lens, weights, rnn, True)
+        lp = O.masked_log_softmax(proj(hidden_states), log_mask)
+        loss = O.ctc_loss_wrapper(lp, chars[:, 1:], lens, char_lens - 1, "mean")
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 50)
+        opt.step()
+        return float(loss)
+    return step
+
+
+def run_cpu(args, char2idx, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn(args.hidden, args.rnn, char2idx)
+    batch = synth_batch(args.cpu_batch, SEED, char2idx)
+    for _ in range(warmup):
+        step(batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(batch)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return args.cpu_batch * T_FRAMES / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel micro rooflines (rank 0, N=1 only): the HBM-bound kernels of the path
+# ------------------------------------------------------------------------------------------------
+def time_cuda(fn, iters=20, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        if flush is not None:
+            flush.zero_()                       # write a buffer larger than L2 between iterations
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2] * 1e-3
+
+
+def kernel_rooflines(dev, pk, char2idx):
+    import numpy as np
+    from lipreading_b200 import functional as LF
+    out = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm = pk["hbm_gbs"] * 1e9
+    g = torch.Generator().manual_seed(SEED)
+    # CTC alpha/beta + grad: 2*T*C*4 B per clip (39 000 B at T=75, C=65)
+    B, T, C = 4096, 75, 65
+    lp = torch.randn(B, T, C, generator=g).log_softmax(-1).to(dev).requires_grad_(True)
+    tg = torch.randint(5, 65, (B, 30), generator=g).to(dev).int()
+    il = torch.full((B,), T, dtype=torch.int32, device=dev)
+    tl = torch.randint(10, 31, (B,), generator=g).to(dev).int()
+    s = time_cuda(lambda: LF.ctc_nll(lp, tg, il, tl), flush=flush)
+    out.append({"kernel": "ctc_alpha_beta_grad", "bound": "hbm", "unit": "GB/s", "achieved": B * 2 * T * C * 4 / s / 1e9,
+                "frac": B * 2 * T * C * 4 / s / hbm, "shape": "B=4096,T=75,C=65,L<=30", "ms": s * 1e3})
+    # proj + masked log-softmax fwd: reads M*K*4, writes M*C*4
+    M, K = 256 * 75, 512
+    h = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(C, K, generator=g) / 22).to(dev)
+    b = torch.zeros(C, device=dev)
+    mask = torch.ones(C)
+    mask[1] = mask[2] = 0                       # PAD+1, BOS+1 (better_model.py:43-45)
+    lm = (mask + 1e-45).log().to(dev)
+    s = time_cuda(lambda: LF.proj_masked_log_softmax(h, w, b, lm), flush=flush)
+    byts = M * (K + C) * 4
+    out.append({"kernel": "proj_logsoftmax_fwd", "bound": "hbm", "unit": "GB/s", "achieved": byts / s / 1e9,
+                "frac": byts / s / hbm, "shape": "M=19200,K=512,C=65", "ms": s * 1e3})
+    # warp256: reads size^2*3 u8 window, writes 256*256*3 f32
+    n, H, W = 64, 720, 1280
+    frames = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, generator=g).to(dev)
+    rects = torch.tensor([[400, 700, 150, 450]] * n, dtype=torch.int32, device=dev)
+    rp, crop = LF.rect_geometry(rects, H, W)
+    s = time_cuda(lambda: LF.warp256(frames, crop), flush=flush)
+    size = int(crop[0, 2])
+    byts = n * (size * size * 3 + 256 * 256 * 3 * 4)
+    out.append({"kernel": "warp256", "bound": "hbm", "unit": "GB/s", "achieved": byts / s / 1e9, "frac": byts / s / hbm,
+                "shape": "n=64,720p,size=%d" % size, "ms": s * 1e3})
+    # posmap gather with vertices: reads 43867*12 B (+68*12), writes (43867+68)*24 B per frame
+    gold = os.path.join(ROOT, "tests", "golden")
+    uv = np.loadtxt(os.path.join(gold, "uv_kpt_ind.txt")).astype(np.int64)
+    kidx = torch.from_numpy((uv[1] * 256 + uv[0]).astype(np.int32)).to(dev)
+    fidx = torch.from_numpy(np.load(os.path.join(gold, "face_ind.npy"))).to(dev)
+    pos = (torch.rand(n, 256, 256, 3, generator=g) * 281.6).to(dev)
+    s = time_cuda(lambda: LF.posmap_gather(pos, crop, rp, kidx, fidx), flush=flush)
+    byts = n * (43867 + 68) * (12 + 24)
+    out.append({"kernel": "posmap_gather(lmk+vtx)", "bound": "hbm", "unit": "GB/s", "achieved": byts / s / 1e9,
+                "frac": byts / s / hbm, "shape": "n=64", "ms": s * 1e3})
+    # recurrent layer fwd (BiGRU-256, B=256, T=75): latency-bound; report FLOP/s of the recurrent GEMMs
+    from lipreading_b200.model import NativeRNN
+    rnn = NativeRNN("GRU", 1728, 256, bidirectional=True).to(dev)
+    x = torch.randn(256, 75, 1728, generator=g).to(dev)
+    lens = torch.full((256,), 75, dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        s = time_cuda(lambda: rnn(x, lens), iters=5)
+    fl = 2 * 75 * 256 * 2 * 3 * 256 * (1728 + 256)
+    out.append({"kernel": "bigru256_fwd(layer incl. input GEMM)", "bound": "tensor", "unit": "TFLOP/s",
+                "achieved": fl / s / 1e12, "frac": fl / s / 1e12 / pk["bf16_tflops"], "shape": "B=256,T=75,I=1728,H=256 fp32",
+                "ms": s * 1e3, "us_per_step": s / 75 * 1e6})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    from lipreading_b200.vocab import build_char2idx
+    char2idx = build_char2idx()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    cfg = {"workload": "stcnn+bi%s%d+ctc train step, synthetic u8 clips (B,75,100,50,3), B=%d clips/GPU, L in [10,30]"
+                       % (args.rnn.lower(), args.hidden, args.batch),
+           "clips_per_gpu": args.batch, "clip_shape": [T_FRAMES, H_FRAME, W_FRAME, 3], "optimizer": "adam lr=1e-4, clip 50",
+           "parallelism": "dp%d" % world, "l2": "inputs larger than L2 (288 MB u8 clips per step)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, dt = run_cpu(args, char2idx, args.steps, args.warmup)
+        cores = os.cpu_count() or 1
+        line = {"impl": "reference", "metric": "frames/sec end-to-end (3Dconv+BiGRU+CTC train step)", "value": value,
+                "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": "%d clips/step (same shapes), %d steps" % (args.cpu_batch, args.steps)},
+                "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    from lipreading_b200 import conv_frontend, dist as ldist, native, trainer
+    from lipreading_b200.model import VideoEncoder
+    rank, local_rank, world = ldist.init()
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    native.lib()
+    pk = peaks()
+    torch.manual_seed(SEED)
+    enc = VideoEncoder(1728, args.hidden, frame_processing="conv3d", rnn_type=args.rnn, bidirectional=True,
+                       enable_ctc=True, vocab_size=len(char2idx), char2idx=char2idx, device=dev).to(dev)
+    opt = torch.optim.Adam(enc.parameters(), lr=1e-4)
+    reducer = ldist.GradAllReducer(world) if world > 1 else None
+    host = [synth_batch(args.batch, SEED + 17 * rank + i, char2idx) for i in range(2)]
+    host = [tuple(t.pin_memory() for t in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def run(loader_fn, steps, on_step=None):
+        trainer.train_ctc(enc, loader_fn(steps), opt, dev, char2idx, grad_norm=50, dist=reducer, on_step=on_step)
+
+    def resident_loader(n):
+        return [resident[i % 2] for i in range(n)]
+
+    # ---- device-resident timing ------------------------------------------------------------
+    run(resident_loader, args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    conv_frontend.KERNEL_TIMING = []
+    n0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run(resident_loader, args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = native.launch_count() - n0
+    ktimes = conv_frontend.KERNEL_TIMING
+    conv_frontend.KERNEL_TIMING = None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t)
+    value = world * args.batch * T_FRAMES * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host batches, H2D inside the timed region, loss read back each step ----
+    from lipreading_b200.data import DevicePrefetcher
+    def host_loader(n):
+        return DevicePrefetcher([host[i % 2] for i in range(n)], dev)
+    losses = []
+    run(host_loader, 2)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    run(host_loader, args.steps, on_step=lambda l: losses.append(l.item()))
+    t1.record()
+    barrier()
+    te = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * args.batch * T_FRAMES * args.steps / (float(te) * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (conv3d_tcgen05_kernel) -----------------------------
+    torch.cuda.synchronize()
+    per = {}
+    for tag, a, b, fl in ktimes:
+        d = per.setdefault(tag, [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b) * 1e-3
+        d[1] += fl
+        d[2] += 1
+    tot_s = sum(v[0] for v in per.values())
+    tot_f = sum(v[1] for v in per.values())
+    peak = pk["bf16_tflops_sustained"]
+    roofline = {"kernel": "conv3d_tcgen05_kernel (5 launches/step: conv1-3 fwd, conv3/conv2 dgrad)",
+                "bound": "tensor", "achieved": tot_f / tot_s / 1e12 if tot_s else None, "peak": peak,
+                "unit": "TFLOP/s", "frac": (tot_f / tot_s / 1e12 / peak) if tot_s else None, "traffic": None,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "share_of_step": tot_s / (ms * 1e-3),
+                "per_launch": {k: {"ms": v[0] / v[2] * 1e3, "tflops": v[1] / v[0] / 1e12} for k, v in per.items()}}
+    line = {"metric": "frames/sec end-to-end (3Dconv+BiGRU+CTC train step)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": cfg, "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "final_loss": losses[-1] if losses else None},
+            "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = run_cpu(args, char2idx, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "%d clips/step (same shapes), 1 warm-up + 2 timed steps" % args.cpu_batch}
+    if world == 1 and not args.no_kernels:
+        try:
+            line["kernels"] = kernel_rooflines(dev, pk, char2idx)
+        except Exception as e:           # micro-benches must never lose the headline
+            line["kernels_error"] = repr(e)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

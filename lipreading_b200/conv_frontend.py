@@ -45,11 +45,25 @@ def feature_dim(H, W):
     return 96 * h * w
 
 
-def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0):
+# bench.py sets this to a list to get per-launch CUDA-event timings of the conv kernel:
+# entries are (tag, start_event, end_event, algorithmic_flops)
+KERNEL_TIMING = None
+
+
+def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
+                  tag="conv", algo_macs=None):
     """Thin call into lr_conv3d_fwd (see include/lr_b200.h)."""
+    rec = KERNEL_TIMING
+    if rec is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Wp,
                                   Cin, CG, Cout, K[0], K[1], K[2], epi_mode, ovol[0], ovol[1], ovol[2],
                                   ooff[0], ooff[1], ooff[2], J, N.stream()), "lr_conv3d_fwd")
+    if rec is not None:
+        e1.record()
+        macs = algo_macs if algo_macs is not None else B * T * H * W * Cout * Cin * CG * K[0] * K[1] * K[2]
+        rec.append((tag, e0, e1, 2.0 * macs))
 
 
 def s2d_weight(w1):
@@ -112,11 +126,12 @@ class _ConvStack(torch.autograd.Function):
         g2 = gemm_weight(w2.detach()).to(bf)
         g3 = gemm_weight(w3.detach()).to(bf)
         conv3d_native(z, g1, b1.detach().float(), a1, am1, B, T, H1, W1, Wp1, 16, 1, 32, (3, 3, 3), 0,
-                      (T + 2, H2 + 4, Wp2), (1, 2, 2))
+                      (T + 2, H2 + 4, Wp2), (1, 2, 2), tag="conv1.fwd",
+                      algo_macs=B * T * H1 * W1 * 32 * 3 * 75)       # the true 3x5x5x3 stride-2 conv
         conv3d_native(a1, g2, b2.detach().float(), a2, am2, B, T, H2, W2, Wp2, 32, 1, 64, (3, 5, 5), 0,
-                      (T + 2, H3 + 2, Wp3), (1, 1, 1))
+                      (T + 2, H3 + 2, Wp3), (1, 1, 1), tag="conv2.fwd")
         conv3d_native(a2, g3, b3.detach().float(), feat, am3, B, T, H3, W3, Wp3, 64, 1, 96, (3, 3, 3), 0,
-                      (T, H4, W4), (0, 0, 0))
+                      (T, H4, W4), (0, 0, 0), tag="conv3.fwd")
         ctx.save_for_backward(z, a1, a2, am1, am2, am3, w1, w2, w3)
         ctx.geom = (B, T, H, W)
         return feat.reshape(B, T, H4 * W4 * 96).float()
@@ -158,7 +173,7 @@ class _ConvStack(torch.autograd.Function):
         db3 = dy3_n.float().sum((0, 2, 3, 4))
         da2 = torch.empty((B, T, H3, W3, 64), dtype=bf, device=dev)
         conv3d_native(dy3, dgrad_weight(w3.detach(), 32).to(bf), None, da2, None, B, T, H3, W3, Wp3, 32, 3, 64,
-                      (3, 3, 3), 1, (T, H3, W3), (0, 0, 0))
+                      (3, 3, 3), 1, (T, H3, W3), (0, 0, 0), tag="conv3.dgrad")
         # ---- layer 2 ----
         dy2 = unpool(da2, am2, H2, W2, 64, 64, (1, 2, 2), Wp2)                   # (1,B,T+2,H2+4,Wp2,64)
         dy2_n = interior(dy2, (1, 2, 2), H2, W2)
@@ -166,7 +181,7 @@ class _ConvStack(torch.autograd.Function):
         db2 = dy2_n.float().sum((0, 2, 3, 4))
         da1 = torch.empty((B, T, H2, W2, 32), dtype=bf, device=dev)
         conv3d_native(dy2, dgrad_weight(w2.detach(), 64).to(bf), None, da1, None, B, T, H2, W2, Wp2, 64, 1, 32,
-                      (3, 5, 5), 1, (T, H2, W2), (0, 0, 0))
+                      (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad")
         # ---- layer 1 (no input gradient: the clip is data) ----
         dy1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), W1)                    # (1,B,T,H1,W1,32)
         dy1_n = interior(dy1, (0, 0, 0), H1, W1)

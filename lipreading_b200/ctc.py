@@ -44,36 +44,45 @@ def ctc_loss(encoder_outputs, labels, frame_lens, label_lens, reduction, device,
     nll = LF.ctc_nll(encoder_outputs, targets, fl_h.to(dev, torch.int32, non_blocking=True),
                      ll_h.to(dev, torch.int32, non_blocking=True))
 
-    finite_h = torch.isfinite(nll.detach()).cpu()               # the reference's torch.isinf(loss) probes
-    cuts = ((fl_h[1:] - fl_h[:-1]).nonzero().squeeze(-1) + 1).tolist() + [n]
-    coef = torch.zeros(n, dtype=torch.float32)
-    count, prev, prev_slice_len, any_term = 0, 0, n, False
-    for cut in cuts:
-        weight = prev_slice_len                                  # quirk: len() of the previous slice
-        idx = torch.arange(prev, cut)
-        prev_slice_len = cut - prev
-        ok = finite_h[prev:cut]
-        if not bool(ok.all()):
-            print("inf CTC loss occurred...")
-            idx = idx[ok]
-            if idx.numel() == 0:
-                print("skipping the entire minibatch")
-                continue                                         # prev_change_point not advanced (:91-93)
-            weight = prev_slice_len = int(idx.numel())
+    def reduce(finite_h):
+        """Host-side run bookkeeping -> per-sample coefficients (needs no device data when every
+        sample is feasible)."""
+        cuts = ((fl_h[1:] - fl_h[:-1]).nonzero().squeeze(-1) + 1).tolist() + [n]
+        coef = torch.zeros(n, dtype=torch.float32)
+        count, prev, prev_slice_len, any_term = 0, 0, n, False
+        for cut in cuts:
+            weight = prev_slice_len                              # quirk: len() of the previous slice
+            idx = torch.arange(prev, cut)
+            prev_slice_len = cut - prev
+            if finite_h is not None and not bool(finite_h[prev:cut].all()):
+                print("inf CTC loss occurred...")
+                idx = idx[finite_h[prev:cut]]
+                if idx.numel() == 0:
+                    print("skipping the entire minibatch")
+                    continue                                     # prev_change_point not advanced (:91-93)
+                weight = prev_slice_len = int(idx.numel())
+            if reduction == "mean":
+                coef[idx] += weight / (idx.numel() * ll_h[idx].clamp(min=1).float())
+                count += weight
+            else:
+                coef[idx] += 1.0
+            any_term = True
+            prev = cut
+        if not any_term:
+            return None
         if reduction == "mean":
-            coef[idx] += weight / (idx.numel() * ll_h[idx].clamp(min=1).float())
-            count += weight
-        else:
-            coef[idx] += 1.0
-        any_term = True
-        prev = cut
-    if not any_term:
-        return None
-    if reduction == "mean":
-        coef /= count
-    coef_d = coef.to(dev, non_blocking=True)
-    # infeasible samples carry coefficient 0; mask their +inf so 0*inf never appears
-    total = (torch.where(coef_d > 0, nll, torch.zeros_like(nll)) * coef_d).sum()
-    if float(total.detach()) == 0:                               # ctc_loss.py:110-112
+            coef /= count
+        coef_d = coef.to(dev, non_blocking=True)
+        # infeasible samples carry coefficient 0; mask their +inf so 0*inf never appears
+        return (torch.where(coef_d > 0, nll, torch.zeros_like(nll)) * coef_d).sum()
+
+    # fast path: assume every sample is feasible, verify with ONE small device->host read (the
+    # reference's torch.isinf(loss) / total_loss == 0 probes, ctc_loss.py:87,110)
+    total = reduce(None)
+    flags = torch.stack([torch.isfinite(nll.detach()).all(), total.detach() != 0]).cpu()
+    if bool(flags[0]):
+        return total if bool(flags[1]) else None
+    total = reduce(torch.isfinite(nll.detach()).cpu())
+    if total is None or float(total.detach()) == 0:
         return None
     return total

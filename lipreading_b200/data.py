@@ -168,3 +168,41 @@ def load_dataset(pickle_dir, out_ext=".pkl"):
         with open(path, "rb") as fh:
             out.append(pickle.load(fh))
     return tuple(out)
+
+
+class DevicePrefetcher:
+    """Iterate a loader of HOST batches one step ahead: the (large) frames tensor of batch i+1 is
+    copied host->device on a side stream while batch i computes.  Lengths and captions stay on the
+    host (the trainer wants them there).  Use pinned host tensors for truly asynchronous copies."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        side = torch.cuda.Stream(self.device)
+
+        def stage(batch):
+            with torch.cuda.stream(side):
+                frames = batch[0].to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return frames, ev, batch[1:]
+
+        it = iter(self.loader)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            frames, ev, rest = nxt
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            frames.record_stream(cur)
+            yield (frames,) + tuple(rest)

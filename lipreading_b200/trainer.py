@@ -124,3 +124,40 @@ def eval(encoder, decoding_step, data_loader, device, char2idx):
     encoder._t_max_hint = None
     count_t = torch.tensor(float(count), device=device)
     return decoder_loss / count_t, correct, count_t
+
+
+def train_ctc(encoder, data_loader, opt, device, char2idx=None, grad_norm=None, dist=None, on_step=None):
+    """CTC-only epoch: encoder -> CTC 'mean' -> backward -> [all-reduce] -> clip -> step.  This is the
+    loop shape of the reference's archived `train_model.py` (src/scripts/archive/train_model.py:
+    model -> CTCLoss -> backward -> clip -> optimizer.step) on top of the live VideoEncoder, i.e. the
+    north-star hot path without the attention decoder.  Returns the average CTC loss.
+    `data_loader` yields (frames|clips, frame_lens, chars, char_lens) with tensors on the host or the
+    device; BOS-prefixed / EOS-terminated chars as everywhere else."""
+    assert encoder.enable_ctc
+    encoder.train()
+    total = torch.zeros((), device=device)
+    n = 0
+    for frames, frame_lens, chars, char_lens in data_loader:
+        fl_h, cl_h = frame_lens.cpu(), char_lens.cpu()
+        ll_h = cl_h - 1
+        frames = frames.to(device, non_blocking=True)
+        labels = chars.to(device, non_blocking=True)[:, 1:]
+        fl_d = fl_h.to(device, non_blocking=True)
+        encoder._t_max_hint = int(fl_h.max())
+        log_probs, _, _ = encoder(frames, fl_d)
+        loss = ctc_loss(log_probs, labels, fl_d, ll_h, "mean", device, host_lens=(fl_h, ll_h))
+        if loss is None:
+            continue
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if dist is not None:
+            dist.allreduce_grads(list(encoder.parameters()))
+        if grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(encoder.parameters(), grad_norm)
+        opt.step()
+        total += loss.detach()
+        n += 1
+        if on_step is not None:
+            on_step(loss)
+    encoder._t_max_hint = None
+    return float(total) / max(n, 1)

@@ -1,0 +1,1 @@
+"""Import-path alias of the reference layout; the implementation lives in lipreading_b200/."""
