@@ -132,12 +132,12 @@ int lr_mouth_crop(const uint8_t* frames, const double* lmk, const int32_t* rect_
  * fp32 (oracle/conv3d.py).  See lipreading_b200/csrc/conv3d_sm100.cu for the tile geometry.     */
 int lr_conv3d_supported(void);
 /* u8 NDHWC clip (B,T,H,W,3) -> /255 -> 2x2 space-to-depth -> zero-padded bf16 volume
- * (B,T+2,H/2+2,Wp,16), interior at (1,1,1); the caller zero-fills the volume once.             */
-int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, int Wp,
+ * (B,T+2,Hp,Wp,16), Hp >= H/2+2, interior at (1,1,1); the caller zero-fills the volume once.             */
+int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, int Hp, int Wp,
                 void* stream);
 /* Stride-1 "same" conv k=(KT,KH,KW) as a shifted-window implicit GEMM on tcgen05.
- *   x : zero-padded channel-grouped bf16 volume [CG][B][T+KT-1][H+KH-1][Wp][Cin], Wp a power of
- *       two >= W+KW-1, Cin in {16,32,64} per group;
+ *   x : zero-padded channel-grouped bf16 volume [CG][B][T+KT-1][Hp][Wp][Cin], Hp >= H+KH-1 (a
+ *       multiple of 128/Wp), Wp a power of two >= W+KW-1, Cin in {16,32,64} per group;
  *   w : bf16 [Cout][CG][KT][KH][KW][Cin]; bias f32 (Cout) or NULL; Cout in {32,64,96,128};
  *   epi_mode 0: bias + ReLU + MaxPool(1,2,2) -> bf16 written at offset (o_t,o_y,o_x) inside the
  *               output volume (B,oTp,oHp,oWp,Cout) [the next layer's padded input], plus one
@@ -145,12 +145,21 @@ int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W,
  *   epi_mode 1: plain bf16 store of the valid (t,y,x) positions (used for dgrad).
  *   J = accumulators (consecutive frames) per CTA work item, 0 = choose.                        */
 int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
-                  int B, int T, int H, int W, int Wp, int Cin, int CG, int Cout, int KT, int KH,
-                  int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
-                  int J, void* stream);
+                  int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
+                  int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y,
+                  int o_x, int J, void* stream);
 /* Backward of ReLU+MaxPool(1,2,2): d_pooled (B,T,H/2,W/2,C) bf16 + argmax -> gradient w.r.t. the
  * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
  * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass.                               */
+/* Weight gradient: out[tap][64][Nc] fp32 = sum_p dy[p,:] (x) x[p+shift(tap),:] on tcgen05 (M=64,
+ * MN-major operands), split over CTAs and reduced in a fixed order.  x [B][T+KT-1][Hp][Wp][Cx];
+ * dy [Gy][B][T+KT-1][Hp][Wp][Cy] zero except its interior, which starts dy_off rows in.
+ * m_is_x = 0: rows of out[tap] are output channels (needs Gy*Cy <= 64), columns the Cx inputs;
+ * m_is_x = 1: rows are the Cx = 64 inputs, columns the Gy*Cy outputs.                          */
+size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits);
+int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, size_t ws_bytes,
+                    int B, int T, int H, int W, int Hp, int Wp, int Cx, int Cy, int Gy,
+                    long long dy_off, int KT, int KH, int KW, int m_is_x, int splits, void* stream);
 int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, int B, int T, int H, int W,
               int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw, void* stream);
 

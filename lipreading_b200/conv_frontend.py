@@ -20,9 +20,11 @@ from . import native as N
 from .native import _i, _vp
 
 N.register("lr_conv3d_supported", _i, [])
-N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _vp])
+N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 N.register("lr_unpool", _i, [_vp, _vp, _vp] + [_i] * 12 + [_vp])
-N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 19 + [_vp])
+N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 20 + [_vp])
+N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 5)
+N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 5 + [_vp])
 
 LAYERS = (  # name, Cin, Cout, kernel, stride, pad
     ("conv1", 3, 32, (3, 5, 5), (1, 2, 2), (1, 2, 2)),
@@ -38,6 +40,28 @@ def _pow2_at_least(n):
     return p
 
 
+def _plane_rows(h_valid, k, wp):
+    """Allocated padded plane height: >= h_valid + k - 1, rounded up to whole 128-position tiles so
+    no tile straddles two planes (required by the weight-gradient pass, harmless for the others)."""
+    r = 128 // wp
+    return (h_valid + k - 1 + r - 1) // r * r
+
+
+def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x, splits=0):
+    """Thin call into lr_conv3d_wgrad -> fp32 [taps][64][Nc]."""
+    L = N.lib()
+    Nc = Gy * Cy if m_is_x else Cx
+    taps = K[0] * K[1] * K[2]
+    if splits <= 0:
+        groups = K[0] * -(-(K[1] * K[2]) // (512 // Nc))
+        splits = max(1, 148 // groups)
+    ws = torch.empty(L.lr_conv3d_wgrad_workspace(K[0], K[1], K[2], Nc, splits), dtype=torch.uint8, device=x.device)
+    out = torch.empty((taps, 64, Nc), dtype=torch.float32, device=x.device)
+    N.check(L.lr_conv3d_wgrad(N.ptr(x), N.ptr(dy), N.ptr(out), N.ptr(ws), ws.numel(), B, T, H, W, Hp, Wp, Cx, Cy,
+                              Gy, dy_off, K[0], K[1], K[2], m_is_x, splits, N.stream()), "lr_conv3d_wgrad")
+    return out
+
+
 def feature_dim(H, W):
     h, w = H // 2, W // 2          # conv1 stride 2 (k5,p2)
     for _ in range(3):
@@ -50,14 +74,14 @@ def feature_dim(H, W):
 KERNEL_TIMING = None
 
 
-def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
+def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
                   tag="conv", algo_macs=None):
     """Thin call into lr_conv3d_fwd (see include/lr_b200.h)."""
     rec = KERNEL_TIMING
     if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Wp,
+    N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Hp, Wp,
                                   Cin, CG, Cout, K[0], K[1], K[2], epi_mode, ovol[0], ovol[1], ovol[2],
                                   ooff[0], ooff[1], ooff[2], J, N.stream()), "lr_conv3d_fwd")
     if rec is not None:
@@ -114,23 +138,24 @@ class _ConvStack(torch.autograd.Function):
         H4, W4 = H3 // 2, W3 // 2                    # after pool3
         Wp1, Wp2, Wp3 = _pow2_at_least(W1 + 2), _pow2_at_least(W2 + 4), _pow2_at_least(W3 + 2)
         # zero-padded channels-last volumes (borders stay zero; interiors are fully overwritten)
-        z = torch.zeros((B, T + 2, H1 + 2, Wp1, 16), dtype=bf, device=dev)
-        a1 = torch.zeros((B, T + 2, H2 + 4, Wp2, 32), dtype=bf, device=dev)
-        a2 = torch.zeros((B, T + 2, H3 + 2, Wp3, 64), dtype=bf, device=dev)
+        Hp1, Hp2, Hp3 = _plane_rows(H1, 3, Wp1), _plane_rows(H2, 5, Wp2), _plane_rows(H3, 3, Wp3)
+        z = torch.zeros((B, T + 2, Hp1, Wp1, 16), dtype=bf, device=dev)
+        a1 = torch.zeros((B, T + 2, Hp2, Wp2, 32), dtype=bf, device=dev)
+        a2 = torch.zeros((B, T + 2, Hp3, Wp3, 64), dtype=bf, device=dev)
         feat = torch.empty((B, T, H4, W4, 96), dtype=bf, device=dev)
         am1 = torch.empty((B, T, H2, W2, 32), dtype=torch.uint8, device=dev)
         am2 = torch.empty((B, T, H3, W3, 64), dtype=torch.uint8, device=dev)
         am3 = torch.empty((B, T, H4, W4, 96), dtype=torch.uint8, device=dev)
-        N.check(L.lr_clip_s2d(N.ptr(N.cont(clip)), N.ptr(z), B, T, H, W, Wp1, N.stream()), "lr_clip_s2d")
+        N.check(L.lr_clip_s2d(N.ptr(N.cont(clip)), N.ptr(z), B, T, H, W, Hp1, Wp1, N.stream()), "lr_clip_s2d")
         g1 = s2d_weight(w1.detach()).to(bf).contiguous()
         g2 = gemm_weight(w2.detach()).to(bf)
         g3 = gemm_weight(w3.detach()).to(bf)
-        conv3d_native(z, g1, b1.detach().float(), a1, am1, B, T, H1, W1, Wp1, 16, 1, 32, (3, 3, 3), 0,
-                      (T + 2, H2 + 4, Wp2), (1, 2, 2), tag="conv1.fwd",
+        conv3d_native(z, g1, b1.detach().float(), a1, am1, B, T, H1, W1, Hp1, Wp1, 16, 1, 32, (3, 3, 3), 0,
+                      (T + 2, Hp2, Wp2), (1, 2, 2), tag="conv1.fwd",
                       algo_macs=B * T * H1 * W1 * 32 * 3 * 75)       # the true 3x5x5x3 stride-2 conv
-        conv3d_native(a1, g2, b2.detach().float(), a2, am2, B, T, H2, W2, Wp2, 32, 1, 64, (3, 5, 5), 0,
-                      (T + 2, H3 + 2, Wp3), (1, 1, 1), tag="conv2.fwd")
-        conv3d_native(a2, g3, b3.detach().float(), feat, am3, B, T, H3, W3, Wp3, 64, 1, 96, (3, 3, 3), 0,
+        conv3d_native(a1, g2, b2.detach().float(), a2, am2, B, T, H2, W2, Hp2, Wp2, 32, 1, 64, (3, 5, 5), 0,
+                      (T + 2, Hp3, Wp3), (1, 1, 1), tag="conv2.fwd")
+        conv3d_native(a2, g3, b3.detach().float(), feat, am3, B, T, H3, W3, Hp3, Wp3, 64, 1, 96, (3, 3, 3), 0,
                       (T, H4, W4), (0, 0, 0), tag="conv3.fwd")
         ctx.save_for_backward(z, a1, a2, am1, am2, am3, w1, w2, w3)
         ctx.geom = (B, T, H, W)
@@ -147,49 +172,44 @@ class _ConvStack(torch.autograd.Function):
         H2, W2 = H1 // 2, W1 // 2
         H3, W3 = H2 // 2, W2 // 2
         H4, W4 = H3 // 2, W3 // 2
+        Hp1, Hp2, Hp3 = z.shape[2], a1.shape[2], a2.shape[2]
         Wp1, Wp2, Wp3 = z.shape[3], a1.shape[3], a2.shape[3]
 
-        def unpool(dp, am, Hf, Wf, C, Cg, pad, Wp):
-            out = torch.zeros((C // Cg, B, T + 2 * pad[0], Hf + 2 * pad[1], Wp, Cg), dtype=bf, device=dev)
-            N.check(L.lr_unpool(N.ptr(dp), N.ptr(am), N.ptr(out), B, T, Hf, Wf, C, Cg, T + 2 * pad[0],
-                                Hf + 2 * pad[1], Wp, pad[0], pad[1], pad[2], N.stream()), "lr_unpool")
+        def unpool(dp, am, Hf, Wf, C, Cg, pad, Hp, Wp):
+            """pooled gradient -> conv-output gradient inside a zero-padded, channel-grouped volume with
+            the SAME plane geometry as the layer's input (so dgrad and wgrad can both read it)."""
+            out = torch.zeros((C // Cg, B, T + 2, Hp, Wp, Cg), dtype=bf, device=dev)
+            N.check(L.lr_unpool(N.ptr(dp), N.ptr(am), N.ptr(out), B, T, Hf, Wf, C, Cg, T + 2, Hp, Wp,
+                                pad[0], pad[1], pad[2], N.stream()), "lr_unpool")
             return out
 
-        def interior(vol, pad, Hf, Wf):
-            """(G,B,Tp,Hp,Wp,Cg) padded grouped volume -> (B,C,T,H,W) view-ish tensor for library calls."""
-            G, _, _, _, _, Cg = vol.shape
-            v = vol[:, :, pad[0]:pad[0] + T, pad[1]:pad[1] + Hf, pad[2]:pad[2] + Wf]
-            return v.permute(1, 0, 5, 2, 3, 4).reshape(B, G * Cg, T, Hf, Wf)
+        def bias_grad(vol):
+            return vol.float().sum((1, 2, 3, 4)).reshape(-1)          # groups are channel-major
 
-        def act_interior(a, pad, Hf, Wf):
-            return a[:, pad[0]:pad[0] + T, pad[1]:pad[1] + Hf, pad[2]:pad[2] + Wf].permute(0, 4, 1, 2, 3)
-
-        # ---- layer 3 ----
+        # ---- layer 3: d_feat -> dY3 (3 groups x 32 ch, interior at (1,1,1)) ----
         dp3 = N.cont(d_feat.reshape(B, T, H4, W4, 96).to(bf))
-        dy3 = unpool(dp3, am3, H3, W3, 96, 32, (1, 1, 1), Wp3)                   # (3,B,T+2,H3+2,Wp3,32)
-        dy3_n = interior(dy3, (1, 1, 1), H3, W3)
-        # weight gradient: library call for now (cuDNN wgrad) — see DESIGN.md "interim"
-        dw3 = torch.nn.grad.conv3d_weight(act_interior(a2, (1, 1, 1), H3, W3), w3.shape, dy3_n, padding=(1, 1, 1))
-        db3 = dy3_n.float().sum((0, 2, 3, 4))
+        dy3 = unpool(dp3, am3, H3, W3, 96, 32, (1, 1, 1), Hp3, Wp3)
+        db3 = bias_grad(dy3)
+        d3 = conv3d_wgrad_native(a2, dy3, B, T, H3, W3, Hp3, Wp3, 64, 32, 3, (Hp3 + 1) * Wp3 + 1, (3, 3, 3), 1)
+        dw3 = d3.reshape(3, 3, 3, 64, 96).permute(4, 3, 0, 1, 2)       # [tap][ci][co] -> (co,ci,kt,ky,kx)
         da2 = torch.empty((B, T, H3, W3, 64), dtype=bf, device=dev)
-        conv3d_native(dy3, dgrad_weight(w3.detach(), 32).to(bf), None, da2, None, B, T, H3, W3, Wp3, 32, 3, 64,
-                      (3, 3, 3), 1, (T, H3, W3), (0, 0, 0), tag="conv3.dgrad")
+        conv3d_native(dy3, dgrad_weight(w3.detach(), 32).to(bf), None, da2, None, B, T, H3, W3, Hp3, Wp3, 32, 3,
+                      64, (3, 3, 3), 1, (T, H3, W3), (0, 0, 0), tag="conv3.dgrad")
         # ---- layer 2 ----
-        dy2 = unpool(da2, am2, H2, W2, 64, 64, (1, 2, 2), Wp2)                   # (1,B,T+2,H2+4,Wp2,64)
-        dy2_n = interior(dy2, (1, 2, 2), H2, W2)
-        dw2 = torch.nn.grad.conv3d_weight(act_interior(a1, (1, 2, 2), H2, W2), w2.shape, dy2_n, padding=(1, 2, 2))
-        db2 = dy2_n.float().sum((0, 2, 3, 4))
+        dy2 = unpool(da2, am2, H2, W2, 64, 64, (1, 2, 2), Hp2, Wp2)
+        db2 = bias_grad(dy2)
+        d2 = conv3d_wgrad_native(a1, dy2, B, T, H2, W2, Hp2, Wp2, 32, 64, 1, (Hp2 + 2) * Wp2 + 2, (3, 5, 5), 0)
+        dw2 = d2.reshape(3, 5, 5, 64, 32).permute(3, 4, 0, 1, 2)       # [tap][co][ci]
         da1 = torch.empty((B, T, H2, W2, 32), dtype=bf, device=dev)
-        conv3d_native(dy2, dgrad_weight(w2.detach(), 64).to(bf), None, da1, None, B, T, H2, W2, Wp2, 64, 1, 32,
-                      (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad")
-        # ---- layer 1 (no input gradient: the clip is data) ----
-        dy1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), W1)                    # (1,B,T,H1,W1,32)
-        dy1_n = interior(dy1, (0, 0, 0), H1, W1)
-        dw1_16 = torch.nn.grad.conv3d_weight(act_interior(z, (1, 1, 1), H1, W1), (32, 16, 3, 3, 3), dy1_n,
-                                             padding=(1, 1, 1))
-        dw1 = s2d_weight_grad(dw1_16.permute(0, 2, 3, 4, 1))
-        db1 = dy1_n.float().sum((0, 2, 3, 4))
-        return None, dw1.float(), db1, dw2.float(), db2, dw3.float(), db3
+        conv3d_native(dy2, dgrad_weight(w2.detach(), 64).to(bf), None, da1, None, B, T, H2, W2, Hp2, Wp2, 64, 1,
+                      32, (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad")
+        # ---- layer 1 (no input gradient: the clip is data); dY1 top-left aligned in z's geometry ----
+        dy1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), Hp1, Wp1)
+        db1 = bias_grad(dy1)
+        d1 = conv3d_wgrad_native(z, dy1, B, T, H1, W1, Hp1, Wp1, 16, 32, 1, 0, (3, 3, 3), 0)
+        dw1_16 = d1[:, :32, :].permute(1, 0, 2).reshape(32, 3, 3, 3, 16)
+        dw1 = s2d_weight_grad(dw1_16)
+        return None, dw1.contiguous(), db1, dw2.contiguous(), db2, dw3.contiguous(), db3
 
 
 class ConvFrontEnd(nn.Module):

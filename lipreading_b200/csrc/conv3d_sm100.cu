@@ -23,9 +23,10 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
 // lane), warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).
-#include "common.cuh"
-#include <cuda.h>
+#include "tcgen05.cuh"
 #include <string.h>
+
+using namespace lr_tc;
 
 namespace {
 
@@ -42,6 +43,7 @@ struct ConvParams {
   int Cout;                    // N, multiple of 32, <= 128
   int R;                       // tile rows = 128 / Wp
   int J;                       // accumulators (consecutive frames) per work item
+  int n_sets;                  // TMEM accumulator sets (2 = epilogue of item i overlaps MMAs of item i+1)
   int n_ytiles, n_tgroups, n_items;
   int CH;                      // chunk rows
   int chunk_bytes;             // 1024-aligned
@@ -61,70 +63,9 @@ struct ConvParams {
   int stage_pitch;             // bytes per staging row
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(lr_smem_u32(dst)), "l"(map), "r"(lr_smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   lr_smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   lr_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t desc_hi) {
-  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);   // start address, LBO = 1 (unused)
-  return ((uint64_t)desc_hi << 32) | lo;
-}
-
 // barrier block layout (uint64 each)
-enum { BAR_A_FULL = 0, BAR_A_EMPTY, BAR_ACC_FULL, BAR_ACC_EMPTY, BAR_W_FULL, BAR_W_EMPTY = BAR_W_FULL + kWStages,
-       BAR_COUNT = BAR_W_EMPTY + kWStages };
+enum { BAR_A_FULL = 0, BAR_A_EMPTY = 1, BAR_ACC_FULL = 2, BAR_ACC_EMPTY = 4, BAR_W_FULL = 6,
+       BAR_W_EMPTY = BAR_W_FULL + kWStages, BAR_COUNT = BAR_W_EMPTY + kWStages };
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -145,8 +86,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   if (threadIdx.x == 0) {
     lr_mbar_init(&bars[BAR_A_FULL], 1);
     lr_mbar_init(&bars[BAR_A_EMPTY], 1);
-    lr_mbar_init(&bars[BAR_ACC_FULL], 1);
-    lr_mbar_init(&bars[BAR_ACC_EMPTY], 4);
+    for (int i = 0; i < 2; ++i) {
+      lr_mbar_init(&bars[BAR_ACC_FULL + i], 1);
+      lr_mbar_init(&bars[BAR_ACC_EMPTY + i], 4);
+    }
     for (int s = 0; s < kWStages; ++s) {
       lr_mbar_init(&bars[BAR_W_FULL + s], 1);
       lr_mbar_init(&bars[BAR_W_EMPTY + s], 1);
@@ -160,17 +103,17 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t wn = 0;   // global weight-stage counter
-      int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int b = item / (p.n_tgroups * p.n_ytiles);
-        const int rem = item - b * (p.n_tgroups * p.n_ytiles);
-        const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
-        const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
-        const int n_chunks = jn + p.KT - 1;
-        lr_mbar_wait(&bars[BAR_A_EMPTY], (it & 1) ^ 1);
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    uint32_t wn = 0;   // global weight-stage counter
+    int it = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int b = item / (p.n_tgroups * p.n_ytiles);
+      const int rem = item - b * (p.n_tgroups * p.n_ytiles);
+      const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
+      const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
+      const int n_chunks = jn + p.KT - 1;
+      lr_mbar_wait(&bars[BAR_A_EMPTY], (it & 1) ^ 1);
+      if (elect_one()) {
         lr_mbar_expect_tx(&bars[BAR_A_FULL], (uint32_t)(n_chunks * p.CG * p.CH * p.row_bytes));
         for (int g = 0; g < p.CG; ++g)
           for (int c = 0; c < n_chunks; ++c) {
@@ -179,54 +122,75 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             tma_load_2d(a_smem + (size_t)(g * (p.J + p.KT - 1) + c) * p.chunk_bytes, &map_x, 0, (int)row0,
                         &bars[BAR_A_FULL]);
           }
-        for (int g = 0; g < p.CG; ++g)
-          for (int tap = 0; tap < n_taps; ++tap, ++wn) {
-            const int s = wn % kWStages;
-            lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / kWStages) & 1) ^ 1);
+      }
+      __syncwarp();
+      for (int g = 0; g < p.CG; ++g)
+        for (int tap = 0; tap < n_taps; ++tap, ++wn) {
+          const int s = wn % kWStages;
+          lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / kWStages) & 1) ^ 1);
+          if (elect_one()) {
             lr_mbar_expect_tx(&bars[BAR_W_FULL + s], (uint32_t)(p.Cout * p.row_bytes));
             tma_load_2d(w_smem + (size_t)s * p.wtile_bytes, &map_w, (g * n_taps + tap) * p.Cin, 0,
                         &bars[BAR_W_FULL + s]);
           }
-      }
+          __syncwarp();
+        }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t wn = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int rem = item % (p.n_tgroups * p.n_ytiles);
-        const int tg = rem / p.n_ytiles;
-        const int t0 = tg * p.J, jn = min(p.J, p.T - t0);
-        lr_mbar_wait(&bars[BAR_ACC_EMPTY], (it & 1) ^ 1);
-        lr_mbar_wait(&bars[BAR_A_FULL], it & 1);
-        tc_fence_after();
-        bool first = true;
-        for (int g = 0; g < p.CG; ++g) {
-          int tap = 0;
-          for (int kt = 0; kt < p.KT; ++kt)
-            for (int ky = 0; ky < p.KH; ++ky)
-              for (int kx = 0; kx < p.KW; ++kx, ++tap, ++wn) {
-                const int s = wn % kWStages;
-                lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / kWStages) & 1);
-                tc_fence_after();
-                const uint32_t w_addr = lr_smem_u32(w_smem + (size_t)s * p.wtile_bytes);
-                const uint32_t shift = (uint32_t)((ky * p.Wp + kx) * p.row_bytes);
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    uint32_t wn = 0;
+    int it = 0;
+    const uint64_t a_desc0 = make_desc(lr_smem_u32(a_smem), p.desc_hi);
+    const uint64_t w_desc0 = make_desc(lr_smem_u32(w_smem), p.desc_hi);
+    const uint32_t chunk16 = (uint32_t)p.chunk_bytes >> 4, wtile16 = (uint32_t)p.wtile_bytes >> 4;
+    const uint32_t row16x = (uint32_t)p.row_bytes;            // shift rows -> bytes; >>4 applied below
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int rem = item % (p.n_tgroups * p.n_ytiles);
+      const int tg = rem / p.n_ytiles;
+      const int t0 = tg * p.J, jn = min(p.J, p.T - t0);
+      const int set = it & (p.n_sets - 1);
+      const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.Cout);
+      lr_mbar_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1);
+      lr_mbar_wait(&bars[BAR_A_FULL], it & 1);
+      tc_fence_after();
+      uint32_t first = 0;      // accumulate flag: 0 for the very first tap of the item
+      for (int g = 0; g < p.CG; ++g) {
+        for (int kt = 0; kt < p.KT; ++kt)
+          for (int ky = 0; ky < p.KH; ++ky)
+            for (int kx = 0; kx < p.KW; ++kx, ++wn) {
+              const int s = wn % kWStages;
+              lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / kWStages) & 1);
+              tc_fence_after();
+              const uint64_t wd = w_desc0 + (uint64_t)(s * wtile16);
+              const uint64_t ad = a_desc0 + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
+                                                       (((uint32_t)(ky * p.Wp + kx) * row16x) >> 4));
+              if (elect_one()) {
                 for (int j = 0; j < jn; ++j) {
-                  const uint32_t a_addr =
-                      lr_smem_u32(a_smem + (size_t)(g * (p.J + p.KT - 1) + j + kt) * p.chunk_bytes) + shift;
-                  const uint32_t d = tmem_base + (uint32_t)(j * p.Cout);
-                  for (int ks = 0; ks < ksteps; ++ks)
-                    umma_bf16(d, make_desc(a_addr + ks * 32, p.desc_hi), make_desc(w_addr + ks * 32, p.desc_hi),
-                              p.idesc, (first && ks == 0) ? 0u : 1u);
+                  const uint64_t aj = ad + (uint64_t)(j * chunk16);
+                  const uint32_t d = d_base + (uint32_t)(j * p.Cout);
+                  if (ksteps == 4) {
+                    umma_bf16(d, aj, wd, p.idesc, first);
+                    umma_bf16(d, aj + 2, wd + 2, p.idesc, 1u);
+                    umma_bf16(d, aj + 4, wd + 4, p.idesc, 1u);
+                    umma_bf16(d, aj + 6, wd + 6, p.idesc, 1u);
+                  } else if (ksteps == 2) {
+                    umma_bf16(d, aj, wd, p.idesc, first);
+                    umma_bf16(d, aj + 2, wd + 2, p.idesc, 1u);
+                  } else {
+                    umma_bf16(d, aj, wd, p.idesc, first);
+                  }
                 }
-                first = false;
                 umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
               }
-        }
-        umma_commit(&bars[BAR_A_EMPTY]);
-        umma_commit(&bars[BAR_ACC_FULL]);
+              __syncwarp();
+              first = 1u;
+            }
       }
+      if (elect_one()) {
+        umma_commit(&bars[BAR_A_EMPTY]);
+        umma_commit(&bars[BAR_ACC_FULL + set]);
+      }
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (4 warps) =====================
@@ -241,14 +205,16 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int rem = item - b * (p.n_tgroups * p.n_ytiles);
       const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
-      lr_mbar_wait(&bars[BAR_ACC_FULL], it & 1);
+      const int set = it & (p.n_sets - 1);
+      const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.Cout);
+      lr_mbar_wait(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1);
       tc_fence_after();
       for (int j = 0; j < jn; ++j) {
         const int t = t0 + j;
         // TMEM -> registers -> (bias, ReLU) -> bf16 staging tile [128][Cout]
         for (int cc = 0; cc < p.Cout; cc += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.Cout + cc), v);
+          tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.Cout + cc), v);
           uint32_t packed[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -319,7 +285,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         named_bar_sync(1, 128);     // staging tile is reused by the next accumulator
       }
       tc_fence_before();
-      if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY]);
+      if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
     }
   }
 
@@ -332,10 +298,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 }
 
 // ---- clip preparation: u8 NDHWC -> /255 -> 2x2 space-to-depth -> zero-padded bf16 volume -------
-// out (B, T+2, H/2+2, Wp, 16): channel = (dy*2+dx)*3 + c for c<3, 12..15 = 0; interior at (1,1,1).
+// out (B, T+2, Hp, Wp, 16): channel = (dy*2+dx)*3 + c for c<3, 12..15 = 0; interior at (1,1,1).
 __global__ void __launch_bounds__(256)
 clip_s2d_kernel(const uint8_t* __restrict__ clip, __nv_bfloat16* __restrict__ out, int B, int T, int H,
-                int W, int Wp) {
+                int W, int Hp, int Wp) {
   const int H2 = H >> 1, W2 = W >> 1;
   const long long total = (long long)B * T * H2 * W2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -357,7 +323,7 @@ clip_s2d_kernel(const uint8_t* __restrict__ clip, __nv_bfloat16* __restrict__ ou
           v[(dy * 2 + dx) * 3 + c] = __float2bfloat16((float)src[((size_t)dy * W + dx) * 3 + c] / 255.0f);
 #pragma unroll
     for (int c = 12; c < 16; ++c) v[c] = __float2bfloat16(0.f);
-    size_t opix = (((size_t)b * (T + 2) + (t + 1)) * (H2 + 2) + (Y + 1)) * Wp + (X + 1);
+    size_t opix = (((size_t)b * (T + 2) + (t + 1)) * Hp + (Y + 1)) * Wp + (X + 1);
     uint4* dst = reinterpret_cast<uint4*>(out + opix * 16);
     dst[0] = reinterpret_cast<const uint4*>(v)[0];
     dst[1] = reinterpret_cast<const uint4*>(v)[1];
@@ -408,41 +374,6 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
   }
 }
 
-// ---- host side -----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
-int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                uint32_t box_outer, int row_bytes) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) { lr_set_error("cuTensorMapEncodeTiled entry point not available"); return LR_ECUDA; }
-  cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {inner * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
-                        : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { lr_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return LR_ECUDA; }
-  return LR_OK;
-}
-
 }  // namespace
 
 extern "C" int lr_conv3d_supported(void) {
@@ -453,16 +384,16 @@ extern "C" int lr_conv3d_supported(void) {
   return major == 10 ? 1 : 0;
 }
 
-extern "C" int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, int Wp,
-                           void* stream) {
+extern "C" int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W, int Hp,
+                           int Wp, void* stream) {
   LR_CHECK_ARG(clip && out_bf16 && B > 0 && T > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0,
                "lr_clip_s2d: H and W must be even");
-  LR_CHECK_ARG(Wp >= W / 2 + 2, "lr_clip_s2d: Wp too small");
+  LR_CHECK_ARG(Wp >= W / 2 + 2 && Hp >= H / 2 + 2, "lr_clip_s2d: padded extents too small");
   long long total = (long long)B * T * (H / 2) * (W / 2);
   int grid = lr_div_up(total, 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   clip_s2d_kernel<<<grid, 256, 0, lr_stream(stream)>>>(clip, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, T,
-                                                       H, W, Wp);
+                                                       H, W, Hp, Wp);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }
@@ -480,17 +411,17 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
   return LR_OK;
 }
 
-// x: zero-padded, channel-grouped bf16 volume [CG][B][Tp][Hp][Wp][Cin] with Tp=T+KT-1, Hp=H+KH-1,
-// Wp = power of two >= W+KW-1.  w: [Cout][CG][KT][KH][KW][Cin] bf16 (K-major per output channel).
+// x: zero-padded, channel-grouped bf16 volume [CG][B][Tp][Hp][Wp][Cin] with Tp=T+KT-1, Hp >= H+KH-1
+// (a multiple of 128/Wp keeps tiles inside their plane), Wp = power of two >= W+KW-1.  w: [Cout][CG][KT][KH][KW][Cin] bf16 (K-major per output channel).
 extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
-                             int B, int T, int H, int W, int Wp, int Cin, int CG, int Cout, int KT, int KH,
-                             int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
+                             int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
+                             int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
                              int J, void* stream) {
   LR_CHECK_ARG(x && w && y, "lr_conv3d_fwd: null pointer");
   LR_CHECK_ARG(Cin == 16 || Cin == 32 || Cin == 64, "lr_conv3d_fwd: Cin per group must be 16/32/64 (got %d)", Cin);
   LR_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 128, "lr_conv3d_fwd: Cout must be 32..128, %%32 (got %d)", Cout);
   LR_CHECK_ARG(Wp == 8 || Wp == 16 || Wp == 32 || Wp == 64 || Wp == 128, "lr_conv3d_fwd: Wp must be 8..128 pow2");
-  LR_CHECK_ARG(Wp >= W + KW - 1, "lr_conv3d_fwd: Wp < W+KW-1");
+  LR_CHECK_ARG(Wp >= W + KW - 1 && Hp >= H + KH - 1, "lr_conv3d_fwd: padded extents smaller than H+KH-1 / W+KW-1");
   LR_CHECK_ARG(KT >= 1 && KH >= 1 && KW >= 1 && CG >= 1 && B > 0 && T > 0 && H > 0 && W > 0, "lr_conv3d_fwd: bad shape");
   LR_CHECK_ARG(epi_mode == 0 || epi_mode == 1, "lr_conv3d_fwd: bad epilogue mode");
   if (!lr_conv3d_supported()) { lr_set_error("lr_conv3d_fwd needs an sm_100 device"); return LR_EARCH; }
@@ -498,7 +429,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H; p.W = W;
-  p.Tp = T + KT - 1; p.Hp = H + KH - 1; p.Wp = Wp;
+  p.Tp = T + KT - 1; p.Hp = Hp; p.Wp = Wp;
   p.KT = KT; p.KH = KH; p.KW = KW; p.Cin = Cin; p.CG = CG; p.Cout = Cout;
   p.R = 128 / Wp;
   LR_CHECK_ARG(epi_mode == 1 || (p.R % 2 == 0), "lr_conv3d_fwd: pooling needs an even number of tile rows");
@@ -512,18 +443,20 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   const int smem_cap = 227 * 1024 - 1024;     // minus alignment slack
   int fixed = kWStages * p.wtile_bytes + stage_bytes + 256;
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
-  int Jmax = 512 / Cout;
+  int n_sets = (512 / Cout) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
+  int Jmax = 512 / Cout / n_sets;
   if (J <= 0 || J > Jmax) J = Jmax;
   while (J > 1 && ((J + KT - 1) * CG > kMaxChunks || (J + KT - 1) * CG * p.chunk_bytes + fixed > smem_cap)) --J;
   LR_CHECK_ARG((J + KT - 1) * CG * p.chunk_bytes + fixed <= smem_cap && (J + KT - 1) * CG <= kMaxChunks,
                "lr_conv3d_fwd: tile does not fit shared memory");
   if (J > T) J = T;
   p.J = J;
+  p.n_sets = n_sets;
   p.n_ytiles = lr_div_up(H, p.R);
   p.n_tgroups = lr_div_up(T, J);
   p.n_items = B * p.n_ytiles * p.n_tgroups;
   int cols = 32;
-  while (cols < J * Cout) cols <<= 1;
+  while (cols < n_sets * J * Cout) cols <<= 1;
   p.tmem_cols = cols;
   p.epi_mode = epi_mode;
   p.has_bias = bias != nullptr;

@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
-def _padded(x_ndhwc, pad, Wp):
-    """(B,T,H,W,C) -> zero padded (B,T+2pt,H+2ph,Wp,C) with the interior at (pt,ph,pw)."""
+def _padded(x_ndhwc, pad, Wp, Hp=None):
+    """(B,T,H,W,C) -> zero padded (B,T+2pt,Hp,Wp,C) with the interior at (pt,ph,pw)."""
     B, T, H, W, C = x_ndhwc.shape
-    out = torch.zeros((B, T + 2 * pad[0], H + 2 * pad[1], Wp, C), dtype=x_ndhwc.dtype, device=x_ndhwc.device)
+    Hp = Hp or H + 2 * pad[1]
+    out = torch.zeros((B, T + 2 * pad[0], Hp, Wp, C), dtype=x_ndhwc.dtype, device=x_ndhwc.device)
     out[:, pad[0]:pad[0] + T, pad[1]:pad[1] + H, pad[2]:pad[2] + W] = x_ndhwc
     return out
 
@@ -33,20 +34,21 @@ def _padded(x_ndhwc, pad, Wp):
     (32, 1, 32, (1, 3, 1), 8, 8, 8, 3, 1),         # y shifts only
 ])
 def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, T, B):
-    from lipreading_b200.conv_frontend import conv3d_native
+    from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
     g = torch.Generator().manual_seed(1234)
     C = Cin * CG
     pad = tuple((k - 1) // 2 for k in K)
+    Hp = _plane_rows(H, K[1], Wp)
     x = torch.randn(B, T, H, W, C, generator=g).to(BF)
     w = (torch.randn(Cout, C, *K, generator=g) / (C * K[0] * K[1] * K[2]) ** 0.5).to(BF)
     ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float(), None, padding=pad).permute(0, 2, 3, 4, 1)
     xd = x.to(cuda)
     # channel-grouped padded volume [CG][B][Tp][Hp][Wp][Cin]
-    vol = torch.stack([_padded(xd[..., gi * Cin:(gi + 1) * Cin], pad, Wp) for gi in range(CG)], 0).contiguous()
+    vol = torch.stack([_padded(xd[..., gi * Cin:(gi + 1) * Cin], pad, Wp, Hp) for gi in range(CG)], 0).contiguous()
     # weights [Cout][CG][taps][Cin]
     wk = w.to(cuda).permute(0, 2, 3, 4, 1).reshape(Cout, -1, CG, Cin).permute(0, 2, 1, 3).contiguous()
     y = torch.full((B, T, H, W, Cout), float("nan"), dtype=BF, device=cuda)
-    conv3d_native(vol, wk, None, y, None, B, T, H, W, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0))
+    conv3d_native(vol, wk, None, y, None, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0))
     torch.cuda.synchronize()
     err = (y.float().cpu() - ref).abs().max() / ref.abs().max()
     assert torch.isfinite(y.float()).all()
@@ -55,7 +57,7 @@ def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp
 
 @pytest.mark.parametrize("J", [0, 1, 2])
 def test_conv3d_relu_pool_epilogue(native_lib, cuda, J):
-    from lipreading_b200.conv_frontend import conv3d_native
+    from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
     g = torch.Generator().manual_seed(77)
     B, T, H, W, Cin, Cout, K, Wp = 2, 5, 25, 12, 32, 64, (3, 5, 5), 16
     x = torch.randn(B, T, H, W, Cin, generator=g).to(BF)
@@ -65,12 +67,13 @@ def test_conv3d_relu_pool_epilogue(native_lib, cuda, J):
     act = F.relu(conv).to(BF).float()
     ref, idx = F.max_pool3d(act, (1, 2, 2), return_indices=True)
     ref = ref.permute(0, 2, 3, 4, 1)                                       # B,T,12,6,C
-    vol = _padded(x.to(cuda), (1, 2, 2), Wp).unsqueeze(0).contiguous()
+    Hp = _plane_rows(H, 5, Wp)
+    vol = _padded(x.to(cuda), (1, 2, 2), Wp, Hp).unsqueeze(0).contiguous()
     wk = w.to(cuda).permute(0, 2, 3, 4, 1).contiguous()
     PH, PW = H // 2, W // 2
     out = torch.zeros((B, T + 2, PH + 2, 8, Cout), dtype=BF, device=cuda)   # next layer's padded volume
     am = torch.full((B, T, PH, PW, Cout), 255, dtype=torch.uint8, device=cuda)
-    conv3d_native(vol, wk, bias.to(cuda), out, am, B, T, H, W, Wp, Cin, 1, Cout, K, 0, (T + 2, PH + 2, 8), (1, 1, 1), J)
+    conv3d_native(vol, wk, bias.to(cuda), out, am, B, T, H, W, Hp, Wp, Cin, 1, Cout, K, 0, (T + 2, PH + 2, 8), (1, 1, 1), J)
     torch.cuda.synchronize()
     got = out[:, 1:1 + T, 1:1 + PH, 1:1 + PW].float().cpu()
     assert float((got - ref).abs().max() / ref.abs().max()) < 2 ** -7
@@ -90,6 +93,40 @@ def test_conv3d_relu_pool_epilogue(native_lib, cuda, J):
     cc = torch.arange(Cout).view(1, 1, 1, 1, Cout).expand_as(am)
     picked = a[bb, tt, yy, xx, cc]
     assert bool((picked[~dead] == ref[~dead]).all())
+
+
+@pytest.mark.parametrize("name,Cx,Cy,Gy,K,H,W,Wp,m_is_x,B,T", [
+    ("conv2", 32, 64, 1, (3, 5, 5), 25, 12, 16, 0, 2, 5),
+    ("conv3", 64, 32, 3, (3, 3, 3), 12, 6, 8, 1, 3, 4),
+    ("conv1", 16, 32, 1, (3, 3, 3), 50, 25, 32, 0, 1, 3),
+])
+def test_conv3d_wgrad_matches_autograd(native_lib, cuda, name, Cx, Cy, Gy, K, H, W, Wp, m_is_x, B, T):
+    from lipreading_b200.conv_frontend import conv3d_wgrad_native, _plane_rows
+    g = torch.Generator().manual_seed(4321)
+    pad = tuple((k - 1) // 2 for k in K)
+    Co = Cy * Gy
+    Hp = _plane_rows(H, K[1], Wp)
+    x = torch.randn(B, T, H, W, Cx, generator=g).to(BF)
+    dy = torch.randn(B, T, H, W, Co, generator=g).to(BF)
+    w = torch.zeros(Co, Cx, *K, requires_grad=True)
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, None, padding=pad)
+    y.backward(dy.float().permute(0, 4, 1, 2, 3))
+    ref = w.grad                                                        # (Co,Cx,kt,ky,kx)
+    xv = _padded(x.to(cuda), pad, Wp, Hp).contiguous()
+    if name == "conv1":            # top-left aligned gradient volume (no interior offset)
+        dyv = torch.zeros((1, B, T + 2, Hp, Wp, Co), dtype=BF, device=cuda)
+        dyv[0, :, :T, :H, :W] = dy.to(cuda)
+        off = 0
+    else:
+        dyd = dy.to(cuda)
+        dyv = torch.stack([_padded(dyd[..., gi * Cy:(gi + 1) * Cy], pad, Wp, Hp) for gi in range(Gy)], 0).contiguous()
+        off = (pad[0] * Hp + pad[1]) * Wp + pad[2]
+    out = conv3d_wgrad_native(xv, dyv, B, T, H, W, Hp, Wp, Cx, Cy, Gy, off, K, m_is_x)
+    torch.cuda.synchronize()
+    out = out.cpu().reshape(K[0], K[1], K[2], 64, -1)
+    got = out.permute(4, 3, 0, 1, 2) if m_is_x else out[:, :, :, :Co].permute(3, 4, 0, 1, 2)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max() / ref.abs().max()) < 2e-3
 
 
 def test_conv_stack_forward_backward_matches_oracle(native_lib, cuda):
