@@ -266,7 +266,8 @@ def main():
         print(json.dumps(line))
         return
 
-    from lipreading_b200 import conv_frontend, dist as ldist, native, trainer
+    from lipreading_b200 import conv_frontend, dist as ldist, functional as LF, native, trainer
+    LF.GEMM_DTYPE = torch.bfloat16          # BASELINE config: bf16 operands, fp32 accumulate
     from lipreading_b200.model import VideoEncoder
     rank, local_rank, world = ldist.init()
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
@@ -295,11 +296,16 @@ def main():
         return [resident[i % 2] for i in range(n)]
 
     # ---- device-resident timing ------------------------------------------------------------
-    run(resident_loader, args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                     # nvidia-smi needs ~0.5 s to come up: start before the warm-up
+    run(resident_loader, args.warmup)
+    barrier()
+    if rank == 0:
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
+        sampler.rows.clear()                # keep only samples taken during the timed region
     conv_frontend.KERNEL_TIMING = []
     n0 = native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

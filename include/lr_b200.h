@@ -91,6 +91,20 @@ int lr_rnn_bwd(int mode, const float* d_hidden, const float* d_h_n, const float*
                int B, int T, int H, int D, float* d_gi, float* d_gh, float* h_prev_all,
                void* workspace, size_t ws_bytes, void* stream);
 
+/* Throughput path of the same layer: ONE persistent launch per pass, 8-CTA clusters keep the W_hh
+ * slices resident in shared memory as bf16, per-step state exchange over distributed shared memory
+ * (csrc/rnn_cluster.cu).  Same tensors as lr_rnn_fwd / lr_rnn_bwd (w_hh un-transposed for both);
+ * bf16 operands, fp32 accumulation and state.  lr_rnn_cluster_supported: H % 128 == 0 and the
+ * slices fit shared memory.                                                                    */
+int lr_rnn_cluster_supported(int mode, int H);
+int lr_rnn_cluster_fwd(int mode, const float* gi, const float* w_hh, const float* b_hh,
+                       const int32_t* lens, int B, int T, int H, int D, float* hidden, float* h_n,
+                       float* c_n, float* saved, void* stream);
+int lr_rnn_cluster_bwd(int mode, const float* d_hidden, const float* d_h_n, const float* d_c_n,
+                       const float* saved, const float* hidden, const float* w_hh,
+                       const int32_t* lens, int B, int T, int H, int D, float* d_gi, float* d_gh,
+                       float* h_prev_all, void* stream);
+
 /* -------- a11: collate / pad -------------------------------------------------------------- */
 /* replaces: src/data/data_loader.py:124-137 (_pad of ragged (T_i,68,3) f64 rows to (B,Tmax,F) f32).
  * src_concat f64 rows back to back, offsets (B+1) i64 in rows, dst (B,Tmax,F) f32 zero padded.  */
@@ -150,18 +164,23 @@ int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint
                   int o_x, int J, void* stream);
 /* Backward of ReLU+MaxPool(1,2,2): d_pooled (B,T,H/2,W/2,C) bf16 + argmax -> gradient w.r.t. the
  * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
- * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass.                               */
+ * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass; d_bias (C) f32 or NULL receives
+ * the per-channel sum (the conv bias gradient).                                                */
 /* Weight gradient: out[tap][64][Nc] fp32 = sum_p dy[p,:] (x) x[p+shift(tap),:] on tcgen05 (M=64,
  * MN-major operands), split over CTAs and reduced in a fixed order.  x [B][T+KT-1][Hp][Wp][Cx];
  * dy [Gy][B][T+KT-1][Hp][Wp][Cy] zero except its interior, which starts dy_off rows in.
  * m_is_x = 0: rows of out[tap] are output channels (needs Gy*Cy <= 64), columns the Cx inputs;
- * m_is_x = 1: rows are the Cx = 64 inputs, columns the Gy*Cy outputs.                          */
+ * m_is_x = 1: rows are the Cx = 64 inputs, columns the Gy*Cy outputs.
+ * stack_kx (m_is_x = 0): the KW kx-taps of a filter row share one MMA (N = KW*Cx, operand blocks
+ * are the same tile shifted by one row each); out is then [KT*KH][64][KW][Cx].                  */
 size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits);
 int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, size_t ws_bytes,
                     int B, int T, int H, int W, int Hp, int Wp, int Cx, int Cy, int Gy,
-                    long long dy_off, int KT, int KH, int KW, int m_is_x, int splits, void* stream);
-int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, int B, int T, int H, int W,
-              int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw, void* stream);
+                    long long dy_off, int KT, int KH, int KW, int m_is_x, int stack_kx, int splits,
+                    void* stream);
+int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_bias, int B, int T,
+              int H, int W, int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw,
+              void* stream);
 
 #ifdef __cplusplus
 }

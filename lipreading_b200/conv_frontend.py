@@ -21,10 +21,10 @@ from .native import _i, _vp
 
 N.register("lr_conv3d_supported", _i, [])
 N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
-N.register("lr_unpool", _i, [_vp, _vp, _vp] + [_i] * 12 + [_vp])
+N.register("lr_unpool", _i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp])
 N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 20 + [_vp])
 N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 5)
-N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 5 + [_vp])
+N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 6 + [_vp])
 
 LAYERS = (  # name, Cin, Cout, kernel, stride, pad
     ("conv1", 3, 32, (3, 5, 5), (1, 2, 2), (1, 2, 2)),
@@ -47,18 +47,26 @@ def _plane_rows(h_valid, k, wp):
     return (h_valid + k - 1 + r - 1) // r * r
 
 
-def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x, splits=0):
-    """Thin call into lr_conv3d_wgrad -> fp32 [taps][64][Nc]."""
+STACK_KX = True      # wgrad: fold the KW kx-taps of a filter row into one N = KW*Cx MMA
+
+
+def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x, splits=0, stack_kx=None):
+    """Thin call into lr_conv3d_wgrad -> fp32 [taps][64][Nc] (Nc = Gy*Cy if m_is_x else Cx)."""
     L = N.lib()
     Nc = Gy * Cy if m_is_x else Cx
     taps = K[0] * K[1] * K[2]
+    stack = (STACK_KX if stack_kx is None else stack_kx) and not m_is_x and K[2] > 1 and K[2] * Cx <= 256
     if splits <= 0:
-        groups = K[0] * -(-(K[1] * K[2]) // (512 // Nc))
+        units, n_mma = (K[1], K[2] * Cx) if stack else (K[1] * K[2], Nc)
+        groups = K[0] * -(-units // (512 // n_mma))
         splits = max(1, 148 // groups)
     ws = torch.empty(L.lr_conv3d_wgrad_workspace(K[0], K[1], K[2], Nc, splits), dtype=torch.uint8, device=x.device)
     out = torch.empty((taps, 64, Nc), dtype=torch.float32, device=x.device)
     N.check(L.lr_conv3d_wgrad(N.ptr(x), N.ptr(dy), N.ptr(out), N.ptr(ws), ws.numel(), B, T, H, W, Hp, Wp, Cx, Cy,
-                              Gy, dy_off, K[0], K[1], K[2], m_is_x, splits, N.stream()), "lr_conv3d_wgrad")
+                              Gy, dy_off, K[0], K[1], K[2], m_is_x, int(stack), splits, N.stream()),
+            "lr_conv3d_wgrad")
+    if stack:                       # [KT*KH][64][KW][Cx] -> [taps][64][Cx]
+        out = out.reshape(K[0] * K[1], 64, K[2], Cx).permute(0, 2, 1, 3).reshape(taps, 64, Cx)
     return out
 
 
@@ -122,6 +130,31 @@ def dgrad_weight(w, cg):
     return wf.permute(0, 2, 1, 3).contiguous()
 
 
+class _VolumePool:
+    """Zero-padded activation volumes are large (GBs at B=256) and only their INTERIOR is rewritten
+    every step; re-zeroing them per step costs ~1 ms of pure memset.  The pool hands out one cached
+    buffer per (tag, shape): borders are zeroed once at allocation and never written again.  A
+    generation counter catches the one unsafe pattern (two forwards before a backward)."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.generation = 0
+        self.enabled = True
+
+    def get(self, tag, shape, dtype, device):
+        if not self.enabled:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        key = (tag, tuple(shape), dtype, str(device))
+        buf = self.bufs.get(key)
+        if buf is None:
+            buf = torch.zeros(shape, dtype=dtype, device=device)
+            self.bufs[key] = buf
+        return buf
+
+
+POOL = _VolumePool()
+
+
 class _ConvStack(torch.autograd.Function):
     @staticmethod
     def forward(ctx, clip, w1, b1, w2, b2, w3, b3):
@@ -139,9 +172,11 @@ class _ConvStack(torch.autograd.Function):
         Wp1, Wp2, Wp3 = _pow2_at_least(W1 + 2), _pow2_at_least(W2 + 4), _pow2_at_least(W3 + 2)
         # zero-padded channels-last volumes (borders stay zero; interiors are fully overwritten)
         Hp1, Hp2, Hp3 = _plane_rows(H1, 3, Wp1), _plane_rows(H2, 5, Wp2), _plane_rows(H3, 3, Wp3)
-        z = torch.zeros((B, T + 2, Hp1, Wp1, 16), dtype=bf, device=dev)
-        a1 = torch.zeros((B, T + 2, Hp2, Wp2, 32), dtype=bf, device=dev)
-        a2 = torch.zeros((B, T + 2, Hp3, Wp3, 64), dtype=bf, device=dev)
+        z = POOL.get("z", (B, T + 2, Hp1, Wp1, 16), bf, dev)
+        a1 = POOL.get("a1", (B, T + 2, Hp2, Wp2, 32), bf, dev)
+        a2 = POOL.get("a2", (B, T + 2, Hp3, Wp3, 64), bf, dev)
+        POOL.generation += 1
+        ctx.generation = POOL.generation
         feat = torch.empty((B, T, H4, W4, 96), dtype=bf, device=dev)
         am1 = torch.empty((B, T, H2, W2, 32), dtype=torch.uint8, device=dev)
         am2 = torch.empty((B, T, H3, W3, 64), dtype=torch.uint8, device=dev)
@@ -164,6 +199,9 @@ class _ConvStack(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_feat):
         z, a1, a2, am1, am2, am3, w1, w2, w3 = ctx.saved_tensors
+        if POOL.enabled and ctx.generation != POOL.generation:
+            raise RuntimeError("conv front-end: another forward ran before this backward and reused the pooled "
+                               "activation volumes; set lipreading_b200.conv_frontend.POOL.enabled = False")
         B, T, H, W = ctx.geom
         dev = z.device
         bf = torch.bfloat16
@@ -178,34 +216,29 @@ class _ConvStack(torch.autograd.Function):
         def unpool(dp, am, Hf, Wf, C, Cg, pad, Hp, Wp):
             """pooled gradient -> conv-output gradient inside a zero-padded, channel-grouped volume with
             the SAME plane geometry as the layer's input (so dgrad and wgrad can both read it)."""
-            out = torch.zeros((C // Cg, B, T + 2, Hp, Wp, Cg), dtype=bf, device=dev)
-            N.check(L.lr_unpool(N.ptr(dp), N.ptr(am), N.ptr(out), B, T, Hf, Wf, C, Cg, T + 2, Hp, Wp,
-                                pad[0], pad[1], pad[2], N.stream()), "lr_unpool")
-            return out
-
-        def bias_grad(vol):
-            return vol.float().sum((1, 2, 3, 4)).reshape(-1)          # groups are channel-major
+            out = POOL.get("dy%d" % C, (C // Cg, B, T + 2, Hp, Wp, Cg), bf, dev)
+            d_bias = torch.empty(C, dtype=torch.float32, device=dev)
+            N.check(L.lr_unpool(N.ptr(dp), N.ptr(am), N.ptr(out), N.ptr(d_bias), B, T, Hf, Wf, C, Cg, T + 2, Hp,
+                                Wp, pad[0], pad[1], pad[2], N.stream()), "lr_unpool")
+            return out, d_bias
 
         # ---- layer 3: d_feat -> dY3 (3 groups x 32 ch, interior at (1,1,1)) ----
         dp3 = N.cont(d_feat.reshape(B, T, H4, W4, 96).to(bf))
-        dy3 = unpool(dp3, am3, H3, W3, 96, 32, (1, 1, 1), Hp3, Wp3)
-        db3 = bias_grad(dy3)
+        dy3, db3 = unpool(dp3, am3, H3, W3, 96, 32, (1, 1, 1), Hp3, Wp3)
         d3 = conv3d_wgrad_native(a2, dy3, B, T, H3, W3, Hp3, Wp3, 64, 32, 3, (Hp3 + 1) * Wp3 + 1, (3, 3, 3), 1)
         dw3 = d3.reshape(3, 3, 3, 64, 96).permute(4, 3, 0, 1, 2)       # [tap][ci][co] -> (co,ci,kt,ky,kx)
         da2 = torch.empty((B, T, H3, W3, 64), dtype=bf, device=dev)
         conv3d_native(dy3, dgrad_weight(w3.detach(), 32).to(bf), None, da2, None, B, T, H3, W3, Hp3, Wp3, 32, 3,
                       64, (3, 3, 3), 1, (T, H3, W3), (0, 0, 0), tag="conv3.dgrad")
         # ---- layer 2 ----
-        dy2 = unpool(da2, am2, H2, W2, 64, 64, (1, 2, 2), Hp2, Wp2)
-        db2 = bias_grad(dy2)
+        dy2, db2 = unpool(da2, am2, H2, W2, 64, 64, (1, 2, 2), Hp2, Wp2)
         d2 = conv3d_wgrad_native(a1, dy2, B, T, H2, W2, Hp2, Wp2, 32, 64, 1, (Hp2 + 2) * Wp2 + 2, (3, 5, 5), 0)
         dw2 = d2.reshape(3, 5, 5, 64, 32).permute(3, 4, 0, 1, 2)       # [tap][co][ci]
         da1 = torch.empty((B, T, H2, W2, 32), dtype=bf, device=dev)
         conv3d_native(dy2, dgrad_weight(w2.detach(), 64).to(bf), None, da1, None, B, T, H2, W2, Hp2, Wp2, 64, 1,
                       32, (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad")
         # ---- layer 1 (no input gradient: the clip is data); dY1 top-left aligned in z's geometry ----
-        dy1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), Hp1, Wp1)
-        db1 = bias_grad(dy1)
+        dy1, db1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), Hp1, Wp1)
         d1 = conv3d_wgrad_native(z, dy1, B, T, H1, W1, Hp1, Wp1, 16, 32, 1, 0, (3, 3, 3), 0)
         dw1_16 = d1[:, :32, :].permute(1, 0, 2).reshape(32, 3, 3, 3, 16)
         dw1 = s2d_weight_grad(dw1_16)

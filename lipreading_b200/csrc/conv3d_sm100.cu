@@ -337,8 +337,12 @@ clip_s2d_kernel(const uint8_t* __restrict__ clip, __nv_bfloat16* __restrict__ ou
 // is not the arg-max or the unit was ReLU-dead), borders stay zero from allocation.
 __global__ void __launch_bounds__(256)
 unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restrict__ argmax,
-              __nv_bfloat16* __restrict__ out, int B, int T, int H, int W, int C, int Cg, int Tp, int Hp,
-              int Wp, int pt, int ph, int pw) {
+              __nv_bfloat16* __restrict__ out, float* __restrict__ d_bias, int B, int T, int H, int W, int C,
+              int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw) {
+  // bias gradient = sum of the routed gradients per channel: accumulated per block in shared memory
+  __shared__ float bias_acc[128];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) bias_acc[i] = 0.f;
+  __syncthreads();
   const int PH = H >> 1, PW = W >> 1;
   const int c8 = C >> 3;
   const long long total = (long long)B * T * H * W * c8;     // one thread per (full-res pixel, 8 ch)
@@ -362,7 +366,11 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
       const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&g);
       const uint8_t* ae = reinterpret_cast<const uint8_t*>(&a);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (ae[e] == which) ? ge[e] : __float2bfloat16(0.f);
+      for (int e = 0; e < 8; ++e) {
+        const bool hit = ae[e] == which;
+        v[e] = hit ? ge[e] : __float2bfloat16(0.f);
+        if (hit && d_bias) atomicAdd(&bias_acc[cg * 8 + e], __bfloat162float(ge[e]));
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16(0.f);
@@ -372,6 +380,9 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
     const size_t opix = (size_t)g * rows_per_group + (((size_t)b * Tp + (t + pt)) * Hp + (y + ph)) * Wp + (x + pw);
     *reinterpret_cast<uint4*>(out + opix * Cg + cl) = *reinterpret_cast<const uint4*>(v);
   }
+  __syncthreads();
+  if (d_bias)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&d_bias[i], bias_acc[i]);
 }
 
 }  // namespace
@@ -398,15 +409,18 @@ extern "C" int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, in
   return LR_OK;
 }
 
-extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, int B, int T, int H, int W,
-                         int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw, void* stream) {
-  LR_CHECK_ARG(d_pooled && argmax && out && C % 8 == 0 && Cg % 8 == 0 && C % Cg == 0, "lr_unpool: bad args");
+extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_bias, int B, int T,
+                         int H, int W, int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw,
+                         void* stream) {
+  LR_CHECK_ARG(d_pooled && argmax && out && C % 8 == 0 && Cg % 8 == 0 && C % Cg == 0 && C <= 128,
+               "lr_unpool: bad args");
+  if (d_bias) LR_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * C, lr_stream(stream)));
   long long total = (long long)B * T * H * W * (C / 8);
   int grid = lr_div_up(total, 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   unpool_kernel<<<grid, 256, 0, lr_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(d_pooled), argmax,
-                                                     reinterpret_cast<__nv_bfloat16*>(out), B, T, H, W, C, Cg,
-                                                     Tp, Hp, Wp, pt, ph, pw);
+                                                     reinterpret_cast<__nv_bfloat16*>(out), d_bias, B, T, H, W,
+                                                     C, Cg, Tp, Hp, Wp, pt, ph, pw);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

@@ -45,7 +45,9 @@ struct WgradParams {
   int n_groups, splits;
   int group_kt[kMaxGroups], group_lo[kMaxGroups], group_n[kMaxGroups], group_tap0[kMaxGroups];
   Side m, n;
-  int Nc;                 // N of the MMA = n.blocks * n.row_bytes / 2
+  int Nc;                 // N of the MMA = n.blocks * n.row_bytes / 2 (x KW when kx taps are stacked)
+  int stack;              // 1: one accumulator per tap; KW: the KW kx-taps of a (kt,ky) row share one MMA
+                          //    (N blocks = the same chunk shifted by one row each: LBO = row pitch)
   int n_taps_total;
   int tmem_cols;
   int stage_bytes;
@@ -132,8 +134,8 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
       const uint32_t acc0 = n == 0 ? 0u : 1u;
       if (elect_one()) {
         for (int j = 0; j < ntap; ++j) {
-          const int tap = tap_lo + j;
-          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          const int unit = tap_lo + j;
+          const int ky = p.stack > 1 ? unit : unit / p.KW, kx = p.stack > 1 ? 0 : unit - ky * p.KW;
           const uint32_t shift = (uint32_t)(ky * p.Wp + kx);
           const uint64_t md = md0 + (uint64_t)(p.m.shifted ? (shift * p.m.row_bytes) >> 4 : 0u);
           const uint64_t nd = nd0 + (uint64_t)(p.n.shifted ? (shift * p.n.row_bytes) >> 4 : 0u);
@@ -206,6 +208,7 @@ void fill_side(Side& s, int ch_per_block, int blocks, int rows, int shifted, int
 
 }  // namespace
 
+// Nc = columns per tap (Cx, or Gy*Cy when m_is_x); the workspace size does not depend on stacking
 extern "C" size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits) {
   return (size_t)splits * KT * KH * KW * 64 * Nc * sizeof(float);
 }
@@ -216,10 +219,11 @@ extern "C" size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int 
 //        interior at row offset dy_off (= pt*Hp*Wp + ph*Wp + pw), zeros everywhere else; Cy in {32,64}
 //   m_is_x: 0 -> D[tap] is [co(64 lanes) x ci]  (M side = dy, needs Gy*Cy <= 64; Cy=32,Gy=1 is
 //                duplicated to fill M=64), 1 -> D[tap] is [ci(64) x co] (M side = x, needs Cx = 64)
-//   out: fp32 [KT*KH*KW][64][Nc], Nc = m_is_x ? Gy*Cy : Cx
+//   out: fp32 [KT*KH*KW][64][Nc], Nc = m_is_x ? Gy*Cy : Cx;  with stack_kx (m_is_x = 0 only) the layout is
+//        [KT*KH][64][KW][Cx] (the kx taps of a row are the column blocks of one accumulator)
 extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, size_t ws_bytes,
                                int B, int T, int H, int W, int Hp, int Wp, int Cx, int Cy, int Gy,
-                               long long dy_off, int KT, int KH, int KW, int m_is_x, int splits,
+                               long long dy_off, int KT, int KH, int KW, int m_is_x, int stack_kx, int splits,
                                void* stream) {
   LR_CHECK_ARG(x && dy && out && workspace, "lr_conv3d_wgrad: null pointer");
   LR_CHECK_ARG(Cx == 16 || Cx == 32 || Cx == 64, "lr_conv3d_wgrad: Cx must be 16/32/64");
@@ -246,11 +250,18 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
     fill_side(p.m, Cy, Cy == 32 ? 2 : 1, 128, 0, Cy == 32, vol_rows, dy_off);
     fill_side(p.n, Cx, 1, CH, 1, 0, 0, 0);
     p.Nc = Cx;
+    if (stack_kx && KW > 1) {          // N = KW*Cx: block j of the N operand = the chunk shifted by j rows
+      p.stack = KW;
+      p.Nc = KW * Cx;
+      p.n.lbo_bytes = p.n.row_bytes;
+    }
   }
+  if (p.stack == 0) p.stack = 1;
   LR_CHECK_ARG(p.Nc % 16 == 0 && p.Nc <= 256, "lr_conv3d_wgrad: bad N (%d)", p.Nc);
   // tap groups: one kt each, at most 512/Nc accumulators
-  const int per_kt = KH * KW;
+  const int per_kt = p.stack > 1 ? KH : KH * KW;      // accumulator units per kt plane
   const int max_taps = 512 / p.Nc;
+  LR_CHECK_ARG(max_taps >= 1, "lr_conv3d_wgrad: N too wide for TMEM");
   int g = 0, tap0 = 0;
   for (int kt = 0; kt < KT; ++kt)
     for (int lo = 0; lo < per_kt; lo += max_taps) {
@@ -261,12 +272,12 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
       ++g;
     }
   p.n_groups = g;
-  p.n_taps_total = KT * per_kt;
+  p.n_taps_total = KT * per_kt;          // accumulator units (taps, or (kt,ky) rows when stacked)
   if (splits <= 0) splits = kNumSMs / p.n_groups;
   if (splits < 1) splits = 1;
   if (splits > p.n_tiles) splits = p.n_tiles;
   p.splits = splits;
-  size_t need = lr_conv3d_wgrad_workspace(KT, KH, KW, p.Nc, splits);
+  size_t need = (size_t)splits * p.n_taps_total * 64 * p.Nc * sizeof(float);
   if (ws_bytes < need) { lr_set_error("lr_conv3d_wgrad: workspace %zu < %zu", ws_bytes, need); return LR_EWORKSPACE; }
   p.ws = reinterpret_cast<float*>(workspace);
   int cols = 32;

@@ -102,6 +102,19 @@ def proj_masked_log_softmax(hidden, weight, bias, log_mask):
 # ------------------------------------------------------------------------------------------------
 # a12/a13: one (bi)directional recurrent layer with packed-sequence semantics
 # ------------------------------------------------------------------------------------------------
+# dtype of the plain GEMMs around the recurrent kernel (x @ W_ih^T, dW_ih, dW_hh, dX).  float32 is the
+# parity path; bfloat16 operands with fp32 accumulation is the throughput path (BASELINE config "bf16").
+GEMM_DTYPE = torch.float32
+# True: run the recurrence on the persistent cluster kernels (bf16 operands) when the shape allows it
+RNN_CLUSTER = False
+
+
+def _mm(a, b):
+    if GEMM_DTYPE == torch.float32:
+        return a @ b
+    return (a.to(GEMM_DTYPE) @ b.to(GEMM_DTYPE)).float()
+
+
 class _RNNLayer(torch.autograd.Function):
     """inputs: x (B,T,I), lens (B) int32, mode str, then per direction (w_ih, w_hh, b_ih, b_hh)."""
 
@@ -117,7 +130,7 @@ class _RNNLayer(torch.autograd.Function):
         b_ih = torch.cat([weights[4 * d + 2] for d in range(D)], 0)
         w_hh = torch.stack([weights[4 * d + 1] for d in range(D)], 0).contiguous()   # (D,G*H,H)
         b_hh = torch.stack([weights[4 * d + 3] for d in range(D)], 0).contiguous()
-        gi = torch.addmm(b_ih, x2, w_ih.t())                                    # plain GEMM -> cuBLAS
+        gi = _mm(x2, w_ih.t()) + b_ih                                           # plain GEMM -> cuBLAS
         lens32 = N.cont(lens, torch.int32)
         dev = x.device
         hidden = torch.empty((B, T, D * H), dtype=torch.float32, device=dev)
@@ -126,10 +139,17 @@ class _RNNLayer(torch.autograd.Function):
         L = N.lib()
         S = L.lr_rnn_saved_per_unit(N.RNN_MODES[mode])
         saved = torch.empty((B, T, D, S * H), dtype=torch.float32, device=dev) if S > 0 else None
-        ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
-        N.check(L.lr_rnn_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T, H, D,
-                             N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.ptr(ws), ws.numel(),
-                             N.stream()), "lr_rnn_fwd")
+        use_cluster = bool(RNN_CLUSTER and L.lr_rnn_cluster_supported(N.RNN_MODES[mode], H))
+        if use_cluster:
+            N.check(L.lr_rnn_cluster_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T,
+                                         H, D, N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.stream()),
+                    "lr_rnn_cluster_fwd")
+        else:
+            ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
+            N.check(L.lr_rnn_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T, H, D,
+                                 N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.ptr(ws), ws.numel(),
+                                 N.stream()), "lr_rnn_fwd")
+        ctx.use_cluster = use_cluster
         ctx.mode, ctx.dims = mode, (B, T, I, H, D, G)
         ctx.save_for_backward(x2, lens32, w_ih, w_hh, hidden, saved if saved is not None else torch.empty(0, device=dev))
         ctx.x_needs_grad = x.requires_grad
@@ -146,28 +166,34 @@ class _RNNLayer(torch.autograd.Function):
         d_hidden = N.cont(d_hidden, torch.float32) if d_hidden is not None else torch.zeros_like(hidden)
         d_h_n = N.cont(d_h_n, torch.float32) if d_h_n is not None else None
         d_c_n = N.cont(d_c_n, torch.float32) if d_c_n is not None else None
-        w_hh_t = w_hh.transpose(1, 2).contiguous()                              # (D,H,G*H)
         d_gi = torch.empty((B, T, D, G * H), dtype=torch.float32, device=dev)
         d_gh = torch.empty((B, T, D, G * H), dtype=torch.float32, device=dev)
         h_prev = torch.empty((B, T, D, H), dtype=torch.float32, device=dev)
         L = N.lib()
-        ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
-        N.check(L.lr_rnn_bwd(N.RNN_MODES[mode], N.ptr(d_hidden), N.ptr(d_h_n), N.ptr(d_c_n),
-                             N.ptr(saved) if saved.numel() else None, N.ptr(hidden), N.ptr(w_hh_t), N.ptr(lens32),
-                             B, T, H, D, N.ptr(d_gi), N.ptr(d_gh), N.ptr(h_prev), N.ptr(ws), ws.numel(),
-                             N.stream()), "lr_rnn_bwd")
+        if ctx.use_cluster:
+            N.check(L.lr_rnn_cluster_bwd(N.RNN_MODES[mode], N.ptr(d_hidden), N.ptr(d_h_n), N.ptr(d_c_n),
+                                         N.ptr(saved) if saved.numel() else None, N.ptr(hidden), N.ptr(w_hh),
+                                         N.ptr(lens32), B, T, H, D, N.ptr(d_gi), N.ptr(d_gh), N.ptr(h_prev),
+                                         N.stream()), "lr_rnn_cluster_bwd")
+        else:
+            w_hh_t = w_hh.transpose(1, 2).contiguous()                          # (D,H,G*H)
+            ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
+            N.check(L.lr_rnn_bwd(N.RNN_MODES[mode], N.ptr(d_hidden), N.ptr(d_h_n), N.ptr(d_c_n),
+                                 N.ptr(saved) if saved.numel() else None, N.ptr(hidden), N.ptr(w_hh_t),
+                                 N.ptr(lens32), B, T, H, D, N.ptr(d_gi), N.ptr(d_gh), N.ptr(h_prev), N.ptr(ws),
+                                 ws.numel(), N.stream()), "lr_rnn_bwd")
         # weight-gradient reductions over B*T: plain GEMMs -> cuBLAS
         d_gi2 = d_gi.reshape(B * T, D * G * H)
-        d_w_ih = d_gi2.t() @ x2                                                 # (D*G*H, I)
+        d_w_ih = _mm(d_gi2.t(), x2)                                             # (D*G*H, I)
         d_b_ih = d_gi2.sum(0)
         d_gh3 = d_gh.reshape(B * T, D, G * H)
         h_prev3 = h_prev.reshape(B * T, D, H)
         grads = []
         for d in range(D):
-            d_w_hh = d_gh3[:, d].t() @ h_prev3[:, d]                            # (G*H, H)
+            d_w_hh = _mm(d_gh3[:, d].t(), h_prev3[:, d])                        # (G*H, H)
             d_b_hh = d_gh3[:, d].sum(0)
             grads += [d_w_ih[d * G * H:(d + 1) * G * H], d_w_hh, d_b_ih[d * G * H:(d + 1) * G * H], d_b_hh]
-        d_x = (d_gi2 @ w_ih).reshape(B, T, I) if ctx.x_needs_grad else None
+        d_x = _mm(d_gi2, w_ih).reshape(B, T, I) if ctx.x_needs_grad else None
         return (d_x, None, None) + tuple(grads)
 
 

@@ -193,3 +193,61 @@ def test_ctc_wrapper_quirk_matches_oracle(native_lib, cuda, reduction):
     assert _relerr(lp_d.grad.cpu(), lp_r.grad) < 1e-4
     # labels too long -> None, like the reference
     assert ctc_loss(lp_d, torch.zeros(B, 300, dtype=torch.long, device=cuda), fl, torch.full((B,), 300), reduction, cuda) is None
+
+
+@pytest.mark.parametrize("rnn_type", ["GRU", "LSTM", "RNN"])
+@pytest.mark.parametrize("bidirectional,B,T,H", [(True, 37, 13, 128), (False, 64, 9, 256), (True, 70, 20, 256)])
+def test_rnn_cluster_kernels_match_oracle_bf16(native_lib, cuda, rnn_type, bidirectional, B, T, H):
+    """Throughput path (persistent 8-CTA cluster kernels, bf16 operands / fp32 accumulate+state) vs the
+    fp32 packed-sequence reference.  Tolerance = bf16 operand rounding through T recurrent steps."""
+    from lipreading_b200 import functional as LF
+    if not native_lib.lr_rnn_cluster_supported({"RNN": 0, "GRU": 1, "LSTM": 2}[rnn_type], H):
+        pytest.skip("shape not supported by the cluster kernels")
+    I = 40
+    g = torch.Generator().manual_seed(2024)
+    ref = getattr(torch.nn, rnn_type)(I, H, bidirectional=bidirectional, batch_first=True)
+    weights = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    x = torch.randn(B, T, I, generator=g)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    for b in range(B):
+        x[b, int(lens[b]):] = 0
+    D = 2 if bidirectional else 1
+    up_h = torch.randn(B, T, D * H, generator=g)
+    up_f = torch.randn(D, B, H, generator=g)
+    wr = {k: v.clone().requires_grad_(True) for k, v in weights.items()}
+    xr = x.clone().requires_grad_(True)
+    m = getattr(torch.nn, rnn_type)(I, H, bidirectional=bidirectional, batch_first=True)
+    out_r, fin_r = torch.func.functional_call(m, wr, (torch.nn.utils.rnn.pack_padded_sequence(
+        xr, lens, batch_first=True, enforce_sorted=False),))
+    out_r, _ = torch.nn.utils.rnn.pad_packed_sequence(out_r, batch_first=True, total_length=T)
+    hn_r = fin_r[0] if rnn_type == "LSTM" else fin_r
+    loss_r = (out_r * up_h).sum() + (hn_r * up_f).sum()
+    if rnn_type == "LSTM":
+        loss_r = loss_r + (fin_r[1] * up_f.flip(0)).sum()
+    loss_r.backward()
+    names = ["weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"]
+    sfx = ["", "_reverse"] if bidirectional else [""]
+    flat = [weights[n + s].to(cuda).requires_grad_(True) for s in sfx for n in names]
+    xd = x.to(cuda).requires_grad_(True)
+    LF.RNN_CLUSTER = True
+    try:
+        res = LF.rnn_layer(xd, lens.to(cuda), rnn_type, flat)
+        loss = (res[0] * up_h.to(cuda)).sum() + (res[1] * up_f.to(cuda)).sum()
+        if rnn_type == "LSTM":
+            loss = loss + (res[2] * up_f.flip(0).to(cuda)).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        LF.RNN_CLUSTER = False
+    assert float((res[0].cpu() - out_r.detach()).abs().max()) < 3e-2
+    assert float((res[1].cpu() - hn_r.detach()).abs().max()) < 3e-2
+    # exact zeros beyond each clip's length, like pad_packed_sequence
+    for b in range(B):
+        assert float(res[0][b, int(lens[b]):].abs().max() if int(lens[b]) < T else 0.0) == 0.0
+    assert _relerr(xd.grad.cpu(), xr.grad) < 5e-2
+    i = 0
+    for s in sfx:
+        for n in names:
+            assert _relerr(flat[i].grad.cpu(), wr[n + s].grad) < 5e-2, n + s
+            i += 1
