@@ -268,6 +268,7 @@ def main():
 
     from lipreading_b200 import conv_frontend, dist as ldist, functional as LF, native, trainer
     LF.GEMM_DTYPE = torch.bfloat16          # BASELINE config: bf16 operands, fp32 accumulate
+    LF.RNN_CLUSTER = True                   # persistent cluster recurrence (bf16 operands, fp32 state)
     from lipreading_b200.model import VideoEncoder
     rank, local_rank, world = ldist.init()
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
