@@ -53,6 +53,10 @@ size_t lr_ctc_workspace(int B, int T, int C, int Lmax);
 int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lens,
                    const int32_t* target_lens, int B, int T, int C, int Lmax,
                    float* nll, float* grad, void* workspace, size_t ws_bytes, void* stream);
+/* Greedy CTC decode for the inference stream (semantics of src/models/lipreader/decoder.py:165-197):
+ * arg-max per frame, collapse repeats, drop blank.  tokens (B,T) i32 zero padded, out_lens (B).   */
+int lr_ctc_greedy_decode(const float* log_probs, const int32_t* lens, int B, int T, int C,
+                         int32_t* tokens, int32_t* out_lens, void* stream);
 /* out[b,:,:] = in[b,:,:] * scale[b]  (chain rule for the per-sample upstream gradient).      */
 int lr_scale_rows(const float* in, const float* scale, float* out, int B, int64_t row_elems,
                   void* stream);
@@ -157,11 +161,13 @@ int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W,
  *               output volume (B,oTp,oHp,oWp,Cout) [the next layer's padded input], plus one
  *               arg-max byte per pooled element (0..3, 4 = ReLU-dead) into argmax (may be NULL);
  *   epi_mode 1: plain bf16 store of the valid (t,y,x) positions (used for dgrad).
- *   J = accumulators (consecutive frames) per CTA work item, 0 = choose.                        */
+ *   J = accumulators (consecutive frames) per CTA work item, 0 = choose.
+ *   swap = 1: D^T = W . X^T (channels on the M lanes, the 128 tile positions on N) — the MMA then
+ *   amortises its A-operand fetch over N = 128 instead of N = Cout; 0: positions on M.           */
 int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
                   int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
                   int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y,
-                  int o_x, int J, void* stream);
+                  int o_x, int J, int swap, void* stream);
 /* Backward of ReLU+MaxPool(1,2,2): d_pooled (B,T,H/2,W/2,C) bf16 + argmax -> gradient w.r.t. the
  * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
  * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass; d_bias (C) f32 or NULL receives

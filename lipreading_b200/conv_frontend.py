@@ -22,7 +22,7 @@ from .native import _i, _vp
 N.register("lr_conv3d_supported", _i, [])
 N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 N.register("lr_unpool", _i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp])
-N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 20 + [_vp])
+N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 21 + [_vp])
 N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 5)
 N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 6 + [_vp])
 
@@ -82,8 +82,11 @@ def feature_dim(H, W):
 KERNEL_TIMING = None
 
 
+SWAP = True      # conv orientation: True = channels on the MMA M lanes, 128 positions on N (see lr_b200.h)
+
+
 def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
-                  tag="conv", algo_macs=None):
+                  tag="conv", algo_macs=None, swap=None):
     """Thin call into lr_conv3d_fwd (see include/lr_b200.h)."""
     rec = KERNEL_TIMING
     if rec is not None:
@@ -91,7 +94,8 @@ def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, e
         e0.record()
     N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Hp, Wp,
                                   Cin, CG, Cout, K[0], K[1], K[2], epi_mode, ovol[0], ovol[1], ovol[2],
-                                  ooff[0], ooff[1], ooff[2], J, N.stream()), "lr_conv3d_fwd")
+                                  ooff[0], ooff[1], ooff[2], J, int(SWAP if swap is None else swap), N.stream()),
+            "lr_conv3d_fwd")
     if rec is not None:
         e1.record()
         macs = algo_macs if algo_macs is not None else B * T * H * W * Cout * Cin * CG * K[0] * K[1] * K[2]

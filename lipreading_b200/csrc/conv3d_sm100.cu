@@ -44,6 +44,11 @@ struct ConvParams {
   int R;                       // tile rows = 128 / Wp
   int J;                       // accumulators (consecutive frames) per work item
   int n_sets;                  // TMEM accumulator sets (2 = epilogue of item i overlaps MMAs of item i+1)
+  int swap;                    // 1: D^T = W . X^T  (M = Cout lanes, N = 128 positions): weights are the A operand
+  int Mt;                      // UMMA M in swap mode (64 or 128)
+  int acc_cols;                // TMEM columns per accumulator (Cout, or 128 in swap mode)
+  int tps;                     // filter taps per weight stage (amortises the per-stage barrier round trip)
+  int w_stages;                // weight ring depth (<= kWStages)
   int n_ytiles, n_tgroups, n_items;
   int CH;                      // chunk rows
   int chunk_bytes;             // 1024-aligned
@@ -66,6 +71,68 @@ struct ConvParams {
 // barrier block layout (uint64 each)
 enum { BAR_A_FULL = 0, BAR_A_EMPTY = 1, BAR_ACC_FULL = 2, BAR_ACC_EMPTY = 4, BAR_W_FULL = 6,
        BAR_W_EMPTY = BAR_W_FULL + kWStages, BAR_COUNT = BAR_W_EMPTY + kWStages };
+
+// Epilogue of the swapped orientation: the accumulator is D^T [channel lanes x 128 position columns].
+// Thread = one output channel (M=64: rows live in lanes 0-15 of each 32-lane quarter, channel = 16q+lane;
+// M=128: channel = 32q+lane).  64 columns (= 64/WP tile rows, always whole pooling row-pairs) are pulled per
+// round; bias + ReLU + MaxPool(1,2,2) + arg-max are register-local; a warp stores one pixel's channels
+// contiguously.
+template <int WP>
+__device__ __forceinline__ void epilogue_swapped(const ConvParams& p, uint32_t tcol, int q, int lane, int b, int t,
+                                                 int y0) {
+  const int ch = p.Mt == 64 ? 16 * q + lane : 32 * q + lane;
+  const bool ch_ok = ch < p.Cout && (p.Mt == 128 || lane < 16);
+  const float bias = (p.has_bias && ch_ok) ? p.bias[ch] : 0.f;
+  const int PW = p.W >> 1, PH = p.H >> 1;
+  constexpr int ROWS = 64 / WP;                      // tile rows per 64-column round
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[64];
+    tmem_ld32(tcol + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+    tmem_ld32(tcol + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+    if (!ch_ok) continue;
+    if (p.epi_mode == 0) {
+#pragma unroll
+      for (int pr = 0; pr < ROWS / 2; ++pr) {
+        const int gy = ((y0 + half * ROWS) >> 1) + pr;                    // pooled row
+        if (gy >= PH) continue;
+#pragma unroll
+        for (int px = 0; px < WP / 2; ++px) {
+          if (px >= PW) continue;
+          const int c00 = (2 * pr) * WP + 2 * px;
+          float m = fmaxf(__uint_as_float(v[c00]) + bias, 0.f);
+          int a = 0;
+          // the stored activation is bf16: compare the rounded values so ties resolve like the oracle
+          m = __bfloat162float(__float2bfloat16(m));
+          float c1 = __bfloat162float(__float2bfloat16(fmaxf(__uint_as_float(v[c00 + 1]) + bias, 0.f)));
+          float c2 = __bfloat162float(__float2bfloat16(fmaxf(__uint_as_float(v[c00 + WP]) + bias, 0.f)));
+          float c3 = __bfloat162float(__float2bfloat16(fmaxf(__uint_as_float(v[c00 + WP + 1]) + bias, 0.f)));
+          if (c1 > m) { m = c1; a = 1; }
+          if (c2 > m) { m = c2; a = 2; }
+          if (c3 > m) { m = c3; a = 3; }
+          const size_t opix = (((size_t)b * p.oTp + (t + p.o_t)) * p.oHp + (gy + p.o_y)) * p.oWp + (px + p.o_x);
+          p.y[opix * p.Cout + ch] = __float2bfloat16(m);
+          if (p.argmax) {
+            const size_t apix = (((size_t)b * p.T + t) * PH + gy) * PW + px;
+            p.argmax[apix * p.Cout + ch] = (uint8_t)(m > 0.f ? a : 4);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const int gy = y0 + half * ROWS + r;
+        if (gy >= p.H) continue;
+#pragma unroll
+        for (int x = 0; x < WP; ++x) {
+          if (x >= p.W) continue;
+          const size_t opix = (((size_t)b * p.oTp + (t + p.o_t)) * p.oHp + (gy + p.o_y)) * p.oWp + (x + p.o_x);
+          p.y[opix * p.Cout + ch] = __float2bfloat16(__uint_as_float(v[r * WP + x]) + bias);
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -125,13 +192,15 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
       __syncwarp();
       for (int g = 0; g < p.CG; ++g)
-        for (int tap = 0; tap < n_taps; ++tap, ++wn) {
-          const int s = wn % kWStages;
-          lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / kWStages) & 1) ^ 1);
+        for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
+          const int s = wn % p.w_stages;
+          const int nt = min(p.tps, n_taps - tap0);
+          lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / p.w_stages) & 1) ^ 1);
           if (elect_one()) {
-            lr_mbar_expect_tx(&bars[BAR_W_FULL + s], (uint32_t)(p.Cout * p.row_bytes));
-            tma_load_2d(w_smem + (size_t)s * p.wtile_bytes, &map_w, (g * n_taps + tap) * p.Cin, 0,
-                        &bars[BAR_W_FULL + s]);
+            lr_mbar_expect_tx(&bars[BAR_W_FULL + s], (uint32_t)(nt * p.Cout * p.row_bytes));
+            for (int i = 0; i < nt; ++i)
+              tma_load_2d(w_smem + (size_t)(s * p.tps + i) * p.wtile_bytes, &map_w, (g * n_taps + tap0 + i) * p.Cin,
+                          0, &bars[BAR_W_FULL + s]);
           }
           __syncwarp();
         }
@@ -149,42 +218,49 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int tg = rem / p.n_ytiles;
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0);
       const int set = it & (p.n_sets - 1);
-      const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.Cout);
+      const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
       lr_mbar_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1);
       lr_mbar_wait(&bars[BAR_A_FULL], it & 1);
       tc_fence_after();
       uint32_t first = 0;      // accumulate flag: 0 for the very first tap of the item
       for (int g = 0; g < p.CG; ++g) {
-        for (int kt = 0; kt < p.KT; ++kt)
-          for (int ky = 0; ky < p.KH; ++ky)
-            for (int kx = 0; kx < p.KW; ++kx, ++wn) {
-              const int s = wn % kWStages;
-              lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / kWStages) & 1);
-              tc_fence_after();
-              const uint64_t wd = w_desc0 + (uint64_t)(s * wtile16);
+        for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
+          const int s = wn % p.w_stages;
+          const int nt = min(p.tps, n_taps - tap0);
+          lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / p.w_stages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int i = 0; i < nt; ++i) {
+              const int tap = tap0 + i;
+              const int kt = tap / (p.KH * p.KW), r2 = tap - kt * (p.KH * p.KW);
+              const int ky = r2 / p.KW, kx = r2 - ky * p.KW;
+              const uint64_t wd = w_desc0 + (uint64_t)((s * p.tps + i) * wtile16);
               const uint64_t ad = a_desc0 + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
                                                        (((uint32_t)(ky * p.Wp + kx) * row16x) >> 4));
-              if (elect_one()) {
-                for (int j = 0; j < jn; ++j) {
-                  const uint64_t aj = ad + (uint64_t)(j * chunk16);
-                  const uint32_t d = d_base + (uint32_t)(j * p.Cout);
-                  if (ksteps == 4) {
-                    umma_bf16(d, aj, wd, p.idesc, first);
-                    umma_bf16(d, aj + 2, wd + 2, p.idesc, 1u);
-                    umma_bf16(d, aj + 4, wd + 4, p.idesc, 1u);
-                    umma_bf16(d, aj + 6, wd + 6, p.idesc, 1u);
-                  } else if (ksteps == 2) {
-                    umma_bf16(d, aj, wd, p.idesc, first);
-                    umma_bf16(d, aj + 2, wd + 2, p.idesc, 1u);
-                  } else {
-                    umma_bf16(d, aj, wd, p.idesc, first);
-                  }
+              for (int j = 0; j < jn; ++j) {
+                const uint64_t aj = ad + (uint64_t)(j * chunk16);
+                const uint32_t d = d_base + (uint32_t)(j * p.acc_cols);
+                // swap: weights are the M-side operand, the 128 positions the N side
+                const uint64_t ma = p.swap ? wd : aj, mb = p.swap ? aj : wd;
+                if (ksteps == 4) {
+                  umma_bf16(d, ma, mb, p.idesc, first);
+                  umma_bf16(d, ma + 2, mb + 2, p.idesc, 1u);
+                  umma_bf16(d, ma + 4, mb + 4, p.idesc, 1u);
+                  umma_bf16(d, ma + 6, mb + 6, p.idesc, 1u);
+                } else if (ksteps == 2) {
+                  umma_bf16(d, ma, mb, p.idesc, first);
+                  umma_bf16(d, ma + 2, mb + 2, p.idesc, 1u);
+                } else {
+                  umma_bf16(d, ma, mb, p.idesc, first);
                 }
-                umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
               }
-              __syncwarp();
               first = 1u;
             }
+            umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
+          }
+          __syncwarp();
+          first = 1u;
+        }
       }
       if (elect_one()) {
         umma_commit(&bars[BAR_A_EMPTY]);
@@ -206,9 +282,20 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
       const int set = it & (p.n_sets - 1);
-      const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.Cout);
+      const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
       lr_mbar_wait(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1);
       tc_fence_after();
+      if (p.swap) {
+        for (int j = 0; j < jn; ++j) {
+          const uint32_t tcol = d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 128);
+          if (p.Wp == 8) epilogue_swapped<8>(p, tcol, q, lane, b, t0 + j, y0);
+          else if (p.Wp == 16) epilogue_swapped<16>(p, tcol, q, lane, b, t0 + j, y0);
+          else epilogue_swapped<32>(p, tcol, q, lane, b, t0 + j, y0);
+        }
+        tc_fence_before();
+        if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
+        continue;
+      }
       for (int j = 0; j < jn; ++j) {
         const int t = t0 + j;
         // TMEM -> registers -> (bias, ReLU) -> bf16 staging tile [128][Cout]
@@ -430,7 +517,7 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
 extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
                              int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
                              int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
-                             int J, void* stream) {
+                             int J, int swap, void* stream) {
   LR_CHECK_ARG(x && w && y, "lr_conv3d_fwd: null pointer");
   LR_CHECK_ARG(Cin == 16 || Cin == 32 || Cin == 64, "lr_conv3d_fwd: Cin per group must be 16/32/64 (got %d)", Cin);
   LR_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 128, "lr_conv3d_fwd: Cout must be 32..128, %%32 (got %d)", Cout);
@@ -453,12 +540,17 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.chunk_bytes = (p.CH * p.row_bytes + 1023) / 1024 * 1024;
   p.wtile_bytes = (Cout * p.row_bytes + 1023) / 1024 * 1024;
   p.stage_pitch = Cout * 2 + 16;
-  const int stage_bytes = 128 * p.stage_pitch;
+  p.swap = swap ? 1 : 0;
+  p.Mt = Cout <= 64 ? 64 : 128;
+  p.acc_cols = swap ? 128 : Cout;
+  // swap mode pools in registers (no staging tile) but reads Mt weight rows per MMA: keep that many
+  // bytes of slack behind the weight ring
+  const int stage_bytes = swap ? p.Mt * p.row_bytes : 128 * p.stage_pitch;
   const int smem_cap = 227 * 1024 - 1024;     // minus alignment slack
-  int fixed = kWStages * p.wtile_bytes + stage_bytes + 256;
+  int fixed = 2 * p.wtile_bytes + stage_bytes + 256;      // at least a 2-deep ring of single taps
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
-  int n_sets = (512 / Cout) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
-  int Jmax = 512 / Cout / n_sets;
+  int n_sets = (512 / p.acc_cols) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
+  int Jmax = 512 / p.acc_cols / n_sets;
   if (J <= 0 || J > Jmax) J = Jmax;
   while (J > 1 && ((J + KT - 1) * CG > kMaxChunks || (J + KT - 1) * CG * p.chunk_bytes + fixed > smem_cap)) --J;
   LR_CHECK_ARG((J + KT - 1) * CG * p.chunk_bytes + fixed <= smem_cap && (J + KT - 1) * CG <= kMaxChunks,
@@ -470,7 +562,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.n_tgroups = lr_div_up(T, J);
   p.n_items = B * p.n_ytiles * p.n_tgroups;
   int cols = 32;
-  while (cols < n_sets * J * Cout) cols <<= 1;
+  while (cols < n_sets * J * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   p.epi_mode = epi_mode;
   p.has_bias = bias != nullptr;
@@ -479,12 +571,28 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.argmax = argmax;
   p.oTp = oTp; p.oHp = oHp; p.oWp = oWp; p.o_t = o_t; p.o_y = o_y; p.o_x = o_x;
   p.rows_per_group = (long long)B * p.Tp * p.Hp * p.Wp;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc = swap ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(p.Mt >> 4) << 24))
+                 : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
   const uint32_t layout = p.row_bytes == 32 ? 6u : (p.row_bytes == 64 ? 4u : 2u);
   const uint32_t sbo = (uint32_t)(8 * p.row_bytes) >> 4;
   p.desc_hi = sbo | (1u << 14) | (layout << 29);
   p.smem_off_w = (J + KT - 1) * CG * p.chunk_bytes;
-  p.smem_off_stage = p.smem_off_w + kWStages * p.wtile_bytes;
+  {
+    // weight ring: as many taps per stage as fit (whole filter rows when possible), 3 stages deep
+    const int n_taps_h = KT * KH * KW;
+    const int avail = smem_cap - p.smem_off_w - stage_bytes - 256;
+    int stages = 3;
+    int tps = avail / (stages * p.wtile_bytes);
+    if (tps < 1) { stages = 2; tps = avail / (stages * p.wtile_bytes); }
+    if (tps > n_taps_h) tps = n_taps_h;
+    if (tps > 32) tps = 32;
+    if (tps >= KW) tps = tps / KW * KW;
+    LR_CHECK_ARG(tps >= 1, "lr_conv3d_fwd: weight ring does not fit shared memory");
+    if (tps == n_taps_h && stages > 2) stages = 2;
+    p.tps = tps;
+    p.w_stages = stages;
+  }
+  p.smem_off_stage = p.smem_off_w + p.w_stages * p.tps * p.wtile_bytes;
   p.smem_off_bar = p.smem_off_stage + stage_bytes;
   const size_t smem_bytes = (size_t)p.smem_off_bar + 256 + 1024;
 

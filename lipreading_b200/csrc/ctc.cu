@@ -263,7 +263,63 @@ ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __re
   }
 }
 
+// Greedy CTC decode (semantics of the reference's GreedyDecoder,
+// src/models/lipreader/decoder.py:165-197): per frame arg-max, collapse repeats, drop the blank.
+// One warp per clip: lanes split the classes for the arg-max (lowest index wins ties, like
+// torch.argmax on CPU), then a ballot + prefix count compacts 32 frames at a time.
+__global__ void __launch_bounds__(128)
+ctc_greedy_decode_kernel(const float* __restrict__ lp, const int32_t* __restrict__ lens, int B, int T, int C,
+                         int32_t* __restrict__ tokens, int32_t* __restrict__ out_lens) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int b = warp;
+  int Tb = lens[b];
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  const float* base = lp + (size_t)b * T * C;
+  int32_t* out = tokens + (size_t)b * T;
+  int n_out = 0, prev = -1;
+  for (int t0 = 0; t0 < Tb; t0 += 32) {
+    // arg-max of frames t0..t0+31: every lane computes all of them cooperatively, lane k keeps frame t0+k
+    int mine = 0;
+    for (int k = 0; k < 32 && t0 + k < Tb; ++k) {
+      const float* row = base + (size_t)(t0 + k) * C;
+      float best = -INFINITY;
+      int arg = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        float v = row[c];
+        if (v > best) { best = v; arg = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if (lane == k) mine = arg;
+    }
+    const bool in_range = t0 + lane < Tb;
+    int left = __shfl_up_sync(0xffffffffu, mine, 1);
+    if (lane == 0) left = prev;
+    const bool keep = in_range && mine != 0 && mine != left;
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[n_out + __popc(mask & ((1u << lane) - 1))] = mine;
+    n_out += __popc(mask);
+    const int last = min(31, Tb - t0 - 1);
+    prev = __shfl_sync(0xffffffffu, mine, last);
+  }
+  for (int i = n_out + lane; i < T; i += 32) out[i] = 0;
+  if (lane == 0) out_lens[b] = n_out;
+}
+
 }  // namespace
+
+extern "C" int lr_ctc_greedy_decode(const float* log_probs, const int32_t* lens, int B, int T, int C,
+                                    int32_t* tokens, int32_t* out_lens, void* stream) {
+  LR_CHECK_ARG(log_probs && lens && tokens && out_lens && B > 0 && T > 0 && C > 0, "lr_ctc_greedy_decode: bad args");
+  ctc_greedy_decode_kernel<<<lr_div_up(B, 4), 128, 0, lr_stream(stream)>>>(log_probs, lens, B, T, C, tokens, out_lens);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
 
 extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
   if (B <= 0 || T <= 0 || C <= 0 || Lmax < 0) return 0;

@@ -59,6 +59,19 @@ def ctc_nll(log_probs, targets, input_lens, target_lens):
     return _CTC.apply(log_probs, targets, input_lens, target_lens)
 
 
+def ctc_greedy_decode(log_probs, lens):
+    """(B,T,C) log-probs -> (tokens (B,T) int32 zero padded, out_lens (B)) : arg-max, collapse repeats,
+    drop blank (GreedyDecoder semantics, decoder.py:165-197)."""
+    N.require_cuda(log_probs, lens)
+    lp = N.cont(log_probs.detach(), torch.float32)
+    B, T, C = lp.shape
+    tokens = torch.empty((B, T), dtype=torch.int32, device=lp.device)
+    out_lens = torch.empty(B, dtype=torch.int32, device=lp.device)
+    N.check(N.lib().lr_ctc_greedy_decode(N.ptr(lp), N.ptr(N.cont(lens, torch.int32)), B, T, C, N.ptr(tokens),
+                                         N.ptr(out_lens), N.stream()), "lr_ctc_greedy_decode")
+    return tokens, out_lens
+
+
 # ------------------------------------------------------------------------------------------------
 # a14: Linear + masked log-softmax
 # ------------------------------------------------------------------------------------------------

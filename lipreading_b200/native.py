@@ -30,6 +30,7 @@ SIGNATURES = {
     "lr_launch_count": (_u64, []),
     "lr_ctc_workspace": (_sz, [_i, _i, _i, _i]),
     "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "lr_ctc_greedy_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lr_scale_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "lr_proj_logsoftmax_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lr_proj_logsoftmax_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

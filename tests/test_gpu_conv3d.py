@@ -33,7 +33,8 @@ def _padded(x_ndhwc, pad, Wp, Hp=None):
     (32, 1, 32, (1, 1, 3), 8, 6, 8, 3, 1),         # x shifts only
     (32, 1, 32, (1, 3, 1), 8, 8, 8, 3, 1),         # y shifts only
 ])
-def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, T, B):
+@pytest.mark.parametrize("swap", [0, 1])
+def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, T, B, swap):
     from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
     g = torch.Generator().manual_seed(1234)
     C = Cin * CG
@@ -48,15 +49,16 @@ def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp
     # weights [Cout][CG][taps][Cin]
     wk = w.to(cuda).permute(0, 2, 3, 4, 1).reshape(Cout, -1, CG, Cin).permute(0, 2, 1, 3).contiguous()
     y = torch.full((B, T, H, W, Cout), float("nan"), dtype=BF, device=cuda)
-    conv3d_native(vol, wk, None, y, None, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0))
+    conv3d_native(vol, wk, None, y, None, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0), swap=swap)
     torch.cuda.synchronize()
     err = (y.float().cpu() - ref).abs().max() / ref.abs().max()
     assert torch.isfinite(y.float()).all()
     assert float(err) < 2 ** -7, float(err)
 
 
+@pytest.mark.parametrize("swap", [0, 1])
 @pytest.mark.parametrize("J", [0, 1, 2])
-def test_conv3d_relu_pool_epilogue(native_lib, cuda, J):
+def test_conv3d_relu_pool_epilogue(native_lib, cuda, J, swap):
     from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
     g = torch.Generator().manual_seed(77)
     B, T, H, W, Cin, Cout, K, Wp = 2, 5, 25, 12, 32, 64, (3, 5, 5), 16
@@ -73,7 +75,7 @@ def test_conv3d_relu_pool_epilogue(native_lib, cuda, J):
     PH, PW = H // 2, W // 2
     out = torch.zeros((B, T + 2, PH + 2, 8, Cout), dtype=BF, device=cuda)   # next layer's padded volume
     am = torch.full((B, T, PH, PW, Cout), 255, dtype=torch.uint8, device=cuda)
-    conv3d_native(vol, wk, bias.to(cuda), out, am, B, T, H, W, Hp, Wp, Cin, 1, Cout, K, 0, (T + 2, PH + 2, 8), (1, 1, 1), J)
+    conv3d_native(vol, wk, bias.to(cuda), out, am, B, T, H, W, Hp, Wp, Cin, 1, Cout, K, 0, (T + 2, PH + 2, 8), (1, 1, 1), J, swap=swap)
     torch.cuda.synchronize()
     got = out[:, 1:1 + T, 1:1 + PH, 1:1 + PW].float().cpu()
     assert float((got - ref).abs().max() / ref.abs().max()) < 2 ** -7

