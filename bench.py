@@ -330,13 +330,29 @@ def main():
     from lipreading_b200.data import DevicePrefetcher
     def host_loader(n):
         return DevicePrefetcher([host[i % 2] for i in range(n)], dev)
-    losses = []
+    # every step's loss is read back to the host inside the timed region, through a pinned staging
+    # slot and an event (the value is collected one step later, so the read does not stall the queue)
+    losses, pending = [], []
+    slots = torch.zeros(args.steps + 4, dtype=torch.float32).pin_memory()
+
+    def read_back(loss):
+        i = len(pending)
+        slots[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append(ev)
+        if i > 0:
+            pending[i - 1].synchronize()
+            losses.append(float(slots[i - 1]))
     run(host_loader, 2)
+    pending.clear()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    run(host_loader, args.steps, on_step=lambda l: losses.append(l.item()))
+    run(host_loader, args.steps, on_step=read_back)
+    pending[-1].synchronize()
+    losses.append(float(slots[len(pending) - 1]))
     t1.record()
     barrier()
     te = torch.tensor([t0.elapsed_time(t1)], device=dev)

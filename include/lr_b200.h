@@ -50,6 +50,9 @@ uint64_t    lr_launch_count(void);
  * grad (B,T,C) f32 or NULL: d nll_b / d log_probs with torch's native-CTC convention
  *   exp(lp) - exp(log(alpha*beta summed per class) + nll - lp), zero for t >= input_len.     */
 size_t lr_ctc_workspace(int B, int T, int C, int Lmax);
+/* 0 (default): warp-per-clip kernel when the lattice fits shared memory, else CTA-per-clip;
+ * 1: always the CTA-per-clip kernel (test hook).                                                */
+void lr_ctc_select_kernel(int force_block);
 int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lens,
                    const int32_t* target_lens, int B, int T, int C, int Lmax,
                    float* nll, float* grad, void* workspace, size_t ws_bytes, void* stream);
@@ -187,6 +190,13 @@ int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, 
 int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_bias, int B, int T,
               int H, int W, int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw,
               void* stream);
+
+/* -------- diagnostics ------------------------------------------------------------------------ */
+/* SM cycles for `iters` back-to-back tcgen05.mma of one shape with operands resident in shared memory
+ * (tools/umma_table.py): the measured per-instruction cost that tile-orientation choices are based on.
+ * Synchronous (the only entry point that is).                                                    */
+long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
+                             int n_acc, int a_tiles, int iters, void* stream);
 
 #ifdef __cplusplus
 }

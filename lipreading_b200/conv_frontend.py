@@ -82,7 +82,7 @@ def feature_dim(H, W):
 KERNEL_TIMING = None
 
 
-SWAP = True      # conv orientation: True = channels on the MMA M lanes, 128 positions on N (see lr_b200.h)
+SWAP = False     # conv orientation: True = channels on the MMA M lanes, 128 positions on N (see lr_b200.h)
 
 
 def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,

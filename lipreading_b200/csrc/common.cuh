@@ -73,12 +73,12 @@ __device__ __forceinline__ float lr_warp_sum(float v) {
 __device__ __forceinline__ float lr_lse2(float a, float b) {
   float m = fmaxf(a, b);
   if (m == LR_NEG_INF) return LR_NEG_INF;
-  return m + logf(expf(a - m) + expf(b - m));
+  return m + __logf(__expf(a - m) + __expf(b - m));
 }
 __device__ __forceinline__ float lr_lse3(float a, float b, float c) {
   float m = fmaxf(a, fmaxf(b, c));
   if (m == LR_NEG_INF) return LR_NEG_INF;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
 // ---- mbarrier / bulk-async (TMA) primitives ---------------------------------------------

@@ -16,6 +16,8 @@
 // HBM traffic is exactly the algorithmic 2*T*C*4 bytes per clip (39 000 B at T=75,C=65).
 #include "common.cuh"
 
+int lr_ctc_force_block_kernel = 0;   // tests flip this to exercise the CTA-per-clip kernel
+
 namespace {
 
 constexpr int kCtcThreads = 128;
@@ -263,6 +265,179 @@ ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Throughput variant: ONE WARP PER CLIP, states in registers, neighbour exchange by warp shuffle.
+//
+// Lane l owns the K = 2*P consecutive lattice states [l*K, (l+1)*K): P (blank, label) pairs.  The alpha
+// step needs exactly one shuffle (the previous lane's last label state), the beta step two (the next
+// lane's first blank/label).  Only the alpha lattice is kept (shared memory, T x 32K floats); beta
+// lives in registers and the gradient row of frame t is produced in the same backward sweep, so the
+// clip's log-probs are read twice from L2/HBM and the gradient written once — nothing else moves.
+// A CTA is a single warp: ~20 KB of shared memory per clip lets ~11 clips share an SM, which is what
+// hides the 75-step dependent chain (the kernel is latency-bound per clip, throughput-bound per SM).
+template <int P>
+__global__ void __launch_bounds__(32)
+ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
+                const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens, int B, int T, int C,
+                int Lmax, float* __restrict__ nll_out, float* __restrict__ grad) {
+  constexpr int K = 2 * P, SP = 32 * K;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int Cpad = (C + 31) / 32 * 32;
+  float* alpha = reinterpret_cast<float*>(smem_raw);                 // [T][SP]
+  float* rows = alpha + (size_t)T * SP;                              // [2][Cpad]
+  float* occ = rows + 2 * Cpad;                                      // [Cpad]
+  float* erow = occ + Cpad;                                          // [32*P] label occupancies of a frame
+  int* nxt = reinterpret_cast<int*>(erow + 32 * P);                  // [32*P]
+  int* head = nxt + 32 * P;                                          // [32*P]
+
+  int Tb = in_lens[b];
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  int L = tgt_lens[b];
+  L = L < 0 ? 0 : (L > Lmax ? Lmax : L);
+  const int S = 2 * L + 1;
+  const float* lp_g = lp_all + (size_t)b * T * C;
+  const int32_t* tgt = targets + (size_t)b * Lmax;
+  float* g_b = grad ? grad + (size_t)b * T * C : nullptr;
+
+  // labels of this lane's pairs: pair i <-> label position j = lane*P + i
+  int lab[P];
+  bool skipa[P], skipb[P], has_lab[P], has_blank[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int j = lane * P + i;
+    has_lab[i] = j < L;
+    has_blank[i] = j <= L;                                           // blank state 2j exists iff 2j < S
+    lab[i] = has_lab[i] ? tgt[j] : 0;
+    skipa[i] = has_lab[i] && j >= 1 && lab[i] != tgt[j - 1];          // alpha: s-2 -> s
+    skipb[i] = has_lab[i] && j + 1 < L && tgt[j + 1] != lab[i];        // beta:  s+2 -> s
+    int h = 1, n = -1;
+    if (has_lab[i]) {
+      for (int k = 0; k < j; ++k) if (tgt[k] == lab[i]) { h = 0; break; }
+      for (int k = j + 1; k < L; ++k) if (tgt[k] == lab[i]) { n = k; break; }
+    }
+    head[j] = has_lab[i] ? h : 0;
+    nxt[j] = n;
+  }
+
+  if (Tb == 0) {
+    if (lane == 0) nll_out[b] = (L == 0) ? 0.f : INFINITY;
+    if (g_b) for (int i = lane; i < T * C; i += 32) g_b[i] = 0.f;
+    return;
+  }
+  auto load_row = [&](int t, float* dst) {
+    for (int c = lane; c < C; c += 32) dst[c] = lp_g[(size_t)t * C + c];
+  };
+  // ---- alpha sweep -------------------------------------------------------------------------------
+  float ab[P], al[P];                                                // blank / label state values
+  load_row(0, rows);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int j = lane * P + i;
+    ab[i] = (j == 0) ? rows[0] : LR_NEG_INF;
+    al[i] = (j == 0 && has_lab[i]) ? rows[lab[i]] : LR_NEG_INF;
+    *reinterpret_cast<float2*>(alpha + lane * K + 2 * i) = make_float2(ab[i], al[i]);
+  }
+  for (int t = 1; t < Tb; ++t) {
+    float* row = rows + (t & 1) * Cpad;
+    load_row(t, row);
+    __syncwarp();
+    const float lpb = row[0];
+    float prev_lab = __shfl_up_sync(0xffffffffu, al[P - 1], 1);      // label state just left of this lane
+    if (lane == 0) prev_lab = LR_NEG_INF;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float nb = has_blank[i] ? lr_lse2(ab[i], prev_lab) + lpb : LR_NEG_INF;
+      const float nl = has_lab[i] ? lr_lse3(al[i], ab[i], skipa[i] ? prev_lab : LR_NEG_INF) + row[lab[i]]
+                                  : LR_NEG_INF;
+      prev_lab = al[i];
+      ab[i] = nb;
+      al[i] = nl;
+      *reinterpret_cast<float2*>(alpha + (size_t)t * SP + lane * K + 2 * i) = make_float2(nb, nl);
+    }
+  }
+  __syncwarp();
+  float nll;
+  {
+    const float* last = alpha + (size_t)(Tb - 1) * SP;
+    const float l1 = last[S - 1];
+    const float l2 = S > 1 ? last[S - 2] : LR_NEG_INF;
+    nll = -lr_lse2(l1, l2);
+  }
+  if (lane == 0) nll_out[b] = nll;
+  if (g_b == nullptr) return;
+  const bool dead = !(nll < INFINITY);
+  for (int t = T - 1; t >= Tb; --t)
+    for (int c = lane; c < C; c += 32) g_b[(size_t)t * C + c] = 0.f;
+  if (dead) {
+    for (int i = lane; i < Tb * C; i += 32) g_b[i] = 0.f;
+    return;
+  }
+  // ---- beta sweep fused with the gradient rows ------------------------------------------------------
+  float bb[P], bl[P];
+  for (int t = Tb - 1; t >= 0; --t) {
+    float* row = rows + (t & 1) * Cpad;
+    load_row(t, row);
+    for (int c = lane; c < Cpad; c += 32) occ[c] = 0.f;
+    __syncwarp();
+    const float lpb = row[0];
+    if (t == Tb - 1) {
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const int j = lane * P + i;
+        bb[i] = (j == L) ? lpb : LR_NEG_INF;                         // state S-1 (final blank)
+        bl[i] = (has_lab[i] && j == L - 1) ? row[lab[i]] : LR_NEG_INF;   // state S-2
+      }
+    } else {
+      float nb_blank = __shfl_down_sync(0xffffffffu, bb[0], 1);      // next lane's first blank / label
+      float nb_lab = __shfl_down_sync(0xffffffffu, bl[0], 1);
+      if (lane == 31) { nb_blank = LR_NEG_INF; nb_lab = LR_NEG_INF; }
+      float nbv[P], nlv[P];
+#pragma unroll
+      for (int i = P - 1; i >= 0; --i) {
+        const float right_blank = (i + 1 < P) ? bb[i + 1] : nb_blank;
+        const float right_lab = (i + 1 < P) ? bl[i + 1] : nb_lab;
+        nlv[i] = has_lab[i] ? lr_lse3(bl[i], right_blank, skipb[i] ? right_lab : LR_NEG_INF) + row[lab[i]]
+                            : LR_NEG_INF;
+        nbv[i] = has_blank[i] ? lr_lse2(bb[i], bl[i]) + lpb : LR_NEG_INF;
+      }
+#pragma unroll
+      for (int i = 0; i < P; ++i) { bb[i] = nbv[i]; bl[i] = nlv[i]; }
+    }
+    // occupancies: exp(alpha + beta + nll - lp) per state (each in [0,1])
+    float eb = 0.f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float2 a = *reinterpret_cast<const float2*>(alpha + (size_t)t * SP + lane * K + 2 * i);
+      const float sb = a.x + bb[i], sl = a.y + bl[i];
+      if (has_blank[i] && sb != LR_NEG_INF) eb += __expf(sb + nll - lpb);
+      erow[lane * P + i] = (has_lab[i] && sl != LR_NEG_INF) ? __expf(sl + nll - row[lab[i]]) : 0.f;
+    }
+    eb = lr_warp_sum(eb);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const int j = lane * P + i;
+      if (has_lab[i] && head[j]) {
+        float acc = erow[j];
+        for (int k = nxt[j]; k >= 0; k = nxt[k]) acc += erow[k];
+        if (lab[i] > 0 && lab[i] < C) occ[lab[i]] = acc;
+      }
+    }
+    if (lane == 0) occ[0] = eb;
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) g_b[(size_t)t * C + c] = __expf(row[c]) - occ[c];
+    __syncwarp();
+  }
+}
+
+size_t warp_kernel_smem(int T, int C, int P) {
+  const int Cpad = (C + 31) / 32 * 32;
+  return ((size_t)T * 64 * P + 3 * Cpad + 32 * P) * sizeof(float) + (size_t)2 * 32 * P * sizeof(int);
+}
+
 // Greedy CTC decode (semantics of the reference's GreedyDecoder,
 // src/models/lipreader/decoder.py:165-197): per frame arg-max, collapse repeats, drop the blank.
 // One warp per clip: lanes split the classes for the arg-max (lowest index wins ties, like
@@ -321,6 +496,8 @@ extern "C" int lr_ctc_greedy_decode(const float* log_probs, const int32_t* lens,
   return LR_OK;
 }
 
+extern "C" void lr_ctc_select_kernel(int force_block) { lr_ctc_force_block_kernel = force_block; }
+
 extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
   if (B <= 0 || T <= 0 || C <= 0 || Lmax < 0) return 0;
   CtcPlan p = make_plan(T, C, Lmax);
@@ -337,6 +514,28 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
   LR_CHECK_ARG(B > 0 && T > 0 && C > 1 && Lmax >= 0, "lr_ctc_fwd_bwd: bad shape B=%d T=%d C=%d L=%d",
                B, T, C, Lmax);
   if (Lmax == 0) Lmax = 1;  // keep array extents non-zero; target_lens still clamp to 0
+  // warp-per-clip kernel whenever the alpha lattice of a clip fits a modest slice of shared memory
+  {
+    const int S = 2 * Lmax + 1;
+    const int P = S <= 64 ? 1 : (S <= 128 ? 2 : (S <= 256 ? 4 : 0));
+    const size_t sm = P ? warp_kernel_smem(T, C, P) : 0;
+    if (P && sm <= 100 * 1024 && !lr_ctc_force_block_kernel) {
+      cudaStream_t st = lr_stream(stream);
+#define LR_LAUNCH_WARP(PP)                                                                                   \
+  do {                                                                                                       \
+    LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                       (int)sm));                                                            \
+    ctc_warp_kernel<PP><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll,  \
+                                            grad);                                                            \
+  } while (0)
+      if (P == 1) LR_LAUNCH_WARP(1);
+      else if (P == 2) LR_LAUNCH_WARP(2);
+      else LR_LAUNCH_WARP(4);
+#undef LR_LAUNCH_WARP
+      LR_CHECK_LAUNCH();
+      return LR_OK;
+    }
+  }
   CtcPlan p = make_plan(T, C, Lmax);
   if (!p.lat_in_smem) {
     size_t need = (size_t)B * 2 * T * p.Smax * sizeof(float);

@@ -1,0 +1,86 @@
+// umma_microbench.cu — measures the issue-to-retire cost of back-to-back tcgen05.mma of a given shape
+// on this GPU (operands resident in shared memory, one accumulator or a ring of accumulators).  Used to
+// choose tile orientation / N per layer from measurement instead of the nominal rate (tools/umma_table.py).
+#include "tcgen05.cuh"
+#include <string.h>
+
+using namespace lr_tc;
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+umma_bench_kernel(uint32_t idesc, uint32_t desc_hi_a, uint32_t desc_hi_b, int a_step16, int b_step16, int n_acc,
+                  int acc_cols, int iters, int a_tiles, int a_tile16, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  // deterministic small values (bf16 1.0 = 0x3f80): avoids NaN-path surprises
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3f803f80u;
+  if (threadIdx.x == 0) { lr_mbar_init(&bar, 1); lr_fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  lr_fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    const uint64_t a0 = make_desc(lr_smem_u32(base), desc_hi_a);
+    const uint64_t b0 = make_desc(lr_smem_u32(base + 64 * 1024), desc_hi_b);
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t d = tmem_base + (uint32_t)((it % n_acc) * acc_cols);
+        const uint64_t a = a0 + (uint64_t)((it % a_tiles) * a_tile16) + (uint64_t)((it & 1) * a_step16);
+        const uint64_t b = b0 + (uint64_t)((it & 1) * b_step16);
+        umma_bf16(d, a, b, idesc, it >= n_acc ? 1u : 0u);
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    lr_mbar_wait(&bar, 0);
+    if (elect_one()) { t1 = clock64(); out[0] = t1 - t0; }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace
+
+// a_major / b_major: 0 = K-major, 1 = MN-major.  row_bytes_* select the swizzle (32/64/128).
+// a_tiles > 1 cycles the A descriptor over that many different tiles (like the conv kernels' per-frame
+// chunks); n_acc accumulators of acc_cols columns are used round-robin.  Returns SM cycles for `iters` MMAs.
+extern "C" long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
+                                        int n_acc, int a_tiles, int iters, void* stream) {
+  if (!(M == 64 || M == 128) || N % 16 != 0 || N < 16 || N > 256) { lr_set_error("lr_umma_microbench: bad shape"); return -1; }
+  int acc_cols = N < 32 ? 32 : N;
+  if (n_acc < 1) n_acc = 1;
+  if (n_acc * acc_cols > 512) n_acc = 512 / acc_cols;
+  uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_major & 1) << 15) | ((uint32_t)(b_major & 1) << 16) |
+                   ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  uint32_t hi_a = desc_hi_for(row_bytes_a, (uint32_t)(8 * row_bytes_a));
+  uint32_t hi_b = desc_hi_for(row_bytes_b, (uint32_t)(8 * row_bytes_b));
+  // K-major: the second k-step is 32 B further along the row; MN-major: 16 rows further
+  int a_step16 = a_major ? (16 * row_bytes_a) >> 4 : 2;
+  int b_step16 = b_major ? (16 * row_bytes_b) >> 4 : 2;
+  if (row_bytes_a == 32 && !a_major) a_step16 = 0;
+  if (row_bytes_b == 32 && !b_major) b_step16 = 0;
+  int a_tile16 = (M * row_bytes_a) >> 4;
+  if (a_tiles < 1) a_tiles = 1;
+  while (a_tiles > 1 && a_tiles * M * row_bytes_a + 4096 > 60 * 1024) --a_tiles;
+  long long* d_out = nullptr;
+  if (cudaMalloc(&d_out, sizeof(long long)) != cudaSuccess) return -2;
+  const size_t smem = 100 * 1024;
+  cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaStream_t st = lr_stream(stream);
+  umma_bench_kernel<<<1, 128, smem, st>>>(idesc, hi_a, hi_b, a_step16, b_step16, n_acc, acc_cols, iters, a_tiles,
+                                          a_tile16, d_out);
+  long long h = -3;
+  if (cudaStreamSynchronize(st) == cudaSuccess) cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  return h;
+}

@@ -51,6 +51,11 @@ __global__ void rect_geometry_kernel(const int32_t* __restrict__ rects, int N, i
 __global__ void __launch_bounds__(256)
 warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ crop,
                float* __restrict__ out, int H, int W) {
+  // image/255. exactly as the reference computes it (float64 division), once per CTA instead of 12
+  // double-precision divisions per output pixel
+  __shared__ double lut[256];
+  lut[threadIdx.x] = (double)threadIdx.x / 255.0;
+  __syncthreads();
   const int n = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;   // 0..65535
   const int v = pix >> 8, u = pix & 255;
@@ -75,10 +80,10 @@ warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ c
   float res[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    double v00 = (r0 && c0) ? (double)p00[ch] / 255.0 : 0.0;
-    double v01 = (r0 && c1) ? (double)p01[ch] / 255.0 : 0.0;
-    double v10 = (r1 && c0) ? (double)p10[ch] / 255.0 : 0.0;
-    double v11 = (r1 && c1) ? (double)p11[ch] / 255.0 : 0.0;
+    double v00 = (r0 && c0) ? lut[p00[ch]] : 0.0;
+    double v01 = (r0 && c1) ? lut[p01[ch]] : 0.0;
+    double v10 = (r1 && c0) ? lut[p10[ch]] : 0.0;
+    double v11 = (r1 && c1) ? lut[p11[ch]] : 0.0;
     double top = (1.0 - dc) * v00 + dc * v01;
     double bot = (1.0 - dc) * v10 + dc * v11;
     res[ch] = (float)((1.0 - dr) * top + dr * bot);

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _rand_labels(g, B, Lmax, lo=1, hi=None, nclass=64, repeat_p=0.3):
-    hi = hi or Lmax
+    hi = max(hi or Lmax, lo)
     lens = torch.randint(lo, hi + 1, (B,), generator=g)
     lab = torch.zeros(B, Lmax, dtype=torch.long)
     for b in range(B):
@@ -29,12 +29,22 @@ def _relerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("B,T,C,Lmax", [(7, 20, 65, 8), (3, 75, 65, 30), (2, 300, 65, 120), (1, 5, 65, 1)])
-def test_ctc_nll_and_grad(native_lib, cuda, B, T, C, Lmax):
+@pytest.fixture(params=["warp_per_clip", "cta_per_clip"])
+def ctc_kernel(request, native_lib):
+    """Both CTC kernels: warp-per-clip (default when the lattice fits) and CTA-per-clip (any size)."""
+    native_lib.lr_ctc_select_kernel(1 if request.param == "cta_per_clip" else 0)
+    yield request.param
+    native_lib.lr_ctc_select_kernel(0)
+
+
+@pytest.mark.parametrize("B,T,C,Lmax", [(7, 20, 65, 8), (3, 75, 65, 30), (2, 300, 65, 120), (1, 5, 65, 1),
+                                        (5, 75, 65, 31), (4, 90, 65, 63), (3, 40, 33, 40)])
+def test_ctc_nll_and_grad(native_lib, cuda, ctc_kernel, B, T, C, Lmax):
     from lipreading_b200 import functional as LF
     g = torch.Generator().manual_seed(123456 + B * T)
     lp = torch.randn(B, T, C, generator=g).log_softmax(-1)
-    lab, tl = _rand_labels(g, B, Lmax, hi=min(Lmax, T // 2))
+    lab, tl = _rand_labels(g, B, Lmax, hi=min(Lmax, T // 2), nclass=C - 1)
+    tl[0] = min(Lmax, T // 2)                             # exercise the longest label the kernel variant allows
     il = torch.randint(max(T // 2, int(tl.max()) * 2), T + 1, (B,), generator=g).sort().values
     tgt = lab + 1
     # reference in float64: torch's own fp32 CPU kernel drifts by ~3e-4 from the exact gradient at
@@ -59,7 +69,7 @@ def test_ctc_nll_and_grad(native_lib, cuda, B, T, C, Lmax):
     assert np.abs(got - g0).max() < (1e-4 if T <= 100 else 3e-4)
 
 
-def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda):
+def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda, ctc_kernel):
     from lipreading_b200 import functional as LF
     g = torch.Generator().manual_seed(1)
     lp = torch.randn(2, 6, 65, generator=g).log_softmax(-1).to(cuda).requires_grad_(True)
