@@ -196,7 +196,7 @@ int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_b
  * (tools/umma_table.py): the measured per-instruction cost that tile-orientation choices are based on.
  * Synchronous (the only entry point that is).                                                    */
 long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
-                             int n_acc, int a_tiles, int iters, void* stream);
+                             int n_acc, int a_tiles, int iters, int a_shift_rows, void* stream);
 
 #ifdef __cplusplus
 }

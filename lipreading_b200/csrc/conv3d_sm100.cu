@@ -44,6 +44,8 @@ struct ConvParams {
   int R;                       // tile rows = 128 / Wp
   int J;                       // accumulators (consecutive frames) per work item
   int n_sets;                  // TMEM accumulator sets (2 = epilogue of item i overlaps MMAs of item i+1)
+  int a_set_bytes;             // bytes of one chunk set
+  int a_sets;                  // chunk-set buffers (2 = next item's planes load while this item computes)
   int swap;                    // 1: D^T = W . X^T  (M = Cout lanes, N = 128 positions): weights are the A operand
   int Mt;                      // UMMA M in swap mode (64 or 128)
   int acc_cols;                // TMEM columns per accumulator (Cout, or 128 in swap mode)
@@ -69,7 +71,7 @@ struct ConvParams {
 };
 
 // barrier block layout (uint64 each)
-enum { BAR_A_FULL = 0, BAR_A_EMPTY = 1, BAR_ACC_FULL = 2, BAR_ACC_EMPTY = 4, BAR_W_FULL = 6,
+enum { BAR_A_FULL = 0, BAR_A_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACC_EMPTY = 6, BAR_W_FULL = 8,
        BAR_W_EMPTY = BAR_W_FULL + kWStages, BAR_COUNT = BAR_W_EMPTY + kWStages };
 
 // Epilogue of the swapped orientation: the accumulator is D^T [channel lanes x 128 position columns].
@@ -151,9 +153,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const int ksteps = p.Cin / 16;
 
   if (threadIdx.x == 0) {
-    lr_mbar_init(&bars[BAR_A_FULL], 1);
-    lr_mbar_init(&bars[BAR_A_EMPTY], 1);
     for (int i = 0; i < 2; ++i) {
+      lr_mbar_init(&bars[BAR_A_FULL + i], 1);
+      lr_mbar_init(&bars[BAR_A_EMPTY + i], 1);
       lr_mbar_init(&bars[BAR_ACC_FULL + i], 1);
       lr_mbar_init(&bars[BAR_ACC_EMPTY + i], 4);
     }
@@ -179,15 +181,17 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int tg = rem / p.n_ytiles, yt = rem - tg * p.n_ytiles;
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
       const int n_chunks = jn + p.KT - 1;
-      lr_mbar_wait(&bars[BAR_A_EMPTY], (it & 1) ^ 1);
+      const int aset = it & (p.a_sets - 1);
+      uint8_t* a_set = a_smem + (size_t)aset * p.a_set_bytes;
+      lr_mbar_wait(&bars[BAR_A_EMPTY + aset], ((it / p.a_sets) & 1) ^ 1);
       if (elect_one()) {
-        lr_mbar_expect_tx(&bars[BAR_A_FULL], (uint32_t)(n_chunks * p.CG * p.CH * p.row_bytes));
+        lr_mbar_expect_tx(&bars[BAR_A_FULL + aset], (uint32_t)(n_chunks * p.CG * p.CH * p.row_bytes));
         for (int g = 0; g < p.CG; ++g)
           for (int c = 0; c < n_chunks; ++c) {
             long long row0 = (long long)g * p.rows_per_group +
                              (((long long)b * p.Tp + (t0 + c)) * p.Hp + y0) * p.Wp;
-            tma_load_2d(a_smem + (size_t)(g * (p.J + p.KT - 1) + c) * p.chunk_bytes, &map_x, 0, (int)row0,
-                        &bars[BAR_A_FULL]);
+            tma_load_2d(a_set + (size_t)(g * (p.J + p.KT - 1) + c) * p.chunk_bytes, &map_x, 0, (int)row0,
+                        &bars[BAR_A_FULL + aset]);
           }
       }
       __syncwarp();
@@ -220,7 +224,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int set = it & (p.n_sets - 1);
       const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
       lr_mbar_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1);
-      lr_mbar_wait(&bars[BAR_A_FULL], it & 1);
+      const int aset = it & (p.a_sets - 1);
+      const uint64_t a_desc_set = a_desc0 + (uint64_t)(aset * (p.a_set_bytes >> 4));
+      lr_mbar_wait(&bars[BAR_A_FULL + aset], (it / p.a_sets) & 1);
       tc_fence_after();
       uint32_t first = 0;      // accumulate flag: 0 for the very first tap of the item
       for (int g = 0; g < p.CG; ++g) {
@@ -235,7 +241,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               const int kt = tap / (p.KH * p.KW), r2 = tap - kt * (p.KH * p.KW);
               const int ky = r2 / p.KW, kx = r2 - ky * p.KW;
               const uint64_t wd = w_desc0 + (uint64_t)((s * p.tps + i) * wtile16);
-              const uint64_t ad = a_desc0 + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
+              const uint64_t ad = a_desc_set + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
                                                        (((uint32_t)(ky * p.Wp + kx) * row16x) >> 4));
               for (int j = 0; j < jn; ++j) {
                 const uint64_t aj = ad + (uint64_t)(j * chunk16);
@@ -263,7 +269,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         }
       }
       if (elect_one()) {
-        umma_commit(&bars[BAR_A_EMPTY]);
+        umma_commit(&bars[BAR_A_EMPTY + aset]);
         umma_commit(&bars[BAR_ACC_FULL + set]);
       }
       __syncwarp();
@@ -576,7 +582,13 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   const uint32_t layout = p.row_bytes == 32 ? 6u : (p.row_bytes == 64 ? 4u : 2u);
   const uint32_t sbo = (uint32_t)(8 * p.row_bytes) >> 4;
   p.desc_hi = sbo | (1u << 14) | (layout << 29);
-  p.smem_off_w = (J + KT - 1) * CG * p.chunk_bytes;
+  p.a_set_bytes = (J + KT - 1) * CG * p.chunk_bytes;
+  // second chunk set when it still leaves room for a 2-deep ring of whole filter rows (or 2 taps)
+  {
+    const int want_w = 2 * (KW < 2 ? 2 : KW) * p.wtile_bytes;
+    p.a_sets = (2 * p.a_set_bytes + stage_bytes + 256 + want_w <= smem_cap) ? 2 : 1;
+  }
+  p.smem_off_w = p.a_sets * p.a_set_bytes;
   {
     // weight ring: as many taps per stage as fit (whole filter rows when possible), 3 stages deep
     const int n_taps_h = KT * KH * KW;

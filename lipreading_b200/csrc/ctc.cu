@@ -285,9 +285,10 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int Cpad = (C + 31) / 32 * 32;
+  constexpr int RING = 8;                                            // log-prob rows in flight (cp.async)
   float* alpha = reinterpret_cast<float*>(smem_raw);                 // [T][SP]
-  float* rows = alpha + (size_t)T * SP;                              // [2][Cpad]
-  float* occ = rows + 2 * Cpad;                                      // [Cpad]
+  float* rows = alpha + (size_t)T * SP;                              // [RING][Cpad]
+  float* occ = rows + RING * Cpad;                                   // [Cpad]
   float* erow = occ + Cpad;                                          // [32*P] label occupancies of a frame
   int* nxt = reinterpret_cast<int*>(erow + 32 * P);                  // [32*P]
   int* head = nxt + 32 * P;                                          // [32*P]
@@ -326,13 +327,25 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
     if (g_b) for (int i = lane; i < T * C; i += 32) g_b[i] = 0.f;
     return;
   }
-  auto load_row = [&](int t, float* dst) {
-    for (int c = lane; c < C; c += 32) dst[c] = lp_g[(size_t)t * C + c];
+  // asynchronous row fetch (LDGSTS): row t lands in ring slot t % RING; one commit group per row
+  const uint32_t rows_addr = lr_smem_u32(rows);
+  auto issue_row = [&](int t) {
+    if (t >= 0 && t < Tb) {
+      const uint32_t dst = rows_addr + (uint32_t)(((t % RING) * Cpad) * 4);
+      for (int c = lane; c < C; c += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + c * 4), "l"(lp_g + (size_t)t * C + c)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto wait_row = [&]() {      // all but the RING-2 most recent groups have landed
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 2) : "memory");
+    __syncwarp();
   };
   // ---- alpha sweep -------------------------------------------------------------------------------
   float ab[P], al[P];                                                // blank / label state values
-  load_row(0, rows);
-  __syncwarp();
+  for (int t = 0; t < RING - 1; ++t) issue_row(t);                   // prologue: RING-1 rows in flight
+  wait_row();
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int j = lane * P + i;
@@ -341,9 +354,10 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
     *reinterpret_cast<float2*>(alpha + lane * K + 2 * i) = make_float2(ab[i], al[i]);
   }
   for (int t = 1; t < Tb; ++t) {
-    float* row = rows + (t & 1) * Cpad;
-    load_row(t, row);
-    __syncwarp();
+    __syncwarp();                                                    // everyone is done with slot (t-2)%RING
+    issue_row(t + RING - 2);
+    wait_row();
+    float* row = rows + (t % RING) * Cpad;
     const float lpb = row[0];
     float prev_lab = __shfl_up_sync(0xffffffffu, al[P - 1], 1);      // label state just left of this lane
     if (lane == 0) prev_lab = LR_NEG_INF;
@@ -377,9 +391,13 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
   }
   // ---- beta sweep fused with the gradient rows ------------------------------------------------------
   float bb[P], bl[P];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  for (int k = 0; k < RING - 1; ++k) issue_row(Tb - 1 - k);          // prologue of the backward sweep
   for (int t = Tb - 1; t >= 0; --t) {
-    float* row = rows + (t & 1) * Cpad;
-    load_row(t, row);
+    if (t < Tb - 1) { __syncwarp(); issue_row(t - (RING - 2)); }
+    wait_row();
+    float* row = rows + (t % RING) * Cpad;
     for (int c = lane; c < Cpad; c += 32) occ[c] = 0.f;
     __syncwarp();
     const float lpb = row[0];
@@ -435,7 +453,7 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
 
 size_t warp_kernel_smem(int T, int C, int P) {
   const int Cpad = (C + 31) / 32 * 32;
-  return ((size_t)T * 64 * P + 3 * Cpad + 32 * P) * sizeof(float) + (size_t)2 * 32 * P * sizeof(int);
+  return ((size_t)T * 64 * P + 9 * Cpad + 32 * P) * sizeof(float) + (size_t)2 * 32 * P * sizeof(int);
 }
 
 // Greedy CTC decode (semantics of the reference's GreedyDecoder,

@@ -10,7 +10,7 @@ namespace {
 
 __global__ void __launch_bounds__(128, 1)
 umma_bench_kernel(uint32_t idesc, uint32_t desc_hi_a, uint32_t desc_hi_b, int a_step16, int b_step16, int n_acc,
-                  int acc_cols, int iters, int a_tiles, int a_tile16, long long* out) {
+                  int acc_cols, int iters, int a_tiles, int a_tile16, int a_shift16, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -26,16 +26,25 @@ umma_bench_kernel(uint32_t idesc, uint32_t desc_hi_a, uint32_t desc_hi_b, int a_
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (warp == 0) {
-    const uint64_t a0 = make_desc(lr_smem_u32(base), desc_hi_a);
+    const uint64_t a0 = make_desc(lr_smem_u32(base), desc_hi_a) + (uint64_t)a_shift16;   // row-shifted start
     const uint64_t b0 = make_desc(lr_smem_u32(base + 64 * 1024), desc_hi_b);
     long long t0 = 0, t1 = 0;
+    // descriptors / accumulators precomputed: the timed loop is nothing but 8 tcgen05.mma per trip
+    uint64_t av[8], bv[8];
+    uint32_t dv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dv[k] = tmem_base + (uint32_t)((k % n_acc) * acc_cols);
+      av[k] = a0 + (uint64_t)((k % a_tiles) * a_tile16) + (uint64_t)((k & 1) * a_step16);
+      bv[k] = b0 + (uint64_t)((k & 1) * b_step16);
+    }
     if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) umma_bf16(dv[k], av[k], bv[k], idesc, 0u);   // initialise accumulators
       t0 = clock64();
-      for (int it = 0; it < iters; ++it) {
-        const uint32_t d = tmem_base + (uint32_t)((it % n_acc) * acc_cols);
-        const uint64_t a = a0 + (uint64_t)((it % a_tiles) * a_tile16) + (uint64_t)((it & 1) * a_step16);
-        const uint64_t b = b0 + (uint64_t)((it & 1) * b_step16);
-        umma_bf16(d, a, b, idesc, it >= n_acc ? 1u : 0u);
+      for (int it = 0; it < iters; it += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(dv[k], av[k], bv[k], idesc, 1u);
       }
       umma_commit(&bar);
     }
@@ -55,7 +64,7 @@ umma_bench_kernel(uint32_t idesc, uint32_t desc_hi_a, uint32_t desc_hi_b, int a_
 // a_tiles > 1 cycles the A descriptor over that many different tiles (like the conv kernels' per-frame
 // chunks); n_acc accumulators of acc_cols columns are used round-robin.  Returns SM cycles for `iters` MMAs.
 extern "C" long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
-                                        int n_acc, int a_tiles, int iters, void* stream) {
+                                        int n_acc, int a_tiles, int iters, int a_shift_rows, void* stream) {
   if (!(M == 64 || M == 128) || N % 16 != 0 || N < 16 || N > 256) { lr_set_error("lr_umma_microbench: bad shape"); return -1; }
   int acc_cols = N < 32 ? 32 : N;
   if (n_acc < 1) n_acc = 1;
@@ -78,7 +87,7 @@ extern "C" long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_b
   cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaStream_t st = lr_stream(stream);
   umma_bench_kernel<<<1, 128, smem, st>>>(idesc, hi_a, hi_b, a_step16, b_step16, n_acc, acc_cols, iters, a_tiles,
-                                          a_tile16, d_out);
+                                          a_tile16, (a_shift_rows * row_bytes_a) >> 4, d_out);
   long long h = -3;
   if (cudaStreamSynchronize(st) == cudaSuccess) cudaMemcpy(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
   cudaFree(d_out);

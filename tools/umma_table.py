@@ -12,7 +12,7 @@ from lipreading_b200 import native  # noqa: E402
 L = native.lib()
 f = ctypes.CDLL(native.LIB_PATH).lr_umma_microbench
 f.restype = ctypes.c_longlong
-f.argtypes = [ctypes.c_int] * 9 + [ctypes.c_void_p]
+f.argtypes = [ctypes.c_int] * 10 + [ctypes.c_void_p]
 torch.zeros(1, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 iters = 2000
@@ -26,6 +26,12 @@ for (M, N, ra, rb, ma, mb, nacc, at) in [
     (64, 32, 128, 64, 1, 1, 8, 1), (64, 160, 128, 64, 1, 1, 3, 1), (64, 96, 128, 64, 1, 1, 5, 1), (64, 16, 64, 32, 1, 1, 8, 1),
     (64, 48, 64, 32, 1, 1, 8, 1), (128, 96, 128, 64, 1, 1, 2, 1), (128, 192, 128, 64, 1, 1, 2, 1), (128, 256, 128, 128, 1, 1, 2, 1),
 ]:
-    c = f(M, N, ra, rb, ma, mb, nacc, at, iters, st)
+    c = f(M, N, ra, rb, ma, mb, nacc, at, iters, 0, st)
     per = c / iters if c > 0 else float("nan")
     print(M, N, ra, rb, ma, mb, nacc, at, "->", "%.1f" % per, "%.0f" % (M * N * 16 / per if c > 0 else 0))
+
+print("row-shifted A operand (the conv kernels' tap shifts): M N rowA shift_rows -> cycles/MMA")
+for (M, N, ra, rb) in [(128, 64, 64, 64), (128, 96, 128, 128), (128, 32, 32, 32), (128, 32, 128, 128)]:
+    for sh in (0, 1, 2, 3, 4, 8, 16, 17):
+        c = f(M, N, ra, rb, 0, 0, 4, 1, iters, sh, st)
+        print(M, N, ra, sh, "->", "%.1f" % (c / iters))
