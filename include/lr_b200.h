@@ -159,7 +159,7 @@ int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W,
 /* Stride-1 "same" conv k=(KT,KH,KW) as a shifted-window implicit GEMM on tcgen05.
  *   x : zero-padded channel-grouped bf16 volume [CG][B][T+KT-1][Hp][Wp][Cin], Hp >= H+KH-1 (a
  *       multiple of 128/Wp), Wp a power of two >= W+KW-1, Cin in {16,32,64} per group;
- *   w : bf16 [Cout][CG][KT][KH][KW][Cin]; bias f32 (Cout) or NULL; Cout in {32,64,96,128};
+ *   w : weight tile images from lr_pack_conv_weights; bias f32 (Cout) or NULL; Cout in {32,64,96,128};
  *   epi_mode 0: bias + ReLU + MaxPool(1,2,2) -> bf16 written at offset (o_t,o_y,o_x) inside the
  *               output volume (B,oTp,oHp,oWp,Cout) [the next layer's padded input], plus one
  *               arg-max byte per pooled element (0..3, 4 = ReLU-dead) into argmax (may be NULL);
@@ -175,6 +175,9 @@ int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint
  * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
  * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass; d_bias (C) f32 or NULL receives
  * the per-channel sum (the conv bias gradient).                                                */
+/* bf16 [Cout][CG][taps][Cin] -> [CG][taps][Cout x Cin] tile images, 16-byte chunks pre-swizzled so a
+ * stage of taps is ONE contiguous bulk copy into shared memory (what lr_conv3d_fwd expects as `w`). */
+int lr_pack_conv_weights(const void* w, void* out, int Cout, int CG, int taps, int Cin, void* stream);
 /* Weight gradient: out[tap][64][Nc] fp32 = sum_p dy[p,:] (x) x[p+shift(tap),:] on tcgen05 (M=64,
  * MN-major operands), split over CTAs and reduced in a fixed order.  x [B][T+KT-1][Hp][Wp][Cx];
  * dy [Gy][B][T+KT-1][Hp][Wp][Cy] zero except its interior, which starts dy_off rows in.

@@ -23,6 +23,7 @@ N.register("lr_conv3d_supported", _i, [])
 N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 N.register("lr_unpool", _i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp])
 N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 21 + [_vp])
+N.register("lr_pack_conv_weights", _i, [_vp, _vp, _i, _i, _i, _i, _vp])
 N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 5)
 N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 6 + [_vp])
 
@@ -87,7 +88,13 @@ SWAP = False     # conv orientation: True = channels on the MMA M lanes, 128 pos
 
 def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
                   tag="conv", algo_macs=None, swap=None):
-    """Thin call into lr_conv3d_fwd (see include/lr_b200.h)."""
+    """Thin call into lr_conv3d_fwd (see include/lr_b200.h).  w: bf16 [Cout][CG][taps][Cin] (packed here)."""
+    taps = K[0] * K[1] * K[2]
+    w = N.cont(w)
+    assert w.dtype == torch.bfloat16 and w.numel() == Cout * CG * taps * Cin
+    wp = torch.empty_like(w)
+    N.check(N.lib().lr_pack_conv_weights(N.ptr(w), N.ptr(wp), Cout, CG, taps, Cin, N.stream()), "lr_pack_conv_weights")
+    w = wp
     rec = KERNEL_TIMING
     if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

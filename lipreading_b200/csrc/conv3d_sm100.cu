@@ -61,6 +61,7 @@ struct ConvParams {
   int oTp, oHp, oWp, o_t, o_y, o_x;   // output volume geometry / interior offset
   long long rows_per_group;    // B*Tp*Hp*Wp
   const float* bias;
+  const uint8_t* w_packed;     // [CG][taps] tile images of wtile_bytes each (swizzled like a TMA box load)
   __nv_bfloat16* y;
   uint8_t* argmax;
   uint32_t idesc;
@@ -137,8 +138,7 @@ __device__ __forceinline__ void epilogue_swapped(const ConvParams& p, uint32_t t
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                      const ConvParams p) {
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -201,10 +201,12 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           const int nt = min(p.tps, n_taps - tap0);
           lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / p.w_stages) & 1) ^ 1);
           if (elect_one()) {
-            lr_mbar_expect_tx(&bars[BAR_W_FULL + s], (uint32_t)(nt * p.Cout * p.row_bytes));
-            for (int i = 0; i < nt; ++i)
-              tma_load_2d(w_smem + (size_t)(s * p.tps + i) * p.wtile_bytes, &map_w, (g * n_taps + tap0 + i) * p.Cin,
-                          0, &bars[BAR_W_FULL + s]);
+            // weights arrive as pre-swizzled tile images (lr_pack_conv_weights): one contiguous bulk copy
+            // per stage instead of Cout narrow strided rows per tap
+            const uint32_t bytes = (uint32_t)(nt * p.wtile_bytes);
+            lr_mbar_expect_tx(&bars[BAR_W_FULL + s], bytes);
+            lr_bulk_g2s(w_smem + (size_t)(s * p.tps) * p.wtile_bytes,
+                        p.w_packed + (size_t)(g * n_taps + tap0) * p.wtile_bytes, bytes, &bars[BAR_W_FULL + s]);
           }
           __syncwarp();
         }
@@ -230,20 +232,19 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       tc_fence_after();
       uint32_t first = 0;      // accumulate flag: 0 for the very first tap of the item
       for (int g = 0; g < p.CG; ++g) {
+        int kt = 0, ky = 0, kx = 0;                       // running (kt,ky,kx) of the next tap: no divisions
         for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
           const int s = wn % p.w_stages;
           const int nt = min(p.tps, n_taps - tap0);
           lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / p.w_stages) & 1);
           tc_fence_after();
-          if (elect_one()) {
+          const bool issuer = elect_one();
+          if (true) {
             for (int i = 0; i < nt; ++i) {
-              const int tap = tap0 + i;
-              const int kt = tap / (p.KH * p.KW), r2 = tap - kt * (p.KH * p.KW);
-              const int ky = r2 / p.KW, kx = r2 - ky * p.KW;
               const uint64_t wd = w_desc0 + (uint64_t)((s * p.tps + i) * wtile16);
               const uint64_t ad = a_desc_set + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
                                                        (((uint32_t)(ky * p.Wp + kx) * row16x) >> 4));
-              for (int j = 0; j < jn; ++j) {
+              for (int j = 0; issuer && j < jn; ++j) {
                 const uint64_t aj = ad + (uint64_t)(j * chunk16);
                 const uint32_t d = d_base + (uint32_t)(j * p.acc_cols);
                 // swap: weights are the M-side operand, the 128 positions the N side
@@ -261,11 +262,11 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 }
               }
               first = 1u;
+              if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kt; } }
             }
-            umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
+            if (issuer) umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
           }
           __syncwarp();
-          first = 1u;
         }
       }
       if (elect_one()) {
@@ -390,6 +391,29 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
 }
 
+
+// ---- weight packing: [Cout][CG][taps][Cin] bf16 -> per-(group,tap) tile images [Cout][Cin] with the
+// 16-byte chunks XOR-swizzled exactly as a TMA box load with the matching swizzle mode would leave them
+// in shared memory (address bits [4:6] ^= bits [7:9] for 128 B rows, [4:5] ^= [7:8] for 64 B, [4] ^= [7]
+// for 32 B).  The conv kernel can then fetch a whole stage of taps with one contiguous bulk copy.
+__global__ void pack_conv_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                         int Cout, int CG, int taps, int Cin) {
+  const int chunks = Cin / 8;
+  const long long total = (long long)CG * taps * Cout * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    long long r = i / chunks;
+    const int row = (int)(r % Cout); r /= Cout;
+    const int tap = (int)(r % taps);
+    const int g = (int)(r / taps);
+    const int row_bytes = Cin * 2;
+    const int sw = row_bytes == 128 ? (row & 7) : (row_bytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    const uint4 v = *reinterpret_cast<const uint4*>(w + (((size_t)row * CG + g) * taps + tap) * Cin + ch * 8);
+    *reinterpret_cast<uint4*>(out + (((size_t)g * taps + tap) * Cout + row) * Cin + (ch ^ sw) * 8) = v;
+  }
+}
+
 // ---- clip preparation: u8 NDHWC -> /255 -> 2x2 space-to-depth -> zero-padded bf16 volume -------
 // out (B, T+2, Hp, Wp, 16): channel = (dy*2+dx)*3 + c for c<3, 12..15 = 0; interior at (1,1,1).
 __global__ void __launch_bounds__(256)
@@ -502,6 +526,16 @@ extern "C" int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, in
   return LR_OK;
 }
 
+extern "C" int lr_pack_conv_weights(const void* w, void* out, int Cout, int CG, int taps, int Cin, void* stream) {
+  LR_CHECK_ARG(w && out && (Cin == 16 || Cin == 32 || Cin == 64) && Cout > 0 && CG > 0 && taps > 0,
+               "lr_pack_conv_weights: bad args");
+  const long long total = (long long)CG * taps * Cout * (Cin / 8);
+  pack_conv_weights_kernel<<<lr_div_up(total, 256), 256, 0, lr_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(out), Cout, CG, taps, Cin);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
 extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_bias, int B, int T,
                          int H, int W, int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw,
                          void* stream) {
@@ -519,7 +553,8 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
 }
 
 // x: zero-padded, channel-grouped bf16 volume [CG][B][Tp][Hp][Wp][Cin] with Tp=T+KT-1, Hp >= H+KH-1
-// (a multiple of 128/Wp keeps tiles inside their plane), Wp = power of two >= W+KW-1.  w: [Cout][CG][KT][KH][KW][Cin] bf16 (K-major per output channel).
+// (a multiple of 128/Wp keeps tiles inside their plane), Wp = power of two >= W+KW-1.
+// w: tile images from lr_pack_conv_weights: [CG][KT*KH*KW][Cout rows x Cin] bf16, 16-byte chunks swizzled.
 extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
                              int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
                              int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
@@ -544,7 +579,8 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   LR_CHECK_ARG(p.CH <= 256, "lr_conv3d_fwd: halo too large for one TMA box (CH=%d)", p.CH);
   p.row_bytes = Cin * 2;
   p.chunk_bytes = (p.CH * p.row_bytes + 1023) / 1024 * 1024;
-  p.wtile_bytes = (Cout * p.row_bytes + 1023) / 1024 * 1024;
+  p.wtile_bytes = Cout * p.row_bytes;
+  LR_CHECK_ARG(p.wtile_bytes % 1024 == 0, "lr_conv3d_fwd: Cout*Cin*2 must be a multiple of 1024");
   p.stage_pitch = Cout * 2 + 16;
   p.swap = swap ? 1 : 0;
   p.Mt = Cout <= 64 ? 64 : 128;
@@ -608,18 +644,16 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.smem_off_bar = p.smem_off_stage + stage_bytes;
   const size_t smem_bytes = (size_t)p.smem_off_bar + 256 + 1024;
 
-  CUtensorMap map_x, map_w;
+  CUtensorMap map_x;
   int rc = make_map_2d(&map_x, x, (uint64_t)Cin, (uint64_t)p.rows_per_group * CG, (uint32_t)Cin, (uint32_t)p.CH,
                        p.row_bytes);
   if (rc != LR_OK) return rc;
-  rc = make_map_2d(&map_w, w, (uint64_t)CG * KT * KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cin, (uint32_t)Cout,
-                   p.row_bytes);
-  if (rc != LR_OK) return rc;
+  p.w_packed = reinterpret_cast<const uint8_t*>(w);
 
   LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes));
   int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  conv3d_tcgen05_kernel<<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, map_w, p);
+  conv3d_tcgen05_kernel<<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

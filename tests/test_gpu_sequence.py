@@ -58,15 +58,20 @@ def test_ctc_nll_and_grad(native_lib, cuda, ctc_kernel, B, T, C, Lmax):
     nll = LF.ctc_nll(lp_d, tgt.to(cuda), il.to(cuda), tl.to(cuda))
     (nll * w.to(cuda)).sum().backward()
     assert torch.allclose(nll.cpu().double(), nll_ref.detach(), atol=1e-4, rtol=1e-6), (nll.cpu(), nll_ref)
-    assert _relerr(lp_d.grad.cpu().double(), lp_ref.grad) < (1e-4 if T <= 100 else 3e-4)
-    # the same torch entry point the reference calls, in fp32, agrees within its own rounding
-    nll32 = O.ctc_nll_torch(lp, tgt, il, tl)
-    assert torch.allclose(nll.cpu(), nll32, atol=1e-3, rtol=1e-5)
+    # the same torch entry point the reference calls, in fp32: its own rounding error vs float64 sets the
+    # bar for long sequences (3.8e-4 at T=300, L=120) — the kernel must be no worse than 1.5x that
+    lp32 = lp.clone().requires_grad_(True)
+    nll32 = O.ctc_nll_torch(lp32, tgt, il, tl)
+    (nll32 * w).sum().backward()
+    ref32_err = _relerr(lp32.grad.double(), lp_ref.grad)
+    tol = max(1e-4, 1.5 * ref32_err)
+    assert _relerr(lp_d.grad.cpu().double(), lp_ref.grad) < tol, (tol, ref32_err)
+    assert torch.allclose(nll.cpu(), nll32.detach(), atol=1e-3, rtol=1e-5)
     # independent restatement (published recursion, float64) on sample 0
     n0, g0 = O.ctc_alpha_beta(lp[0, : int(il[0])].numpy(), tgt[0, : int(tl[0])].numpy())
     assert abs(float(nll[0].detach()) - n0) < 1e-4 * max(1.0, abs(n0))
     got = (lp_d.grad[0, : int(il[0])].cpu() / w[0]).numpy()
-    assert np.abs(got - g0).max() < (1e-4 if T <= 100 else 3e-4)
+    assert np.abs(got - g0).max() < tol
 
 
 def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda, ctc_kernel):
