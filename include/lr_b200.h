@@ -198,6 +198,9 @@ int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_b
 /* SM cycles for `iters` back-to-back tcgen05.mma of one shape with operands resident in shared memory
  * (tools/umma_table.py): the measured per-instruction cost that tile-orientation choices are based on.
  * Synchronous (the only entry point that is).                                                    */
+/* Device buffer (148*8 int64, or NULL to stop) that subsequent lr_conv3d_fwd launches fill with the
+ * cycles each warp role spent waiting on its barriers (tools/conv_waits.py).                      */
+void lr_conv3d_set_debug(long long* device_buffer);
 long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
                              int n_acc, int a_tiles, int iters, int a_shift_rows, void* stream);
 

@@ -61,6 +61,7 @@ struct ConvParams {
   int oTp, oHp, oWp, o_t, o_y, o_x;   // output volume geometry / interior offset
   long long rows_per_group;    // B*Tp*Hp*Wp
   const float* bias;
+  long long* dbg;              // optional [grid][8] cycle counters (lr_conv3d_set_debug): where the roles wait
   const uint8_t* w_packed;     // [CG][taps] tile images of wtile_bytes each (swizzled like a TMA box load)
   __nv_bfloat16* y;
   uint8_t* argmax;
@@ -70,6 +71,13 @@ struct ConvParams {
   int smem_off_w, smem_off_stage, smem_off_bar;
   int stage_pitch;             // bytes per staging row
 };
+
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { lr_mbar_wait(bar, parity); return; }
+  const long long t = clock64();
+  lr_mbar_wait(bar, parity);
+  acc += clock64() - t;
+}
 
 // barrier block layout (uint64 each)
 enum { BAR_A_FULL = 0, BAR_A_EMPTY = 2, BAR_ACC_FULL = 4, BAR_ACC_EMPTY = 6, BAR_W_FULL = 8,
@@ -170,6 +178,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool dbg_on = p.dbg != nullptr;
+  long long dbg0 = 0, dbg1 = 0, dbg2 = 0;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -183,7 +194,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
       const int n_chunks = jn + p.KT - 1;
       const int aset = it & (p.a_sets - 1);
       uint8_t* a_set = a_smem + (size_t)aset * p.a_set_bytes;
-      lr_mbar_wait(&bars[BAR_A_EMPTY + aset], ((it / p.a_sets) & 1) ^ 1);
+      timed_wait(&bars[BAR_A_EMPTY + aset], ((it / p.a_sets) & 1) ^ 1, dbg0, dbg_on);
       if (elect_one()) {
         lr_mbar_expect_tx(&bars[BAR_A_FULL + aset], (uint32_t)(n_chunks * p.CG * p.CH * p.row_bytes));
         for (int g = 0; g < p.CG; ++g)
@@ -199,7 +210,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
         for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
           const int s = wn % p.w_stages;
           const int nt = min(p.tps, n_taps - tap0);
-          lr_mbar_wait(&bars[BAR_W_EMPTY + s], ((wn / p.w_stages) & 1) ^ 1);
+          timed_wait(&bars[BAR_W_EMPTY + s], ((wn / p.w_stages) & 1) ^ 1, dbg1, dbg_on);
           if (elect_one()) {
             // weights arrive as pre-swizzled tile images (lr_pack_conv_weights): one contiguous bulk copy
             // per stage instead of Cout narrow strided rows per tap
@@ -225,10 +236,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0);
       const int set = it & (p.n_sets - 1);
       const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
-      lr_mbar_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1);
+      timed_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1, dbg0, dbg_on);
       const int aset = it & (p.a_sets - 1);
       const uint64_t a_desc_set = a_desc0 + (uint64_t)(aset * (p.a_set_bytes >> 4));
-      lr_mbar_wait(&bars[BAR_A_FULL + aset], (it / p.a_sets) & 1);
+      timed_wait(&bars[BAR_A_FULL + aset], (it / p.a_sets) & 1, dbg1, dbg_on);
       tc_fence_after();
       uint32_t first = 0;      // accumulate flag: 0 for the very first tap of the item
       for (int g = 0; g < p.CG; ++g) {
@@ -236,7 +247,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
         for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
           const int s = wn % p.w_stages;
           const int nt = min(p.tps, n_taps - tap0);
-          lr_mbar_wait(&bars[BAR_W_FULL + s], (wn / p.w_stages) & 1);
+          timed_wait(&bars[BAR_W_FULL + s], (wn / p.w_stages) & 1, dbg2, dbg_on);
           tc_fence_after();
           const bool issuer = elect_one();
           if (true) {
@@ -290,7 +301,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
       const int set = it & (p.n_sets - 1);
       const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
-      lr_mbar_wait(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1);
+      timed_wait(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1, dbg0, dbg_on);
       tc_fence_after();
       if (p.swap) {
         for (int j = 0; j < jn; ++j) {
@@ -456,7 +467,9 @@ __global__ void __launch_bounds__(256)
 unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restrict__ argmax,
               __nv_bfloat16* __restrict__ out, float* __restrict__ d_bias, int B, int T, int H, int W, int C,
               int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw) {
-  // bias gradient = sum of the routed gradients per channel: accumulated per block in shared memory
+  // bias gradient = per-channel sum of the routed gradients.  The grid stride is a multiple of C/8, so a
+  // thread keeps the same 8-channel group for its whole loop: accumulate in registers, then one shared
+  // and one global atomic per (thread|block, channel).
   __shared__ float bias_acc[128];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) bias_acc[i] = 0.f;
   __syncthreads();
@@ -464,9 +477,11 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
   const int c8 = C >> 3;
   const long long total = (long long)B * T * H * W * c8;     // one thread per (full-res pixel, 8 ch)
   const long long rows_per_group = (long long)B * Tp * Hp * Wp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(i % c8);
+  float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int my_cg = (int)(first % c8);
+  for (long long i = first; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = my_cg;
     long long r = i / c8;
     int x = (int)(r % W); r /= W;
     int y = (int)(r % H); r /= H;
@@ -486,7 +501,7 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
       for (int e = 0; e < 8; ++e) {
         const bool hit = ae[e] == which;
         v[e] = hit ? ge[e] : __float2bfloat16(0.f);
-        if (hit && d_bias) atomicAdd(&bias_acc[cg * 8 + e], __bfloat162float(ge[e]));
+        if (hit) bsum[e] += __bfloat162float(ge[e]);
       }
     } else {
 #pragma unroll
@@ -497,12 +512,20 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
     const size_t opix = (size_t)g * rows_per_group + (((size_t)b * Tp + (t + pt)) * Hp + (y + ph)) * Wp + (x + pw);
     *reinterpret_cast<uint4*>(out + opix * Cg + cl) = *reinterpret_cast<const uint4*>(v);
   }
-  __syncthreads();
-  if (d_bias)
+  if (d_bias) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&bias_acc[my_cg * 8 + e], bsum[e]);
+    __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&d_bias[i], bias_acc[i]);
+  }
 }
 
 }  // namespace
+
+static long long* g_conv_dbg = nullptr;
+// diagnostics: device buffer of 148*8 int64 that the next conv launches fill with per-role wait cycles
+// [producer a_empty, producer w_empty, mma acc_empty, mma a_full, mma w_full, epilogue acc_full, -, mma total]
+extern "C" void lr_conv3d_set_debug(long long* device_buffer) { g_conv_dbg = device_buffer; }
 
 extern "C" int lr_conv3d_supported(void) {
   int dev = 0;
@@ -545,6 +568,8 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
   long long total = (long long)B * T * H * W * (C / 8);
   int grid = lr_div_up(total, 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  const int c8 = C / 8;
+  grid = (grid + c8 - 1) / c8 * c8;         // grid*256 is then a multiple of C/8: fixed channel group per thread
   unpool_kernel<<<grid, 256, 0, lr_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(d_pooled), argmax,
                                                      reinterpret_cast<__nv_bfloat16*>(out), d_bias, B, T, H, W,
                                                      C, Cg, Tp, Hp, Wp, pt, ph, pw);
@@ -649,6 +674,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
                        p.row_bytes);
   if (rc != LR_OK) return rc;
   p.w_packed = reinterpret_cast<const uint8_t*>(w);
+  p.dbg = g_conv_dbg;
 
   LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes));

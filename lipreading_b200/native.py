@@ -29,6 +29,7 @@ SIGNATURES = {
     "lr_last_error": (ctypes.c_char_p, []),
     "lr_launch_count": (_u64, []),
     "lr_ctc_workspace": (_sz, [_i, _i, _i, _i]),
+    "lr_conv3d_set_debug": (None, [_vp]),
     "lr_umma_microbench": (ctypes.c_longlong, [_i] * 10 + [_vp]),
     "lr_ctc_select_kernel": (None, [_i]),
     "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
