@@ -82,6 +82,18 @@ __device__ __forceinline__ float lr_lse3(float a, float b, float c) {
   return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
+// fast variants (MUFU ex2/lg2 based): 4-5x fewer instructions; accurate enough for chains of <= ~128 steps
+__device__ __forceinline__ float lr_lse2_fast(float a, float b) {
+  float m = fmaxf(a, b);
+  if (m == LR_NEG_INF) return LR_NEG_INF;
+  return m + __logf(__expf(a - m) + __expf(b - m));
+}
+__device__ __forceinline__ float lr_lse3_fast(float a, float b, float c) {
+  float m = fmaxf(a, fmaxf(b, c));
+  if (m == LR_NEG_INF) return LR_NEG_INF;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
 // ---- mbarrier / bulk-async (TMA) primitives ---------------------------------------------
 __device__ __forceinline__ void lr_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lr_smem_u32(bar)), "r"(count));

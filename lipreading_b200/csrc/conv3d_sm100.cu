@@ -394,6 +394,12 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
     }
   }
 
+  if (dbg_on && lane == 0 && warp <= 2) {
+    long long* o = p.dbg + (size_t)blockIdx.x * 8;
+    if (warp == 0) { o[0] = dbg0; o[1] = dbg1; }                       // producer: a_empty, w_empty
+    if (warp == 1) { o[2] = dbg0; o[3] = dbg1; o[4] = dbg2; o[7] = clock64() - t_start; }   // mma: acc_empty, a_full, w_full
+    if (warp == 2) { o[5] = dbg0; }                                    // epilogue: acc_full
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

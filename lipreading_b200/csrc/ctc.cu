@@ -276,7 +276,7 @@ ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __re
 // clip's log-probs are read twice from L2/HBM and the gradient written once — nothing else moves.
 // A CTA is a single warp: ~20 KB of shared memory per clip lets ~11 clips share an SM, which is what
 // hides the 75-step dependent chain (the kernel is latency-bound per clip, throughput-bound per SM).
-template <int P>
+template <int P, bool FAST>
 __global__ void __launch_bounds__(32)
 ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
                 const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens, int B, int T, int C,
@@ -363,8 +363,8 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
     if (lane == 0) prev_lab = LR_NEG_INF;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      const float nb = has_blank[i] ? lr_lse2(ab[i], prev_lab) + lpb : LR_NEG_INF;
-      const float nl = has_lab[i] ? lr_lse3(al[i], ab[i], skipa[i] ? prev_lab : LR_NEG_INF) + row[lab[i]]
+      const float nb = has_blank[i] ? (FAST ? lr_lse2_fast : lr_lse2)(ab[i], prev_lab) + lpb : LR_NEG_INF;
+      const float nl = has_lab[i] ? (FAST ? lr_lse3_fast : lr_lse3)(al[i], ab[i], skipa[i] ? prev_lab : LR_NEG_INF) + row[lab[i]]
                                   : LR_NEG_INF;
       prev_lab = al[i];
       ab[i] = nb;
@@ -378,7 +378,7 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
     const float* last = alpha + (size_t)(Tb - 1) * SP;
     const float l1 = last[S - 1];
     const float l2 = S > 1 ? last[S - 2] : LR_NEG_INF;
-    nll = -lr_lse2(l1, l2);
+    nll = -(FAST ? lr_lse2_fast : lr_lse2)(l1, l2);
   }
   if (lane == 0) nll_out[b] = nll;
   if (g_b == nullptr) return;
@@ -417,9 +417,9 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
       for (int i = P - 1; i >= 0; --i) {
         const float right_blank = (i + 1 < P) ? bb[i + 1] : nb_blank;
         const float right_lab = (i + 1 < P) ? bl[i + 1] : nb_lab;
-        nlv[i] = has_lab[i] ? lr_lse3(bl[i], right_blank, skipb[i] ? right_lab : LR_NEG_INF) + row[lab[i]]
+        nlv[i] = has_lab[i] ? (FAST ? lr_lse3_fast : lr_lse3)(bl[i], right_blank, skipb[i] ? right_lab : LR_NEG_INF) + row[lab[i]]
                             : LR_NEG_INF;
-        nbv[i] = has_blank[i] ? lr_lse2(bb[i], bl[i]) + lpb : LR_NEG_INF;
+        nbv[i] = has_blank[i] ? (FAST ? lr_lse2_fast : lr_lse2)(bb[i], bl[i]) + lpb : LR_NEG_INF;
       }
 #pragma unroll
       for (int i = 0; i < P; ++i) { bb[i] = nbv[i]; bl[i] = nlv[i]; }
@@ -541,10 +541,17 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
       cudaStream_t st = lr_stream(stream);
 #define LR_LAUNCH_WARP(PP)                                                                                   \
   do {                                                                                                       \
-    LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                       (int)sm));                                                            \
-    ctc_warp_kernel<PP><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll,  \
-                                            grad);                                                            \
+    if (T <= 128) {          /* fast exp/log: chains this short stay inside the 1e-4 parity bar */     \
+      LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)sm));                                                          \
+      ctc_warp_kernel<PP, true><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax,  \
+                                                    nll, grad);                                               \
+    } else {                                                                                                 \
+      LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)sm));                                                          \
+      ctc_warp_kernel<PP, false><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, \
+                                                     nll, grad);                                              \
+    }                                                                                                        \
   } while (0)
       if (P == 1) LR_LAUNCH_WARP(1);
       else if (P == 2) LR_LAUNCH_WARP(2);
