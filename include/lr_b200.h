@@ -50,8 +50,8 @@ uint64_t    lr_launch_count(void);
  * grad (B,T,C) f32 or NULL: d nll_b / d log_probs with torch's native-CTC convention
  *   exp(lp) - exp(log(alpha*beta summed per class) + nll - lp), zero for t >= input_len.     */
 size_t lr_ctc_workspace(int B, int T, int C, int Lmax);
-/* 0 (default): warp-per-clip kernel when the lattice fits shared memory, else CTA-per-clip;
- * 1: always the CTA-per-clip kernel (test hook).                                                */
+/* 0 (default): warp-per-clip kernel for large batches (>= 1024 clips) whose lattice fits shared
+ * memory, else CTA-per-clip; 1: always CTA-per-clip; 2: warp-per-clip whenever it fits (test hooks). */
 void lr_ctc_select_kernel(int force_block);
 int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lens,
                    const int32_t* target_lens, int B, int T, int C, int Lmax,

@@ -21,8 +21,9 @@
 //   are never stored (their windows wrap across rows, which is harmless).
 // The same kernel run on the un-pooled output gradient with flipped/transposed weights is dgrad.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
-// lane), warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).
+// Warp roles (288 threads): warp 0 = TMA producer, warps 1-4 = MMA issuers (one elected lane each,
+// accumulator j belongs to issuer j % 4; warp 1 also owns the TMEM allocation), warps 5-8 = epilogue
+// (TMEM lane quarter = warp_id % 4).
 #include "tcgen05.cuh"
 #include <string.h>
 
@@ -30,7 +31,8 @@ using namespace lr_tc;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kMmaWarps = 4;                      // MMA-issuing warps (accumulator j is issued by warp j % 4)
+constexpr int kThreads = 32 * (1 + kMmaWarps + 4); // producer + issuers + 4 epilogue warps
 constexpr int kMaxChunks = 16;   // (J + KT - 1) * channel groups
 constexpr int kWStages = 4;
 
@@ -163,13 +165,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       lr_mbar_init(&bars[BAR_A_FULL + i], 1);
-      lr_mbar_init(&bars[BAR_A_EMPTY + i], 1);
-      lr_mbar_init(&bars[BAR_ACC_FULL + i], 1);
+      lr_mbar_init(&bars[BAR_A_EMPTY + i], kMmaWarps);
+      lr_mbar_init(&bars[BAR_ACC_FULL + i], kMmaWarps);
       lr_mbar_init(&bars[BAR_ACC_EMPTY + i], 4);
     }
     for (int s = 0; s < kWStages; ++s) {
       lr_mbar_init(&bars[BAR_W_FULL + s], 1);
-      lr_mbar_init(&bars[BAR_W_EMPTY + s], 1);
+      lr_mbar_init(&bars[BAR_W_EMPTY + s], kMmaWarps);
     }
     lr_fence_barrier_init();
   }
@@ -222,8 +224,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
           __syncwarp();
         }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+  } else if (warp <= kMmaWarps) {
+    // ===================== MMA issuers: warp m issues accumulators j = m, m+4, ... ======================
+    // (one thread cannot feed the tensor pipe for N < 128: ~20 scalar instructions per small MMA)
+    const int mw = warp - 1;
     uint32_t wn = 0;
     int it = 0;
     const uint64_t a_desc0 = make_desc(lr_smem_u32(a_smem), p.desc_hi);
@@ -255,7 +259,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
               const uint64_t wd = w_desc0 + (uint64_t)((s * p.tps + i) * wtile16);
               const uint64_t ad = a_desc_set + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
                                                        (((uint32_t)(ky * p.Wp + kx) * row16x) >> 4));
-              for (int j = 0; issuer && j < jn; ++j) {
+              for (int j = mw; issuer && j < jn; j += kMmaWarps) {
                 const uint64_t aj = ad + (uint64_t)(j * chunk16);
                 const uint32_t d = d_base + (uint32_t)(j * p.acc_cols);
                 // swap: weights are the M-side operand, the 128 positions the N side
@@ -289,7 +293,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
   } else {
     // ===================== epilogue (4 warps) =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int etid = (warp - 2) * 32 + lane;      // 0..127 among epilogue threads
+    const int etid = (warp - 1 - kMmaWarps) * 32 + lane;      // 0..127 among epilogue threads
     const int row = q * 32 + lane;                // accumulator row (tile position) held by this thread
     const int PW = p.W >> 1;
     const int cgroups = p.Cout >> 3;
@@ -394,11 +398,11 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
     }
   }
 
-  if (dbg_on && lane == 0 && warp <= 2) {
+  if (dbg_on && lane == 0 && (warp <= 1 || warp == 1 + kMmaWarps)) {
     long long* o = p.dbg + (size_t)blockIdx.x * 8;
     if (warp == 0) { o[0] = dbg0; o[1] = dbg1; }                       // producer: a_empty, w_empty
     if (warp == 1) { o[2] = dbg0; o[3] = dbg1; o[4] = dbg2; o[7] = clock64() - t_start; }   // mma: acc_empty, a_full, w_full
-    if (warp == 2) { o[5] = dbg0; }                                    // epilogue: acc_full
+    if (warp == 1 + kMmaWarps) { o[5] = dbg0; }                        // epilogue: acc_full
   }
   tc_fence_before();
   __syncthreads();

@@ -23,7 +23,8 @@ using namespace lr_tc;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kMmaWarps = 4;                       // issuing warps: accumulator unit j belongs to warp j % 4
+constexpr int kThreads = 32 * (1 + kMmaWarps + 4);
 constexpr int kStages = 3;
 constexpr int kMaxGroups = 32;
 
@@ -84,9 +85,9 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       lr_mbar_init(&bars[BAR_FULL + s], 1);
-      lr_mbar_init(&bars[BAR_EMPTY + s], 1);
+      lr_mbar_init(&bars[BAR_EMPTY + s], kMmaWarps);
     }
-    lr_mbar_init(&bars[BAR_ACC], 1);
+    lr_mbar_init(&bars[BAR_ACC], kMmaWarps);
     lr_fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -120,8 +121,9 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // MMA issuer: warp-uniform loop, one elected lane issues
+  } else if (warp <= kMmaWarps) {
+    // MMA issuers: warp-uniform loops, one elected lane each; unit j is issued by warp j % kMmaWarps
+    const int mw = warp - 1;
     uint32_t n = 0;
     const uint32_t m_step = (uint32_t)(16 * p.m.row_bytes) >> 4, n_step = (uint32_t)(16 * p.n.row_bytes) >> 4;
     for (int tile = split; tile < p.n_tiles; tile += p.splits, ++n) {
@@ -133,7 +135,7 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
       const uint64_t nd0 = make_desc_lbo(m_addr + (uint32_t)m_bytes, (uint32_t)p.n.lbo_bytes, p.n.desc_hi);
       const uint32_t acc0 = n == 0 ? 0u : 1u;
       if (elect_one()) {
-        for (int j = 0; j < ntap; ++j) {
+        for (int j = mw; j < ntap; j += kMmaWarps) {
           const int unit = tap_lo + j;
           const int ky = p.stack > 1 ? unit : unit / p.KW, kx = p.stack > 1 ? 0 : unit - ky * p.KW;
           const uint32_t shift = (uint32_t)(ky * p.Wp + kx);

@@ -16,7 +16,7 @@
 // HBM traffic is exactly the algorithmic 2*T*C*4 bytes per clip (39 000 B at T=75,C=65).
 #include "common.cuh"
 
-int lr_ctc_force_block_kernel = 0;   // tests flip this to exercise the CTA-per-clip kernel
+int lr_ctc_force_block_kernel = 0;   // 0 auto (by batch size), 1 always CTA-per-clip, 2 always warp-per-clip
 
 namespace {
 
@@ -537,7 +537,9 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
     const int S = 2 * Lmax + 1;
     const int P = S <= 64 ? 1 : (S <= 128 ? 2 : (S <= 256 ? 4 : 0));
     const size_t sm = P ? warp_kernel_smem(T, C, P) : 0;
-    if (P && sm <= 100 * 1024 && !lr_ctc_force_block_kernel) {
+    // one warp per clip maximises clips in flight per SM (throughput); with few clips the CTA-per-clip kernel
+    // (alpha and beta on two warps, 4-warp gradient) has the shorter critical path
+    if (P && sm <= 100 * 1024 && lr_ctc_force_block_kernel != 1 && (B >= 1024 || lr_ctc_force_block_kernel == 2)) {
       cudaStream_t st = lr_stream(stream);
 #define LR_LAUNCH_WARP(PP)                                                                                   \
   do {                                                                                                       \

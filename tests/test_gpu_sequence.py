@@ -32,7 +32,7 @@ def _relerr(a, b):
 @pytest.fixture(params=["warp_per_clip", "cta_per_clip"])
 def ctc_kernel(request, native_lib):
     """Both CTC kernels: warp-per-clip (default when the lattice fits) and CTA-per-clip (any size)."""
-    native_lib.lr_ctc_select_kernel(1 if request.param == "cta_per_clip" else 0)
+    native_lib.lr_ctc_select_kernel(1 if request.param == "cta_per_clip" else 2)
     yield request.param
     native_lib.lr_ctc_select_kernel(0)
 
