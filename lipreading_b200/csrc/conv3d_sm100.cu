@@ -440,25 +440,26 @@ __global__ void pack_conv_weights_kernel(const __nv_bfloat16* __restrict__ w, __
 __global__ void __launch_bounds__(256)
 clip_s2d_kernel(const uint8_t* __restrict__ clip, __nv_bfloat16* __restrict__ out, int B, int T, int H,
                 int W, int Hp, int Wp) {
+  // u8 -> bf16(x/255) through an exact 256-entry table (no per-element division)
+  __shared__ __nv_bfloat16 lut[256];
+  if (threadIdx.x < 256) lut[threadIdx.x] = __float2bfloat16((float)threadIdx.x / 255.0f);
+  __syncthreads();
   const int H2 = H >> 1, W2 = W >> 1;
-  const long long total = (long long)B * T * H2 * W2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int X = (int)(i % W2);
-    long long r = i / W2;
-    int Y = (int)(r % H2);
-    r /= H2;
-    int t = (int)(r % T);
-    int b = (int)(r / T);
+  const int bt = blockIdx.y;
+  const int b = bt / T, t = bt - b * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H2 * W2; i += gridDim.x * blockDim.x) {
+    const int Y = i / W2, X = i - Y * W2;
     const uint8_t* src = clip + ((((size_t)b * T + t) * H + 2 * Y) * W + 2 * X) * 3;
     __align__(16) __nv_bfloat16 v[16];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          v[(dy * 2 + dx) * 3 + c] = __float2bfloat16((float)src[((size_t)dy * W + dx) * 3 + c] / 255.0f);
+    for (int dy = 0; dy < 2; ++dy) {
+      // the 2 pixels x 3 channels of this row are 6 contiguous bytes at an even address
+      const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src + (size_t)dy * W * 3);
+      const uint16_t p0 = s16[0], p1 = s16[1], p2 = s16[2];
+      v[dy * 6 + 0] = lut[p0 & 0xff]; v[dy * 6 + 1] = lut[p0 >> 8];
+      v[dy * 6 + 2] = lut[p1 & 0xff]; v[dy * 6 + 3] = lut[p1 >> 8];
+      v[dy * 6 + 4] = lut[p2 & 0xff]; v[dy * 6 + 5] = lut[p2 >> 8];
+    }
 #pragma unroll
     for (int c = 12; c < 16; ++c) v[c] = __float2bfloat16(0.f);
     size_t opix = (((size_t)b * (T + 2) + (t + 1)) * Hp + (Y + 1)) * Wp + (X + 1);
@@ -485,18 +486,21 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
   __syncthreads();
   const int PH = H >> 1, PW = W >> 1;
   const int c8 = C >> 3;
-  const long long total = (long long)B * T * H * W * c8;     // one thread per (full-res pixel, 8 ch)
   const long long rows_per_group = (long long)B * Tp * Hp * Wp;
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int my_cg = (int)(first % c8);
-  for (long long i = first; i < total; i += (long long)gridDim.x * blockDim.x) {
+  // blockIdx.y = frame (b,t); threads stride over the frame's H*W*(C/8) elements.  The stride is a
+  // multiple of C/8, so the channel group is fixed per thread and (y,x) advance incrementally.
+  const int bt = blockIdx.y;
+  const int b = bt / T, t = bt - b * T;
+  const int plane = H * W * c8;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  const int my_cg = first % c8;
+  const int pstep = stride / c8, dy = pstep / W, dx = pstep - dy * W;
+  int pix = first / c8;
+  int y = pix / W, x = pix - y * W;
+  for (int i = first; i < plane; i += stride) {
     const int cg = my_cg;
-    long long r = i / c8;
-    int x = (int)(r % W); r /= W;
-    int y = (int)(r % H); r /= H;
-    int t = (int)(r % T);
-    int b = (int)(r / T);
     __align__(16) __nv_bfloat16 v[8];
     const int py = y >> 1, px = x >> 1;
     const bool inside = py < PH && px < PW;
@@ -521,6 +525,8 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
     const int g = c0 / Cg, cl = c0 - g * Cg;
     const size_t opix = (size_t)g * rows_per_group + (((size_t)b * Tp + (t + pt)) * Hp + (y + ph)) * Wp + (x + pw);
     *reinterpret_cast<uint4*>(out + opix * Cg + cl) = *reinterpret_cast<const uint4*>(v);
+    x += dx; y += dy;
+    if (x >= W) { x -= W; ++y; }
   }
   if (d_bias) {
 #pragma unroll
@@ -550,9 +556,8 @@ extern "C" int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, in
   LR_CHECK_ARG(clip && out_bf16 && B > 0 && T > 0 && H > 0 && W > 0 && (H % 2) == 0 && (W % 2) == 0,
                "lr_clip_s2d: H and W must be even");
   LR_CHECK_ARG(Wp >= W / 2 + 2 && Hp >= H / 2 + 2, "lr_clip_s2d: padded extents too small");
-  long long total = (long long)B * T * (H / 2) * (W / 2);
-  int grid = lr_div_up(total, 256);
-  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  LR_CHECK_ARG(B * T <= 65535, "lr_clip_s2d: B*T must be <= 65535");
+  dim3 grid(lr_div_up((H / 2) * (W / 2), 256), B * T);
   clip_s2d_kernel<<<grid, 256, 0, lr_stream(stream)>>>(clip, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, T,
                                                        H, W, Hp, Wp);
   LR_CHECK_LAUNCH();
@@ -575,11 +580,12 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
   LR_CHECK_ARG(d_pooled && argmax && out && C % 8 == 0 && Cg % 8 == 0 && C % Cg == 0 && C <= 128,
                "lr_unpool: bad args");
   if (d_bias) LR_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * C, lr_stream(stream)));
-  long long total = (long long)B * T * H * W * (C / 8);
-  int grid = lr_div_up(total, 256);
-  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   const int c8 = C / 8;
-  grid = (grid + c8 - 1) / c8 * c8;         // grid*256 is then a multiple of C/8: fixed channel group per thread
+  LR_CHECK_ARG(B * T <= 65535, "lr_unpool: B*T must be <= 65535");
+  int gx = lr_div_up((long long)H * W * c8, 256 * 2);   // ~2 elements per thread per frame
+  if (gx < 1) gx = 1;
+  gx = (gx + c8 - 1) / c8 * c8;             // gx*256 is then a multiple of C/8: fixed channel group per thread
+  dim3 grid(gx, B * T);
   unpool_kernel<<<grid, 256, 0, lr_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(d_pooled), argmax,
                                                      reinterpret_cast<__nv_bfloat16*>(out), d_bias, B, T, H, W,
                                                      C, Cg, Tp, Hp, Wp, pt, ph, pw);
