@@ -490,15 +490,17 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   // blockIdx.y = frame (b,t); threads stride over the frame's H*W*(C/8) elements.  The stride is a
   // multiple of C/8, so the channel group is fixed per thread and (y,x) advance incrementally.
-  const int bt = blockIdx.y;
-  const int b = bt / T, t = bt - b * T;
   const int plane = H * W * c8;
   const int first = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
   const int my_cg = first % c8;
   const int pstep = stride / c8, dy = pstep / W, dx = pstep - dy * W;
-  int pix = first / c8;
-  int y = pix / W, x = pix - y * W;
+  const int pix0 = first / c8;
+  const int y_first = pix0 / W, x_first = pix0 - y_first * W;
+  // blockIdx.y strides over frames: few blocks, so the bias partial sums stay in registers for long
+  for (int bt = blockIdx.y; bt < B * T; bt += gridDim.y) {
+  const int b = bt / T, t = bt - b * T;
+  int y = y_first, x = x_first;
   for (int i = first; i < plane; i += stride) {
     const int cg = my_cg;
     __align__(16) __nv_bfloat16 v[8];
@@ -527,6 +529,7 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
     *reinterpret_cast<uint4*>(out + opix * Cg + cl) = *reinterpret_cast<const uint4*>(v);
     x += dx; y += dy;
     if (x >= W) { x -= W; ++y; }
+  }
   }
   if (d_bias) {
 #pragma unroll
@@ -581,11 +584,13 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
                "lr_unpool: bad args");
   if (d_bias) LR_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * C, lr_stream(stream)));
   const int c8 = C / 8;
-  LR_CHECK_ARG(B * T <= 65535, "lr_unpool: B*T must be <= 65535");
   int gx = lr_div_up((long long)H * W * c8, 256 * 2);   // ~2 elements per thread per frame
   if (gx < 1) gx = 1;
   gx = (gx + c8 - 1) / c8 * c8;             // gx*256 is then a multiple of C/8: fixed channel group per thread
-  dim3 grid(gx, B * T);
+  int gy = kNumSMs * 16 / gx;
+  if (gy < 1) gy = 1;
+  if (gy > B * T) gy = B * T;
+  dim3 grid(gx, gy);
   unpool_kernel<<<grid, 256, 0, lr_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(d_pooled), argmax,
                                                      reinterpret_cast<__nv_bfloat16*>(out), d_bias, B, T, H, W,
                                                      C, Cg, Tp, Hp, Wp, pt, ph, pw);
