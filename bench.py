@@ -241,6 +241,7 @@ def kernel_rooflines(dev, pk, char2idx):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: exactly one JSON line
     args = parse()
     from lipreading_b200.vocab import build_char2idx
     char2idx = build_char2idx()
@@ -361,6 +362,10 @@ def main():
     e2e_value = world * args.batch * T_FRAMES * args.steps / (float(te) * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
+    if world > 1:
+        torch.distributed.barrier()
+        if rank != 0:
+            torch.distributed.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (conv3d_tcgen05_kernel) -----------------------------
@@ -374,9 +379,19 @@ def main():
     tot_s = sum(v[0] for v in per.values())
     tot_f = sum(v[1] for v in per.values())
     peak = pk["bf16_tflops_sustained"]
+    # DRAM traffic of the largest launch (conv2.fwd) from the committed `ncu --set full` capture
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_conv_b256.json")) as fh:
+            cap = json.load(fh)["conv2.fwd"]
+        if args.batch == 256:
+            traffic = {"bytes_per_launch": (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6, "launch": "conv2.fwd",
+                       "source": "profiles/r1_ncu_full_conv_b256.json"}
+    except Exception:
+        pass
     roofline = {"kernel": "conv3d_tcgen05_kernel (5 launches/step: conv1-3 fwd, conv3/conv2 dgrad)",
                 "bound": "tensor", "achieved": tot_f / tot_s / 1e12 if tot_s else None, "peak": peak,
-                "unit": "TFLOP/s", "frac": (tot_f / tot_s / 1e12 / peak) if tot_s else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": (tot_f / tot_s / 1e12 / peak) if tot_s else None, "traffic": traffic,
                 "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "share_of_step": tot_s / (ms * 1e-3),
                 "per_launch": {k: {"ms": v[0] / v[2] * 1e3, "tflops": v[1] / v[0] / 1e12} for k, v in per.items()}}
@@ -393,10 +408,23 @@ def main():
                                 "sample": "%d clips/step (same shapes), 1 warm-up + 2 timed steps" % args.cpu_batch}
     if world == 1 and not args.no_kernels:
         try:
+            # BASELINE config 5: frames -> characters inference stream (conv front-end -> BiGRU -> greedy CTC)
+            from lipreading_b200.infer import Recognizer
+            rec = Recognizer(enc, char2idx)
+            clips_d, lens_d = resident[0][0], resident[0][1]
+            s_inf = time_cuda(lambda: rec.tokens(clips_d, lens_d), iters=5, warm=2)
+            line["inference_stream"] = {"value": args.batch * T_FRAMES / s_inf, "unit": "frames/s",
+                                        "ms_per_batch": s_inf * 1e3, "what": "u8 clips resident -> token ids, greedy CTC"}
+            enc.train()
+        except Exception as e:
+            line["inference_error"] = repr(e)
+        try:
             line["kernels"] = kernel_rooflines(dev, pk, char2idx)
         except Exception as e:           # micro-benches must never lose the headline
             line["kernels_error"] = repr(e)
     print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
