@@ -26,6 +26,7 @@
 // (TMEM lane quarter = warp_id % 4).
 #include "tcgen05.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 using namespace lr_tc;
 
@@ -638,6 +639,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   int fixed = 2 * p.wtile_bytes + stage_bytes + 256;      // at least a 2-deep ring of single taps
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
   int n_sets = (512 / p.acc_cols) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
+  if (getenv("LR_CONV_SETS")) { int v = atoi(getenv("LR_CONV_SETS")); if (v == 1 || (v == 2 && 512 / p.acc_cols >= 2)) n_sets = v; }   // tuning hook
   int Jmax = 512 / p.acc_cols / n_sets;
   if (J <= 0 || J > Jmax) J = Jmax;
   while (J > 1 && ((J + KT - 1) * CG > kMaxChunks || (J + KT - 1) * CG * p.chunk_bytes + fixed > smem_cap)) --J;

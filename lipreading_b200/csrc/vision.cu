@@ -88,10 +88,17 @@ warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ c
     double bot = (1.0 - dc) * v10 + dc * v11;
     res[ch] = (float)((1.0 - dr) * top + dr * bot);
   }
-  float* o = out + ((size_t)n * 65536 + pix) * 3;
-  o[0] = res[0];
-  o[1] = res[1];
-  o[2] = res[2];
+  // stage the CTA's 256 pixels x 3 floats in shared memory and write them as 192 coalesced float4
+  // (a direct 12-byte-strided store makes every warp store touch 12 partial sectors)
+  __shared__ __align__(16) float stage[256 * 3];
+  stage[threadIdx.x * 3 + 0] = res[0];
+  stage[threadIdx.x * 3 + 1] = res[1];
+  stage[threadIdx.x * 3 + 2] = res[2];
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    float4* o4 = reinterpret_cast<float4*>(out + ((size_t)n * 65536 + (size_t)blockIdx.x * 256) * 3);
+    lr_stg_stream_f4(o4 + threadIdx.x, reinterpret_cast<const float4*>(stage)[threadIdx.x]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
