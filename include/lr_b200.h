@@ -184,12 +184,17 @@ int lr_pack_conv_weights(const void* w, void* out, int Cout, int CG, int taps, i
  * m_is_x = 0: rows of out[tap] are output channels (needs Gy*Cy <= 64), columns the Cx inputs;
  * m_is_x = 1: rows are the Cx = 64 inputs, columns the Gy*Cy outputs.
  * stack_kx (m_is_x = 0): the KW kx-taps of a filter row share one MMA (N = KW*Cx, operand blocks
- * are the same tile shifted by one row each); out is then [KT*KH][64][KW][Cx].                  */
-size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits);
+ * are the same tile shifted by one row each); out is then [KT*KH][64][KW][Cx].
+ * stack_ky = S = 128/Cy (with stack_kx): S filter rows share one M = 128 MMA (M block b = the dY tile
+ * shifted by b image rows); out is [KT][ceil(KH/S)][S][Cy][KW][Cx] with block b of unit u holding
+ * ky = u*S + (S-1-b) (ky >= KH: scratch).  fuse_kt: one CTA accumulates all KT planes of a tile.
+ * lr_conv3d_wgrad_out_floats = elements of `out` (and of one split of the workspace).          */
+size_t lr_conv3d_wgrad_out_floats(int KT, int KH, int KW, int Nc, int stack_ky);
+size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits, int stack_ky);
 int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, size_t ws_bytes,
                     int B, int T, int H, int W, int Hp, int Wp, int Cx, int Cy, int Gy,
-                    long long dy_off, int KT, int KH, int KW, int m_is_x, int stack_kx, int splits,
-                    void* stream);
+                    long long dy_off, int KT, int KH, int KW, int m_is_x, int stack_kx, int stack_ky,
+                    int fuse_kt, int splits, void* stream);
 int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_bias, int B, int T,
               int H, int W, int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw,
               void* stream);

@@ -24,8 +24,9 @@ N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 N.register("lr_unpool", _i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp])
 N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 21 + [_vp])
 N.register("lr_pack_conv_weights", _i, [_vp, _vp, _i, _i, _i, _i, _vp])
-N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 5)
-N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 6 + [_vp])
+N.register("lr_conv3d_wgrad_out_floats", N._sz, [_i] * 5)
+N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 6)
+N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 8 + [_vp])
 
 LAYERS = (  # name, Cin, Cout, kernel, stride, pad
     ("conv1", 3, 32, (3, 5, 5), (1, 2, 2), (1, 2, 2)),
@@ -49,25 +50,41 @@ def _plane_rows(h_valid, k, wp):
 
 
 STACK_KX = True      # wgrad: fold the KW kx-taps of a filter row into one N = KW*Cx MMA
+STACK_KY = True      # wgrad: also fold 128/Cy filter rows into one M = 128 MMA (M = 64 is half rate)
 
 
-def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x, splits=0, stack_kx=None):
-    """Thin call into lr_conv3d_wgrad -> fp32 [taps][64][Nc] (Nc = Gy*Cy if m_is_x else Cx)."""
+def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x, splits=0, stack_kx=None,
+                        stack_ky=None):
+    """Thin call into lr_conv3d_wgrad -> fp32 [taps][rows][Nc]: rows = 64 input channels, Nc = Gy*Cy if
+    m_is_x; else rows = output channels (64, or Cy when ky-stacked) and Nc = Cx."""
     L = N.lib()
     Nc = Gy * Cy if m_is_x else Cx
-    taps = K[0] * K[1] * K[2]
-    stack = (STACK_KX if stack_kx is None else stack_kx) and not m_is_x and K[2] > 1 and K[2] * Cx <= 256
+    KT, KH, KW = K
+    taps = KT * KH * KW
+    stack = (STACK_KX if stack_kx is None else stack_kx) and not m_is_x and KW > 1 and KW * Cx <= 256
+    S = 128 // Cy if (stack and Gy == 1 and (STACK_KY if stack_ky is None else stack_ky)) else 1
+    U = -(-KH // S)
+    if S > 1 and (128 + (U * S - 1) * Wp + KW - 1 > 256 or -(-(H + min(S, KH) - 1) // (128 // Wp)) * (128 // Wp) > Hp):
+        S, U = 1, KH                                            # halo / plane height do not allow stacking
+    fuse_kt = S > 1 and KT * U * KW * Cx <= 512
     if splits <= 0:
-        units, n_mma = (K[1], K[2] * Cx) if stack else (K[1] * K[2], Nc)
-        groups = K[0] * -(-units // (512 // n_mma))
+        if S > 1:
+            groups = 1 if fuse_kt else KT * -(-U // (512 // (KW * Cx)))
+        else:
+            units, n_mma = (KH, KW * Cx) if stack else (KH * KW, Nc)
+            groups = KT * -(-units // (512 // n_mma))
         splits = max(1, 148 // groups)
-    ws = torch.empty(L.lr_conv3d_wgrad_workspace(K[0], K[1], K[2], Nc, splits), dtype=torch.uint8, device=x.device)
-    out = torch.empty((taps, 64, Nc), dtype=torch.float32, device=x.device)
+    ws = torch.empty(L.lr_conv3d_wgrad_workspace(KT, KH, KW, Nc, splits, S), dtype=torch.uint8, device=x.device)
+    out = torch.empty(L.lr_conv3d_wgrad_out_floats(KT, KH, KW, Nc, S), dtype=torch.float32, device=x.device)
     N.check(L.lr_conv3d_wgrad(N.ptr(x), N.ptr(dy), N.ptr(out), N.ptr(ws), ws.numel(), B, T, H, W, Hp, Wp, Cx, Cy,
-                              Gy, dy_off, K[0], K[1], K[2], m_is_x, int(stack), splits, N.stream()),
+                              Gy, dy_off, KT, KH, KW, m_is_x, int(stack), S, int(fuse_kt), splits, N.stream()),
             "lr_conv3d_wgrad")
+    if S > 1:                       # [KT][U][S(b)][Cy][KW][Cx], ky = u*S + S-1-b -> [taps][Cy][Cx]
+        out = out.reshape(KT, U, S, Cy, KW, Cx).flip(2).reshape(KT, U * S, Cy, KW, Cx)[:, :KH]
+        return out.permute(0, 1, 3, 2, 4).reshape(taps, Cy, Cx)
+    out = out.reshape(taps, 64, Nc)
     if stack:                       # [KT*KH][64][KW][Cx] -> [taps][64][Cx]
-        out = out.reshape(K[0] * K[1], 64, K[2], Cx).permute(0, 2, 1, 3).reshape(taps, 64, Cx)
+        out = out.reshape(KT * KH, 64, KW, Cx).permute(0, 2, 1, 3).reshape(taps, 64, Cx)
     return out
 
 

@@ -36,6 +36,8 @@ constexpr int kMmaWarps = 4;                      // MMA-issuing warps (accumula
 constexpr int kThreads = 32 * (1 + kMmaWarps + 4); // producer + issuers + 4 epilogue warps
 constexpr int kMaxChunks = 16;   // (J + KT - 1) * channel groups
 constexpr int kWStages = 4;
+constexpr int kMaxTaps = 80;
+constexpr int kEpiIters = 4;    // pooled (row,x,channel-group) items per epilogue thread: <= 32*16/128
 
 struct ConvParams {
   int B, T, H, W;              // valid (un-padded) extents, same for input and conv output
@@ -73,6 +75,10 @@ struct ConvParams {
   int row_bytes;
   int smem_off_w, smem_off_stage, smem_off_bar;
   int stage_pitch;             // bytes per staging row
+  int stage_bufs;              // 1 or 2 staging tiles (2: one named barrier per accumulator instead of two)
+  int cg_shift, wp_shift;      // log2(Cout/8) (or -1) and log2(Wp) for the plain-store epilogue
+  uint32_t tap_off[kMaxTaps];  // per tap: descriptor offset (16-byte units) of its window inside a chunk set
+                               // = kt * chunk + (ky*Wp + kx) rows — read with uniform constant loads
 };
 
 __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
@@ -148,8 +154,18 @@ __device__ __forceinline__ void epilogue_swapped(const ConvParams& p, uint32_t t
   }
 }
 
+// KS = Cin/16 K-steps per tap (1, 2, 4); SWAP = swapped orientation (weights on M)
+template <int KS, bool SWAP>
+__device__ __forceinline__ void mma_tap(uint32_t d, uint64_t a, uint64_t w, uint32_t idesc, uint32_t acc) {
+  const uint64_t ma = SWAP ? w : a, mb = SWAP ? a : w;
+  umma_bf16(d, ma, mb, idesc, acc);
+#pragma unroll
+  for (int k = 1; k < KS; ++k) umma_bf16(d, ma + 2 * k, mb + 2 * k, idesc, 1u);
+}
+
+template <int KS, bool SWAP>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParams p) {
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -158,10 +174,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
   uint8_t* stage = base + p.smem_off_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + p.smem_off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+  float* bias_s = reinterpret_cast<float*>(base + p.smem_off_bar + 256);      // [128], zeros without a bias
+  if (threadIdx.x < 128) bias_s[threadIdx.x] = (p.has_bias && (int)threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform (role dispatch, descriptor math on
+  // the uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_taps = p.KT * p.KH * p.KW;
-  const int ksteps = p.Cin / 16;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -226,15 +245,16 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
         }
     }
   } else if (warp <= kMmaWarps) {
-    // ===================== MMA issuers: warp m issues accumulators j = m, m+4, ... ======================
-    // (one thread cannot feed the tensor pipe for N < 128: ~20 scalar instructions per small MMA)
+    // ===================== MMA issuers: warp m issues accumulators j = m and m+4 ========================
+    // (one thread cannot feed the tensor pipe for N < 128; the per-MMA scalar work is kept to one 64-bit
+    // add: per-item descriptor bases + a per-tap offset table in constant memory)
     const int mw = warp - 1;
     uint32_t wn = 0;
     int it = 0;
     const uint64_t a_desc0 = make_desc(lr_smem_u32(a_smem), p.desc_hi);
     const uint64_t w_desc0 = make_desc(lr_smem_u32(w_smem), p.desc_hi);
     const uint32_t chunk16 = (uint32_t)p.chunk_bytes >> 4, wtile16 = (uint32_t)p.wtile_bytes >> 4;
-    const uint32_t row16x = (uint32_t)p.row_bytes;            // shift rows -> bytes; >>4 applied below
+    const uint32_t group16 = (uint32_t)(p.J + p.KT - 1) * chunk16;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int rem = item % (p.n_tgroups * p.n_ytiles);
       const int tg = rem / p.n_ytiles;
@@ -243,44 +263,30 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
       const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
       timed_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1, dbg0, dbg_on);
       const int aset = it & (p.a_sets - 1);
-      const uint64_t a_desc_set = a_desc0 + (uint64_t)(aset * (p.a_set_bytes >> 4));
       timed_wait(&bars[BAR_A_FULL + aset], (it / p.a_sets) & 1, dbg1, dbg_on);
       tc_fence_after();
+      // this warp's (at most two) accumulators: frames mw and mw + 4 of the item
+      const uint64_t aj0 = a_desc0 + (uint64_t)(aset * (p.a_set_bytes >> 4)) + (uint64_t)(mw * chunk16);
+      const uint64_t aj1 = aj0 + (uint64_t)(kMmaWarps * chunk16);
+      const uint32_t d0 = d_base + (uint32_t)(mw * p.acc_cols), d1 = d0 + (uint32_t)(kMmaWarps * p.acc_cols);
+      const bool has0 = mw < jn, has1 = mw + kMmaWarps < jn;
       uint32_t first = 0;      // accumulate flag: 0 for the very first tap of the item
       for (int g = 0; g < p.CG; ++g) {
-        int kt = 0, ky = 0, kx = 0;                       // running (kt,ky,kx) of the next tap: no divisions
+        const uint32_t goff = (uint32_t)g * group16;
         for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
           const int s = wn % p.w_stages;
           const int nt = min(p.tps, n_taps - tap0);
           timed_wait(&bars[BAR_W_FULL + s], (wn / p.w_stages) & 1, dbg2, dbg_on);
           tc_fence_after();
-          const bool issuer = elect_one();
-          if (true) {
-            for (int i = 0; i < nt; ++i) {
-              const uint64_t wd = w_desc0 + (uint64_t)((s * p.tps + i) * wtile16);
-              const uint64_t ad = a_desc_set + (uint64_t)((g * (p.J + p.KT - 1) + kt) * chunk16 +
-                                                       (((uint32_t)(ky * p.Wp + kx) * row16x) >> 4));
-              for (int j = mw; issuer && j < jn; j += kMmaWarps) {
-                const uint64_t aj = ad + (uint64_t)(j * chunk16);
-                const uint32_t d = d_base + (uint32_t)(j * p.acc_cols);
-                // swap: weights are the M-side operand, the 128 positions the N side
-                const uint64_t ma = p.swap ? wd : aj, mb = p.swap ? aj : wd;
-                if (ksteps == 4) {
-                  umma_bf16(d, ma, mb, p.idesc, first);
-                  umma_bf16(d, ma + 2, mb + 2, p.idesc, 1u);
-                  umma_bf16(d, ma + 4, mb + 4, p.idesc, 1u);
-                  umma_bf16(d, ma + 6, mb + 6, p.idesc, 1u);
-                } else if (ksteps == 2) {
-                  umma_bf16(d, ma, mb, p.idesc, first);
-                  umma_bf16(d, ma + 2, mb + 2, p.idesc, 1u);
-                } else {
-                  umma_bf16(d, ma, mb, p.idesc, first);
-                }
-              }
+          if (elect_one()) {
+            uint64_t wd = w_desc0 + (uint64_t)((uint32_t)(s * p.tps) * wtile16);
+            for (int i = 0; i < nt; ++i, wd += wtile16) {
+              const uint32_t off = p.tap_off[tap0 + i] + goff;
+              if (has0) mma_tap<KS, SWAP>(d0, aj0 + off, wd, p.idesc, first);
+              if (has1) mma_tap<KS, SWAP>(d1, aj1 + off, wd, p.idesc, first);
               first = 1u;
-              if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++kt; } }
             }
-            if (issuer) umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
+            umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
           }
           __syncwarp();
         }
@@ -298,6 +304,21 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
     const int row = q * 32 + lane;                // accumulator row (tile position) held by this thread
     const int PW = p.W >> 1;
     const int cgroups = p.Cout >> 3;
+    // pooling work items of this thread (idx = etid + 128k -> pooled row, x, channel group): fixed per layer
+    int e_src[kEpiIters], e_out[kEpiIters], e_am[kEpiIters], e_py[kEpiIters], e_cg[kEpiIters];
+    const int epi_n = ((p.R >> 1) * PW * cgroups + 127) / 128;
+#pragma unroll
+    for (int k = 0; k < kEpiIters; ++k) {
+      const int idx = etid + 128 * k;
+      const int cg = idx % cgroups, pp = idx / cgroups;
+      const int px = pp % (PW > 0 ? PW : 1), py = pp / (PW > 0 ? PW : 1);
+      e_cg[k] = cg;
+      e_py[k] = idx < (p.R >> 1) * PW * cgroups ? py : (1 << 30);      // beyond the tile: never valid
+      e_src[k] = ((2 * py) * p.Wp + 2 * px) * p.stage_pitch + cg * 16;
+      e_out[k] = py * p.oWp + px;
+      e_am[k] = py * PW + px;
+    }
+    int ebuf = 0;
     int it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int b = item / (p.n_tgroups * p.n_ytiles);
@@ -308,7 +329,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
       const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
       timed_wait(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1, dbg0, dbg_on);
       tc_fence_after();
-      if (p.swap) {
+      if (SWAP) {
         for (int j = 0; j < jn; ++j) {
           const uint32_t tcol = d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 128);
           if (p.Wp == 8) epilogue_swapped<8>(p, tcol, q, lane, b, t0 + j, y0);
@@ -319,8 +340,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
         if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
         continue;
       }
+      const size_t obase = (((size_t)b * p.oTp + (t0 + p.o_t)) * p.oHp + ((p.epi_mode == 0 ? (y0 >> 1) : y0) + p.o_y)) *
+                               p.oWp + p.o_x;                       // output pixel of (t0, tile row 0, x 0)
+      const size_t oframe = (size_t)p.oHp * p.oWp;
+      const int rows_left = (p.epi_mode == 0 ? (p.H >> 1) - (y0 >> 1) : p.H - y0);   // valid output rows from y0 on
       for (int j = 0; j < jn; ++j) {
         const int t = t0 + j;
+        uint8_t* stg = stage + (size_t)((ebuf++) & (p.stage_bufs - 1)) * (128 * p.stage_pitch);
         // TMEM -> registers -> (bias, ReLU) -> bf16 staging tile [128][Cout]
         for (int cc = 0; cc < p.Cout; cc += 32) {
           uint32_t v[32];
@@ -328,33 +354,32 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
           uint32_t packed[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float f0 = __uint_as_float(v[2 * i]), f1 = __uint_as_float(v[2 * i + 1]);
-            if (p.has_bias) { f0 += p.bias[cc + 2 * i]; f1 += p.bias[cc + 2 * i + 1]; }
+            const float2 bb = *reinterpret_cast<const float2*>(bias_s + cc + 2 * i);     // smem broadcast
+            float f0 = __uint_as_float(v[2 * i]) + bb.x, f1 = __uint_as_float(v[2 * i + 1]) + bb.y;
             if (p.epi_mode == 0) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
             __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
             packed[i] = *reinterpret_cast<uint32_t*>(&h);
           }
-          uint4* dst = reinterpret_cast<uint4*>(stage + (size_t)row * p.stage_pitch + cc * 2);
+          uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)row * p.stage_pitch + cc * 2);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
         }
         named_bar_sync(1, 128);
+        const size_t ob = obase + (size_t)j * oframe;
         if (p.epi_mode == 0) {
-          // MaxPool(1,2,2) over the staged tile; 8 channels (16 B) per thread-item
-          const int n_out = (p.R >> 1) * PW * cgroups;
-          for (int idx = etid; idx < n_out; idx += 128) {
-            const int cg = idx % cgroups;
-            const int pp = idx / cgroups;
-            const int px = pp % PW, py = pp / PW;
-            const int gy = (y0 >> 1) + py;
-            if (gy >= (p.H >> 1)) continue;
-            const int r00 = (2 * py) * p.Wp + 2 * px;
+          // MaxPool(1,2,2) over the staged tile; 8 channels (16 B) per thread-item; the (row, x, channel
+          // group) decomposition of each item was hoisted out of the item loop (no divisions here)
+          const size_t ab = (((size_t)b * p.T + t) * (p.H >> 1) + (y0 >> 1)) * PW;
+#pragma unroll
+          for (int k = 0; k < kEpiIters; ++k) {
+            if (k >= epi_n || e_py[k] >= rows_left) continue;
+            const uint8_t* src = stg + e_src[k];
             uint4 q4[4];
-            q4[0] = *reinterpret_cast<const uint4*>(stage + (size_t)r00 * p.stage_pitch + cg * 16);
-            q4[1] = *reinterpret_cast<const uint4*>(stage + (size_t)(r00 + 1) * p.stage_pitch + cg * 16);
-            q4[2] = *reinterpret_cast<const uint4*>(stage + (size_t)(r00 + p.Wp) * p.stage_pitch + cg * 16);
-            q4[3] = *reinterpret_cast<const uint4*>(stage + (size_t)(r00 + p.Wp + 1) * p.stage_pitch + cg * 16);
+            q4[0] = *reinterpret_cast<const uint4*>(src);
+            q4[1] = *reinterpret_cast<const uint4*>(src + p.stage_pitch);
+            q4[2] = *reinterpret_cast<const uint4*>(src + (size_t)p.Wp * p.stage_pitch);
+            q4[3] = *reinterpret_cast<const uint4*>(src + (size_t)(p.Wp + 1) * p.stage_pitch);
             const __nv_bfloat16* e0 = reinterpret_cast<const __nv_bfloat16*>(&q4[0]);
             const __nv_bfloat16* e1 = reinterpret_cast<const __nv_bfloat16*>(&q4[1]);
             const __nv_bfloat16* e2 = reinterpret_cast<const __nv_bfloat16*>(&q4[2]);
@@ -372,27 +397,25 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const ConvParam
               outv[e] = __float2bfloat16(m);
               am[e] = (uint8_t)(m > 0.f ? a : 4);
             }
-            const size_t opix = (((size_t)b * p.oTp + (t + p.o_t)) * p.oHp + (gy + p.o_y)) * p.oWp + (px + p.o_x);
-            *reinterpret_cast<uint4*>(p.y + opix * p.Cout + cg * 8) = *reinterpret_cast<const uint4*>(outv);
-            if (p.argmax) {
-              const size_t apix = (((size_t)b * p.T + t) * (p.H >> 1) + gy) * PW + px;
-              *reinterpret_cast<uint2*>(p.argmax + apix * p.Cout + cg * 8) = *reinterpret_cast<const uint2*>(am);
-            }
+            *reinterpret_cast<uint4*>(p.y + (ob + e_out[k]) * p.Cout + e_cg[k] * 8) =
+                *reinterpret_cast<const uint4*>(outv);
+            if (p.argmax)
+              *reinterpret_cast<uint2*>(p.argmax + (ab + e_am[k]) * p.Cout + e_cg[k] * 8) =
+                  *reinterpret_cast<const uint2*>(am);
           }
         } else {
           const int n_out = 128 * cgroups;
           for (int idx = etid; idx < n_out; idx += 128) {
-            const int cg = idx % cgroups;
-            const int r = idx / cgroups;
-            const int yl = r / p.Wp, x = r - yl * p.Wp;
-            const int gy = y0 + yl;
-            if (x >= p.W || gy >= p.H) continue;
-            const size_t opix = (((size_t)b * p.oTp + (t + p.o_t)) * p.oHp + (gy + p.o_y)) * p.oWp + (x + p.o_x);
-            *reinterpret_cast<uint4*>(p.y + opix * p.Cout + cg * 8) =
-                *reinterpret_cast<const uint4*>(stage + (size_t)r * p.stage_pitch + cg * 16);
+            int cg, r;
+            if (p.cg_shift >= 0) { cg = idx & (cgroups - 1); r = idx >> p.cg_shift; }
+            else { cg = idx % cgroups; r = idx / cgroups; }
+            const int yl = r >> p.wp_shift, x = r & (p.Wp - 1);
+            if (x >= p.W || yl >= rows_left) continue;
+            *reinterpret_cast<uint4*>(p.y + (ob + (size_t)yl * p.oWp + x) * p.Cout + cg * 8) =
+                *reinterpret_cast<const uint4*>(stg + (size_t)r * p.stage_pitch + cg * 16);
           }
         }
-        named_bar_sync(1, 128);     // staging tile is reused by the next accumulator
+        if (p.stage_bufs == 1) named_bar_sync(1, 128);     // single staging tile: reused by the next accumulator
       }
       tc_fence_before();
       if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
@@ -613,6 +636,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   LR_CHECK_ARG(Wp >= W + KW - 1 && Hp >= H + KH - 1, "lr_conv3d_fwd: padded extents smaller than H+KH-1 / W+KW-1");
   LR_CHECK_ARG(KT >= 1 && KH >= 1 && KW >= 1 && CG >= 1 && B > 0 && T > 0 && H > 0 && W > 0, "lr_conv3d_fwd: bad shape");
   LR_CHECK_ARG(epi_mode == 0 || epi_mode == 1, "lr_conv3d_fwd: bad epilogue mode");
+  LR_CHECK_ARG(KT * KH * KW <= kMaxTaps, "lr_conv3d_fwd: more than %d taps", kMaxTaps);
   if (!lr_conv3d_supported()) { lr_set_error("lr_conv3d_fwd needs an sm_100 device"); return LR_EARCH; }
 
   ConvParams p;
@@ -635,13 +659,14 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   // swap mode pools in registers (no staging tile) but reads Mt weight rows per MMA: keep that many
   // bytes of slack behind the weight ring
   const int stage_bytes = swap ? p.Mt * p.row_bytes : 128 * p.stage_pitch;
-  const int smem_cap = 227 * 1024 - 1024;     // minus alignment slack
+  const int smem_cap = 227 * 1024 - 1024 - 512;     // minus alignment slack and the bias copy
   int fixed = 2 * p.wtile_bytes + stage_bytes + 256;      // at least a 2-deep ring of single taps
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
   int n_sets = (512 / p.acc_cols) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
   if (getenv("LR_CONV_SETS")) { int v = atoi(getenv("LR_CONV_SETS")); if (v == 1 || (v == 2 && 512 / p.acc_cols >= 2)) n_sets = v; }   // tuning hook
   int Jmax = 512 / p.acc_cols / n_sets;
   if (J <= 0 || J > Jmax) J = Jmax;
+  if (J > 2 * kMmaWarps) J = 2 * kMmaWarps;      // each issuing warp owns at most two accumulators
   while (J > 1 && ((J + KT - 1) * CG > kMaxChunks || (J + KT - 1) * CG * p.chunk_bytes + fixed > smem_cap)) --J;
   LR_CHECK_ARG((J + KT - 1) * CG * p.chunk_bytes + fixed <= smem_cap && (J + KT - 1) * CG <= kMaxChunks,
                "lr_conv3d_fwd: tile does not fit shared memory");
@@ -689,8 +714,15 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
     p.w_stages = stages;
   }
   p.smem_off_stage = p.smem_off_w + p.w_stages * p.tps * p.wtile_bytes;
-  p.smem_off_bar = p.smem_off_stage + stage_bytes;
-  const size_t smem_bytes = (size_t)p.smem_off_bar + 256 + 1024;
+  // a second staging tile (drops one of the two named barriers per accumulator) when shared memory is left over
+  p.stage_bufs = (!swap && p.smem_off_stage + 2 * stage_bytes + 256 <= smem_cap) ? 2 : 1;
+  p.smem_off_bar = p.smem_off_stage + p.stage_bufs * stage_bytes;
+  p.cg_shift = -1;
+  for (int sft = 0; sft < 8; ++sft) {
+    if ((Cout >> 3) == (1 << sft)) p.cg_shift = sft;
+    if (Wp == (1 << sft)) p.wp_shift = sft;
+  }
+  const size_t smem_bytes = (size_t)p.smem_off_bar + 256 + 512 + 1024;
 
   CUtensorMap map_x;
   int rc = make_map_2d(&map_x, x, (uint64_t)Cin, (uint64_t)p.rows_per_group * CG, (uint32_t)Cin, (uint32_t)p.CH,
@@ -699,10 +731,26 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.w_packed = reinterpret_cast<const uint8_t*>(w);
   p.dbg = g_conv_dbg;
 
-  LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes));
+  for (int kt = 0, tap = 0; kt < KT; ++kt)
+    for (int ky = 0; ky < KH; ++ky)
+      for (int kx = 0; kx < KW; ++kx, ++tap)
+        p.tap_off[tap] = (uint32_t)kt * ((uint32_t)p.chunk_bytes >> 4) +
+                         (((uint32_t)(ky * Wp + kx) * (uint32_t)p.row_bytes) >> 4);
+
   int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  conv3d_tcgen05_kernel<<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);
+#define LR_LAUNCH_CONV(KS, SW)                                                                              \
+  do {                                                                                                      \
+    LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel<KS, SW>,                                       \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));      \
+    conv3d_tcgen05_kernel<KS, SW><<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);             \
+  } while (0)
+  const int ks = Cin / 16;
+  if (p.swap) {
+    if (ks == 1) LR_LAUNCH_CONV(1, true); else if (ks == 2) LR_LAUNCH_CONV(2, true); else LR_LAUNCH_CONV(4, true);
+  } else {
+    if (ks == 1) LR_LAUNCH_CONV(1, false); else if (ks == 2) LR_LAUNCH_CONV(2, false); else LR_LAUNCH_CONV(4, false);
+  }
+#undef LR_LAUNCH_CONV
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

@@ -11,8 +11,11 @@
 // 64-/32-/16-channel blocks LBO apart — which is how three 32-channel gradient volumes become one
 // N = 96 operand).
 //
-// One MMA atom is M=64 x N x K=16 positions; per 128-position tile a CTA issues
-// taps_in_group x 8 of them into taps_in_group TMEM accumulators (64 lanes x N fp32 columns each).
+// One MMA atom is M x N x K=16 positions; per 128-position tile a CTA issues units_in_group x 8 of
+// them into units_in_group TMEM accumulators (M lanes x N fp32 columns each).  M = 64 is half rate
+// on the tensor pipe (profiles/r1_umma_table.txt), so the layers whose M side is dY stack S = 128/Cy
+// filter rows (ky taps) on M = 128: M block b is the SAME dY tile shifted up by b image rows
+// (descriptor LBO = Wp * row pitch), exactly like the kx taps are stacked on N.
 // Grid = tap groups x splits; every CTA walks its share of the B*T*ytiles position tiles through a
 // 3-stage TMA ring, then dumps its partial accumulators (fp32) to a workspace; a second kernel
 // reduces the splits in a fixed order (deterministic).
@@ -45,6 +48,11 @@ struct WgradParams {
   int R, n_ytiles, n_tiles;
   int n_groups, splits;
   int group_kt[kMaxGroups], group_lo[kMaxGroups], group_n[kMaxGroups], group_tap0[kMaxGroups];
+  int group_nkt;          // kt planes per group (1, or KT when the whole filter depth is fused into one CTA)
+  int per_kt;             // accumulator units per kt plane
+  int Mrows;              // 64 or 128 (M of the MMA)
+  int m_stack;            // S: ky taps stacked on M (1 = off); unit u covers ky = u*S .. u*S+S-1
+  int n_region_bytes;     // smem bytes of one kt plane of the N-side operand
   Side m, n;
   int Nc;                 // N of the MMA = n.blocks * n.row_bytes / 2 (x KW when kx taps are stacked)
   int stack;              // 1: one accumulator per tap; KW: the KW kx-taps of a (kt,ky) row share one MMA
@@ -99,7 +107,8 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues
     uint32_t n = 0;
-    const uint32_t tx = (uint32_t)(p.m.blocks * p.m.rows * p.m.row_bytes + p.n.blocks * p.n.rows * p.n.row_bytes);
+    const uint32_t tx = (uint32_t)(p.m.blocks * p.m.rows * p.m.row_bytes +
+                                   p.group_nkt * p.n.blocks * p.n.rows * p.n.row_bytes);
     for (int tile = split; tile < p.n_tiles; tile += p.splits, ++n) {
       const int s = n % kStages;
       const int yt = tile % p.n_ytiles;
@@ -114,10 +123,13 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
           long long row = p0 + p.m.base_off + (p.m.shifted ? (long long)kt * p.Hp * p.Wp : 0) + blk * p.m.group_rows;
           tma_load_2d(st + (size_t)blk * p.m.tile_bytes, &map_m, 0, (int)row, &bars[BAR_FULL + s]);
         }
-        for (int blk = 0; blk < p.n.blocks; ++blk) {
-          long long row = p0 + p.n.base_off + (p.n.shifted ? (long long)kt * p.Hp * p.Wp : 0) + blk * p.n.group_rows;
-          tma_load_2d(st + m_bytes + (size_t)blk * p.n.tile_bytes, &map_n, 0, (int)row, &bars[BAR_FULL + s]);
-        }
+        for (int kk = 0; kk < p.group_nkt; ++kk)
+          for (int blk = 0; blk < p.n.blocks; ++blk) {
+            long long row = p0 + p.n.base_off + (p.n.shifted ? (long long)(kt + kk) * p.Hp * p.Wp : 0) +
+                            blk * p.n.group_rows;
+            tma_load_2d(st + m_bytes + (size_t)kk * p.n_region_bytes + (size_t)blk * p.n.tile_bytes, &map_n, 0,
+                        (int)row, &bars[BAR_FULL + s]);
+          }
       }
       __syncwarp();
     }
@@ -136,11 +148,13 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
       const uint32_t acc0 = n == 0 ? 0u : 1u;
       if (elect_one()) {
         for (int j = mw; j < ntap; j += kMmaWarps) {
-          const int unit = tap_lo + j;
-          const int ky = p.stack > 1 ? unit : unit / p.KW, kx = p.stack > 1 ? 0 : unit - ky * p.KW;
+          const int kk = j / p.per_kt;                 // kt plane inside a fused group (else 0: groups never span)
+          const int unit = p.group_nkt > 1 ? j - kk * p.per_kt : tap_lo + j;
+          const int ky = p.stack > 1 ? unit * p.m_stack : unit / p.KW, kx = p.stack > 1 ? 0 : unit - ky * p.KW;
           const uint32_t shift = (uint32_t)(ky * p.Wp + kx);
           const uint64_t md = md0 + (uint64_t)(p.m.shifted ? (shift * p.m.row_bytes) >> 4 : 0u);
-          const uint64_t nd = nd0 + (uint64_t)(p.n.shifted ? (shift * p.n.row_bytes) >> 4 : 0u);
+          const uint64_t nd = nd0 + (uint64_t)((uint32_t)(kk * p.n_region_bytes) >> 4) +
+                              (uint64_t)(p.n.shifted ? (shift * p.n.row_bytes) >> 4 : 0u);
           const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
           umma_bf16(d, md, nd, p.idesc, acc0);
 #pragma unroll
@@ -153,18 +167,21 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
     if (elect_one()) umma_commit(&bars[BAR_ACC]);
     __syncwarp();
   } else {
-    // epilogue: M=64 accumulators live in lanes {0-15, 32-47, 64-79, 96-111}: row m = 16*q + lane
+    // epilogue: M=64 accumulators live in lanes {0-15, 32-47, 64-79, 96-111}: row m = 16*q + lane;
+    // M=128: row m = lane of the TMEM = 32*q + lane
     const int q = warp & 3;
     lr_mbar_wait(&bars[BAR_ACC], 0);
     tc_fence_after();
     const bool any_tile = split < p.n_tiles;
+    const bool wide = p.Mrows == 128;
+    const int row = wide ? q * 32 + lane : q * 16 + lane;
     for (int j = 0; j < ntap; ++j) {
       const int tap_global = p.group_tap0[gi] + j;
-      float* dst = p.ws + (((size_t)split * p.n_taps_total + tap_global) * 64 + (q * 16 + lane)) * p.Nc;
+      float* dst = p.ws + (((size_t)split * p.n_taps_total + tap_global) * p.Mrows + row) * p.Nc;
       for (int cc = 0; cc < p.Nc; cc += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.Nc + cc), v);
-        if (lane < 16) {
+        if (wide || lane < 16) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             float4 o = any_tile ? make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
@@ -210,9 +227,14 @@ void fill_side(Side& s, int ch_per_block, int blocks, int rows, int shifted, int
 
 }  // namespace
 
-// Nc = columns per tap (Cx, or Gy*Cy when m_is_x); the workspace size does not depend on stacking
-extern "C" size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits) {
-  return (size_t)splits * KT * KH * KW * 64 * Nc * sizeof(float);
+// Floats per split (= size of `out`): without ky stacking [KT*KH*KW][64][Nc] (Nc = Cx, or Gy*Cy when m_is_x);
+// with stack_ky = S > 1 (m_is_x = 0, kx stacked): [KT*ceil(KH/S)][128][KW*Cx].
+extern "C" size_t lr_conv3d_wgrad_out_floats(int KT, int KH, int KW, int Nc, int stack_ky) {
+  if (stack_ky > 1) return (size_t)KT * ((KH + stack_ky - 1) / stack_ky) * 128 * KW * Nc;
+  return (size_t)KT * KH * KW * 64 * Nc;
+}
+extern "C" size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits, int stack_ky) {
+  return (size_t)splits * lr_conv3d_wgrad_out_floats(KT, KH, KW, Nc, stack_ky) * sizeof(float);
 }
 
 // dW partials for one layer.
@@ -222,26 +244,43 @@ extern "C" size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int 
 //   m_is_x: 0 -> D[tap] is [co(64 lanes) x ci]  (M side = dy, needs Gy*Cy <= 64; Cy=32,Gy=1 is
 //                duplicated to fill M=64), 1 -> D[tap] is [ci(64) x co] (M side = x, needs Cx = 64)
 //   out: fp32 [KT*KH*KW][64][Nc], Nc = m_is_x ? Gy*Cy : Cx;  with stack_kx (m_is_x = 0 only) the layout is
-//        [KT*KH][64][KW][Cx] (the kx taps of a row are the column blocks of one accumulator)
+//        [KT*KH][64][KW][Cx] (the kx taps of a row are the column blocks of one accumulator);
+//        with stack_ky = S = 128/Cy as well: [KT][U = ceil(KH/S)][S][Cy][KW][Cx], where M block b of unit u
+//        holds filter row ky = u*S + (S-1-b) (rows with ky >= KH are scratch).
+//   fuse_kt (stack_ky only): one CTA accumulates all KT planes of a position tile (needs KT*U*KW*Cx <= 512
+//        TMEM columns) instead of one tap group per kt -> the dY tile is fetched once, not KT times.
 extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, size_t ws_bytes,
                                int B, int T, int H, int W, int Hp, int Wp, int Cx, int Cy, int Gy,
-                               long long dy_off, int KT, int KH, int KW, int m_is_x, int stack_kx, int splits,
-                               void* stream) {
+                               long long dy_off, int KT, int KH, int KW, int m_is_x, int stack_kx, int stack_ky,
+                               int fuse_kt, int splits, void* stream) {
   LR_CHECK_ARG(x && dy && out && workspace, "lr_conv3d_wgrad: null pointer");
   LR_CHECK_ARG(Cx == 16 || Cx == 32 || Cx == 64, "lr_conv3d_wgrad: Cx must be 16/32/64");
   LR_CHECK_ARG(Cy == 32 || Cy == 64, "lr_conv3d_wgrad: Cy must be 32/64");
   LR_CHECK_ARG(Wp == 8 || Wp == 16 || Wp == 32 || Wp == 64 || Wp == 128, "lr_conv3d_wgrad: Wp pow2 8..128");
   LR_CHECK_ARG(Wp >= W + KW - 1 && Hp >= H + KH - 1, "lr_conv3d_wgrad: padded extents too small");
+  const int S = stack_ky > 1 ? stack_ky : 1;
+  if (S > 1) {
+    LR_CHECK_ARG(!m_is_x && stack_kx && Gy == 1 && S * Cy == 128,
+                 "lr_conv3d_wgrad: stack_ky needs m_is_x = 0, stack_kx and stack_ky * Cy == 128");
+  }
+  LR_CHECK_ARG(!fuse_kt || S > 1, "lr_conv3d_wgrad: fuse_kt needs stack_ky");
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.T = T; p.H = H; p.W = W; p.Tp = T + KT - 1; p.Hp = Hp; p.Wp = Wp; p.KH = KH; p.KW = KW;
   p.R = 128 / Wp;
   LR_CHECK_ARG(Hp % p.R == 0, "lr_conv3d_wgrad: Hp must be a multiple of %d (tiles may not straddle planes)", p.R);
   p.n_ytiles = lr_div_up(H, p.R);
+  // ky stacking pairs dY image row (y - sh) with tile row y, sh = 0 .. min(S,KH)-1 for the filter rows that
+  // exist: the tiles of a plane must reach row H-1+sh
+  if (S > 1) p.n_ytiles = lr_div_up(H + (S < KH ? S : KH) - 1, p.R);
+  LR_CHECK_ARG(p.n_ytiles * p.R <= Hp, "lr_conv3d_wgrad: padded plane too short for the stacked tiles");
   p.n_tiles = B * T * p.n_ytiles;
-  const int CH = 128 + (KH - 1) * Wp + (KW - 1);
+  const int U = (KH + S - 1) / S;                       // units per kt plane when ky is stacked
+  const int CH = 128 + (S > 1 ? U * S - 1 : KH - 1) * Wp + (KW - 1);
   LR_CHECK_ARG(CH <= 256, "lr_conv3d_wgrad: halo too large");
   const long long vol_rows = (long long)B * p.Tp * Hp * Wp;
+  p.Mrows = S > 1 ? 128 : 64;
+  p.m_stack = S;
   if (m_is_x) {
     LR_CHECK_ARG(Cx == 64, "lr_conv3d_wgrad: m_is_x needs Cx = 64");
     fill_side(p.m, Cx, 1, CH, 1, 0, 0, 0);
@@ -249,7 +288,14 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
     p.Nc = Gy * Cy;
   } else {
     LR_CHECK_ARG(Gy == 1 && (Cy == 64 || Cy == 32), "lr_conv3d_wgrad: M side = dy needs one group of 32/64 channels");
-    fill_side(p.m, Cy, Cy == 32 ? 2 : 1, 128, 0, Cy == 32, vol_rows, dy_off);
+    if (S > 1) {
+      // one TMA box of 128 + (S-1)*Wp rows starting (S-1) image rows above the tile; M block b = rows shifted
+      // down by b*Wp, i.e. dY[p - (S-1-b)*Wp]  <->  filter row ky0 + (S-1-b)
+      fill_side(p.m, Cy, 1, 128 + (S - 1) * Wp, 0, 0, vol_rows, dy_off - (long long)(S - 1) * Wp);
+      p.m.lbo_bytes = Wp * p.m.row_bytes;
+    } else {
+      fill_side(p.m, Cy, Cy == 32 ? 2 : 1, 128, 0, Cy == 32, vol_rows, dy_off);
+    }
     fill_side(p.n, Cx, 1, CH, 1, 0, 0, 0);
     p.Nc = Cx;
     if (stack_kx && KW > 1) {          // N = KW*Cx: block j of the N operand = the chunk shifted by j rows
@@ -259,39 +305,52 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
     }
   }
   if (p.stack == 0) p.stack = 1;
+  LR_CHECK_ARG(S == 1 || p.stack > 1, "lr_conv3d_wgrad: stack_ky needs KW > 1");
   LR_CHECK_ARG(p.Nc % 16 == 0 && p.Nc <= 256, "lr_conv3d_wgrad: bad N (%d)", p.Nc);
-  // tap groups: one kt each, at most 512/Nc accumulators
-  const int per_kt = p.stack > 1 ? KH : KH * KW;      // accumulator units per kt plane
+  // tap groups: one kt each (or all kt when fused), at most 512/Nc accumulators
+  const int per_kt = S > 1 ? U : (p.stack > 1 ? KH : KH * KW);      // accumulator units per kt plane
   const int max_taps = 512 / p.Nc;
   LR_CHECK_ARG(max_taps >= 1, "lr_conv3d_wgrad: N too wide for TMEM");
+  p.per_kt = per_kt;
+  p.group_nkt = 1;
   int g = 0, tap0 = 0;
-  for (int kt = 0; kt < KT; ++kt)
-    for (int lo = 0; lo < per_kt; lo += max_taps) {
-      LR_CHECK_ARG(g < kMaxGroups, "lr_conv3d_wgrad: too many tap groups");
-      p.group_kt[g] = kt; p.group_lo[g] = lo; p.group_n[g] = per_kt - lo < max_taps ? per_kt - lo : max_taps;
-      p.group_tap0[g] = tap0;
-      tap0 += p.group_n[g];
-      ++g;
-    }
+  if (fuse_kt) {
+    LR_CHECK_ARG(KT * per_kt <= max_taps, "lr_conv3d_wgrad: fuse_kt does not fit TMEM");
+    p.group_nkt = KT;
+    p.group_kt[0] = 0; p.group_lo[0] = 0; p.group_n[0] = KT * per_kt; p.group_tap0[0] = 0;
+    g = 1;
+  } else {
+    for (int kt = 0; kt < KT; ++kt)
+      for (int lo = 0; lo < per_kt; lo += max_taps) {
+        LR_CHECK_ARG(g < kMaxGroups, "lr_conv3d_wgrad: too many tap groups");
+        p.group_kt[g] = kt; p.group_lo[g] = lo; p.group_n[g] = per_kt - lo < max_taps ? per_kt - lo : max_taps;
+        p.group_tap0[g] = tap0;
+        tap0 += p.group_n[g];
+        ++g;
+      }
+  }
   p.n_groups = g;
   p.n_taps_total = KT * per_kt;          // accumulator units (taps, or (kt,ky) rows when stacked)
   if (splits <= 0) splits = kNumSMs / p.n_groups;
   if (splits < 1) splits = 1;
   if (splits > p.n_tiles) splits = p.n_tiles;
   p.splits = splits;
-  size_t need = (size_t)splits * p.n_taps_total * 64 * p.Nc * sizeof(float);
+  size_t need = (size_t)splits * p.n_taps_total * p.Mrows * p.Nc * sizeof(float);
   if (ws_bytes < need) { lr_set_error("lr_conv3d_wgrad: workspace %zu < %zu", ws_bytes, need); return LR_EWORKSPACE; }
   p.ws = reinterpret_cast<float*>(workspace);
+  int max_units = 0;
+  for (int i = 0; i < g; ++i) max_units = p.group_n[i] > max_units ? p.group_n[i] : max_units;
   int cols = 32;
-  while (cols < max_taps * p.Nc && cols < 512) cols <<= 1;
+  while (cols < max_units * p.Nc && cols < 512) cols <<= 1;
   p.tmem_cols = cols;
-  p.stage_bytes = p.m.blocks * p.m.tile_bytes + p.n.blocks * p.n.tile_bytes;
+  p.n_region_bytes = p.n.blocks * p.n.tile_bytes;
+  p.stage_bytes = p.m.blocks * p.m.tile_bytes + p.group_nkt * p.n_region_bytes;
   p.smem_off_bar = kStages * p.stage_bytes;
   const size_t smem_bytes = (size_t)p.smem_off_bar + 256 + 1024;
   LR_CHECK_ARG(smem_bytes <= 227 * 1024, "lr_conv3d_wgrad: stages do not fit shared memory");
-  // instruction descriptor: f32 accum, bf16 x bf16, both operands MN-major, M=64
+  // instruction descriptor: f32 accum, bf16 x bf16, both operands MN-major, M = 64 / 128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Nc >> 3) << 17) |
-            ((uint32_t)(64 >> 4) << 24);
+            ((uint32_t)(p.Mrows >> 4) << 24);
 
   const void* m_base = m_is_x ? x : dy;
   const void* n_base = m_is_x ? dy : x;
@@ -310,7 +369,7 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
   cudaStream_t st = lr_stream(stream);
   conv3d_wgrad_tcgen05_kernel<<<p.n_groups * splits, kThreads, smem_bytes, st>>>(map_m, map_n, p);
   LR_CHECK_LAUNCH();
-  const long long per_split = (long long)p.n_taps_total * 64 * p.Nc;
+  const long long per_split = (long long)p.n_taps_total * p.Mrows * p.Nc;
   wgrad_reduce_kernel<<<lr_div_up(per_split, 256), 256, 0, st>>>(p.ws, out, splits, per_split);
   LR_CHECK_LAUNCH();
   return LR_OK;

@@ -102,7 +102,7 @@ def test_conv3d_relu_pool_epilogue(native_lib, cuda, J, swap):
     ("conv3", 64, 32, 3, (3, 3, 3), 12, 6, 8, 1, 3, 4),
     ("conv1", 16, 32, 1, (3, 3, 3), 50, 25, 32, 0, 1, 3),
 ])
-@pytest.mark.parametrize("stack", [False, True])
+@pytest.mark.parametrize("stack", [0, 1, 2])     # 0: one MMA per tap; 1: kx on N; 2: + ky on M=128 (+ fused kt)
 def test_conv3d_wgrad_matches_autograd(native_lib, cuda, name, Cx, Cy, Gy, K, H, W, Wp, m_is_x, B, T, stack):
     from lipreading_b200.conv_frontend import conv3d_wgrad_native, _plane_rows
     g = torch.Generator().manual_seed(4321)
@@ -124,9 +124,10 @@ def test_conv3d_wgrad_matches_autograd(native_lib, cuda, name, Cx, Cy, Gy, K, H,
         dyd = dy.to(cuda)
         dyv = torch.stack([_padded(dyd[..., gi * Cy:(gi + 1) * Cy], pad, Wp, Hp) for gi in range(Gy)], 0).contiguous()
         off = (pad[0] * Hp + pad[1]) * Wp + pad[2]
-    out = conv3d_wgrad_native(xv, dyv, B, T, H, W, Hp, Wp, Cx, Cy, Gy, off, K, m_is_x, stack_kx=stack)
+    out = conv3d_wgrad_native(xv, dyv, B, T, H, W, Hp, Wp, Cx, Cy, Gy, off, K, m_is_x, stack_kx=stack >= 1,
+                              stack_ky=stack == 2)
     torch.cuda.synchronize()
-    out = out.cpu().reshape(K[0], K[1], K[2], 64, -1)
+    out = out.cpu().reshape(K[0], K[1], K[2], out.shape[1], -1)
     got = out.permute(4, 3, 0, 1, 2) if m_is_x else out[:, :, :, :Co].permute(3, 4, 0, 1, 2)
     assert got.shape == ref.shape
     assert float((got - ref).abs().max() / ref.abs().max()) < 2e-3
