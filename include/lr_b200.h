@@ -174,7 +174,9 @@ int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint
 /* Backward of ReLU+MaxPool(1,2,2): d_pooled (B,T,H/2,W/2,C) bf16 + argmax -> gradient w.r.t. the
  * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
  * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass; d_bias (C) f32 or NULL receives
- * the per-channel sum (the conv bias gradient).                                                */
+ * the per-channel sum (the conv bias gradient).  Only the 2x2 windows of the pooled pixels are
+ * written: `out` must already be zero everywhere else (borders, and the last row/column of an odd
+ * H or W) — allocate it zeroed once and reuse it.                                              */
 /* bf16 [Cout][CG][taps][Cin] -> [CG][taps][Cout x Cin] tile images, 16-byte chunks pre-swizzled so a
  * stage of taps is ONE contiguous bulk copy into shared memory (what lr_conv3d_fwd expects as `w`). */
 int lr_pack_conv_weights(const void* w, void* out, int Cout, int CG, int taps, int Cin, void* stream);

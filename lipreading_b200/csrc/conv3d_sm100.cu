@@ -496,68 +496,75 @@ clip_s2d_kernel(const uint8_t* __restrict__ clip, __nv_bfloat16* __restrict__ ou
 // ---- backward helper: route pooled gradients through the stored argmax (ReLU'd max-pool) --------
 // d_pooled (B,T,H/2,W/2,C) bf16 + argmax u8 -> d_conv_out written into the interior of the
 // zero-padded, channel-grouped volume the dgrad/wgrad passes read:
-//   out[g][b][t+pt][y+ph][x+pw][c % Cg], g = c / Cg.  Every interior element is written (0 where it
-// is not the arg-max or the unit was ReLU-dead), borders stay zero from allocation.
+//   out[g][b][t+pt][y+ph][x+pw][c % Cg], g = c / Cg.
+// One thread owns one POOLED pixel x 8 channels: it reads the gradient (16 B) and the arg-max bytes (8 B)
+// once and writes the four positions of the 2x2 window (the arg-max one gets the gradient, the others 0).
+// Interior rows/columns beyond the last whole window (odd H or W) are never written by anyone and keep the
+// zeros they were allocated with, like the borders.  blockIdx.y strides over frames; a thread's
+// (pooled row, x, channel group) is fixed, so there is no index arithmetic in the loop, and kUnpoolBatch
+// frames are loaded before any store is issued (memory-level parallelism).
+constexpr int kUnpoolBatch = 4;
 __global__ void __launch_bounds__(256)
 unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restrict__ argmax,
               __nv_bfloat16* __restrict__ out, float* __restrict__ d_bias, int B, int T, int H, int W, int C,
               int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw) {
-  // bias gradient = per-channel sum of the routed gradients.  The grid stride is a multiple of C/8, so a
-  // thread keeps the same 8-channel group for its whole loop: accumulate in registers, then one shared
-  // and one global atomic per (thread|block, channel).
   __shared__ float bias_acc[128];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) bias_acc[i] = 0.f;
   __syncthreads();
   const int PH = H >> 1, PW = W >> 1;
   const int c8 = C >> 3;
+  const int per_frame = PH * PW * c8;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = item < per_frame;
+  const int cg = item % c8, pp = item / c8;
+  const int px = pp % PW, py = pp / PW;
+  const int c0 = cg * 8, g = c0 / Cg, cl = c0 - g * Cg;
   const long long rows_per_group = (long long)B * Tp * Hp * Wp;
+  const size_t frame_in = (size_t)per_frame * 8;                       // elements per frame of d_pooled / argmax
+  const size_t in_off = (size_t)item * 8;
+  // output element offset of window position (0,0) in frame (b=0,t=0)
+  const size_t out_off = ((size_t)g * rows_per_group + ((size_t)pt * Hp + (2 * py + ph)) * Wp + (2 * px + pw)) * Cg + cl;
+  const size_t out_frame = (size_t)Hp * Wp * Cg, out_clip = (size_t)Tp * out_frame;
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  // blockIdx.y = frame (b,t); threads stride over the frame's H*W*(C/8) elements.  The stride is a
-  // multiple of C/8, so the channel group is fixed per thread and (y,x) advance incrementally.
-  const int plane = H * W * c8;
-  const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  const int stride = gridDim.x * blockDim.x;
-  const int my_cg = first % c8;
-  const int pstep = stride / c8, dy = pstep / W, dx = pstep - dy * W;
-  const int pix0 = first / c8;
-  const int y_first = pix0 / W, x_first = pix0 - y_first * W;
-  // blockIdx.y strides over frames: few blocks, so the bias partial sums stay in registers for long
-  for (int bt = blockIdx.y; bt < B * T; bt += gridDim.y) {
-  const int b = bt / T, t = bt - b * T;
-  int y = y_first, x = x_first;
-  for (int i = first; i < plane; i += stride) {
-    const int cg = my_cg;
-    __align__(16) __nv_bfloat16 v[8];
-    const int py = y >> 1, px = x >> 1;
-    const bool inside = py < PH && px < PW;
-    const int which = (y & 1) * 2 + (x & 1);
-    if (inside) {
-      const size_t pp = ((((size_t)b * T + t) * PH + py) * PW + px) * C + cg * 8;
-      uint4 g = *reinterpret_cast<const uint4*>(d_pooled + pp);
-      uint2 a = *reinterpret_cast<const uint2*>(argmax + pp);
-      const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&g);
-      const uint8_t* ae = reinterpret_cast<const uint8_t*>(&a);
+  const int n_frames = B * T;
+  if (active) {
+    for (int bt0 = blockIdx.y * kUnpoolBatch; bt0 < n_frames; bt0 += gridDim.y * kUnpoolBatch) {
+      uint4 gr[kUnpoolBatch];
+      uint2 am[kUnpoolBatch];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const bool hit = ae[e] == which;
-        v[e] = hit ? ge[e] : __float2bfloat16(0.f);
-        if (hit) bsum[e] += __bfloat162float(ge[e]);
+      for (int k = 0; k < kUnpoolBatch; ++k) {
+        const int bt = bt0 + k;
+        if (bt < n_frames) {
+          gr[k] = *reinterpret_cast<const uint4*>(d_pooled + (size_t)bt * frame_in + in_off);
+          am[k] = *reinterpret_cast<const uint2*>(argmax + (size_t)bt * frame_in + in_off);
+        }
       }
-    } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16(0.f);
+      for (int k = 0; k < kUnpoolBatch; ++k) {
+        const int bt = bt0 + k;
+        if (bt >= n_frames) break;
+        const int b = bt / T, t = bt - b * T;
+        const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gr[k]);
+        const uint8_t* ae = reinterpret_cast<const uint8_t*>(&am[k]);
+        __nv_bfloat16* o = out + (size_t)b * out_clip + (size_t)t * out_frame + out_off;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = ae[e] == w ? ge[e] : __float2bfloat16(0.f);
+          *reinterpret_cast<uint4*>(o + ((size_t)(w >> 1) * Wp + (w & 1)) * Cg) = *reinterpret_cast<const uint4*>(v);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (ae[e] < 4) bsum[e] += __bfloat162float(ge[e]);
+      }
     }
-    const int c0 = cg * 8;
-    const int g = c0 / Cg, cl = c0 - g * Cg;
-    const size_t opix = (size_t)g * rows_per_group + (((size_t)b * Tp + (t + pt)) * Hp + (y + ph)) * Wp + (x + pw);
-    *reinterpret_cast<uint4*>(out + opix * Cg + cl) = *reinterpret_cast<const uint4*>(v);
-    x += dx; y += dy;
-    if (x >= W) { x -= W; ++y; }
-  }
   }
   if (d_bias) {
+    if (active) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&bias_acc[my_cg * 8 + e], bsum[e]);
+      for (int e = 0; e < 8; ++e) atomicAdd(&bias_acc[cg * 8 + e], bsum[e]);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&d_bias[i], bias_acc[i]);
   }
@@ -607,13 +614,13 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
   LR_CHECK_ARG(d_pooled && argmax && out && C % 8 == 0 && Cg % 8 == 0 && C % Cg == 0 && C <= 128,
                "lr_unpool: bad args");
   if (d_bias) LR_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * C, lr_stream(stream)));
-  const int c8 = C / 8;
-  int gx = lr_div_up((long long)H * W * c8, 256 * 2);   // ~2 elements per thread per frame
-  if (gx < 1) gx = 1;
-  gx = (gx + c8 - 1) / c8 * c8;             // gx*256 is then a multiple of C/8: fixed channel group per thread
-  int gy = kNumSMs * 16 / gx;
-  if (gy < 1) gy = 1;
-  if (gy > B * T) gy = B * T;
+  const int per_frame = (H / 2) * (W / 2) * (C / 8);
+  if (per_frame == 0) return LR_OK;
+  const int gx = lr_div_up(per_frame, 256);
+  int gy = lr_div_up(kNumSMs * 8, gx);                    // ~8 resident blocks per SM
+  const int max_gy = lr_div_up(B * T, kUnpoolBatch);
+  if (gy > max_gy) gy = max_gy;
+  if (gy > 65535) gy = 65535;
   dim3 grid(gx, gy);
   unpool_kernel<<<grid, 256, 0, lr_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(d_pooled), argmax,
                                                      reinterpret_cast<__nv_bfloat16*>(out), d_bias, B, T, H, W,

@@ -40,6 +40,16 @@ __global__ void rect_geometry_kernel(const int32_t* __restrict__ rects, int N, i
   reinterpret_cast<int4*>(crop)[i] = c;
 }
 
+// image/255. as the reference computes it (a float64 division): the 256 possible quotients, evaluated by
+// the host compiler at build time (IEEE round-to-nearest, the same value the device division gives)
+struct Lut255 {
+  double v[256];
+  constexpr Lut255() : v() {
+    for (int i = 0; i < 256; ++i) v[i] = (double)i / 255.0;
+  }
+};
+__device__ const Lut255 kLut255 = Lut255();
+
 // ---------------------------------------------------------------------------------------------
 // a4.  One thread per output pixel (u fastest => 12-byte stores coalesce into 384 B per warp).
 // Source sampling follows skimage 0.14 `_warp_fast` bilinear, mode='constant', cval=0:
@@ -54,16 +64,20 @@ warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ c
   // image/255. exactly as the reference computes it (float64 division), once per CTA instead of 12
   // double-precision divisions per output pixel
   __shared__ double lut[256];
-  lut[threadIdx.x] = (double)threadIdx.x / 255.0;
-  __syncthreads();
+  __shared__ double geo[3];
   const int n = blockIdx.y;
+  lut[threadIdx.x] = kLut255.v[threadIdx.x];          // correctly rounded i/255. (compile-time table)
+  if (threadIdx.x == 0) {                             // one fp64 division per CTA, not per pixel
+    const int4 c = reinterpret_cast<const int4*>(crop)[n];
+    const double size = (double)c.z;
+    geo[0] = size / 255.0;
+    geo[1] = 0.5 * (double)c.x - 0.5 * size;
+    geo[2] = 0.5 * (double)c.y - 0.5 * size;
+  }
+  __syncthreads();
   const int pix = blockIdx.x * 256 + threadIdx.x;   // 0..65535
   const int v = pix >> 8, u = pix & 255;
-  const int4 c = reinterpret_cast<const int4*>(crop)[n];
-  const double size = (double)c.z;
-  const double step = size / 255.0;
-  const double x0 = 0.5 * (double)c.x - 0.5 * size;
-  const double y0 = 0.5 * (double)c.y - 0.5 * size;
+  const double step = geo[0], x0 = geo[1], y0 = geo[2];
   const double x = (double)u * step + x0;
   const double y = (double)v * step + y0;
   const double fx = floor(x), fy = floor(y);

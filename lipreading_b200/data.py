@@ -173,7 +173,12 @@ def load_dataset(pickle_dir, out_ext=".pkl"):
 class DevicePrefetcher:
     """Iterate a loader of HOST batches one step ahead: the (large) frames tensor of batch i+1 is
     copied host->device on a side stream while batch i computes.  Lengths and captions stay on the
-    host (the trainer wants them there).  Use pinned host tensors for truly asynchronous copies."""
+    host (the trainer wants them there).  Use pinned host tensors for truly asynchronous copies.
+
+    The device side is a ring of two persistent buffers (re-allocated only when a batch's shape
+    changes), so the steady state makes no allocator calls: the copy into slot k waits, on the side
+    stream, for the event recorded when the consumer asked for the batch after the one that last
+    used slot k (i.e. all work reading the slot has been enqueued)."""
 
     def __init__(self, loader, device):
         self.loader, self.device = loader, torch.device(device)
@@ -183,26 +188,40 @@ class DevicePrefetcher:
 
     def __iter__(self):
         side = torch.cuda.Stream(self.device)
+        slots = [None, None]            # device buffers
+        released = [None, None]         # event: consumer is done enqueueing work on the slot
 
-        def stage(batch):
+        def stage(batch, k):
+            src = batch[0]
+            buf = slots[k]
+            if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+                buf = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                slots[k] = buf
+            if released[k] is not None:
+                side.wait_event(released[k])
             with torch.cuda.stream(side):
-                frames = batch[0].to(self.device, non_blocking=True)
+                buf.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(side)
-            return frames, ev, batch[1:]
+            return buf, ev, batch[1:]
 
         it = iter(self.loader)
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), 0)
         except StopIteration:
             return
+        i = 0
         while nxt is not None:
             frames, ev, rest = nxt
             try:
-                nxt = stage(next(it))
+                nxt = stage(next(it), (i + 1) & 1)
             except StopIteration:
                 nxt = None
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
-            frames.record_stream(cur)
             yield (frames,) + tuple(rest)
+            # the consumer came back for the next batch: everything that reads `frames` is enqueued
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+            released[i & 1] = done
+            i += 1

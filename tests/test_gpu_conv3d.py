@@ -153,3 +153,35 @@ def test_conv_stack_forward_backward_matches_oracle(native_lib, cuda):
         r = params[name].grad
         err = float((p.grad.cpu() - r).abs().max() / (r.abs().max() + 1e-12))
         assert err < 3e-2, (name, err)
+
+
+@pytest.mark.parametrize("H,W,C,Cg,pad", [(50, 25, 32, 32, (0, 0, 0)), (25, 12, 64, 64, (1, 2, 2)), (12, 6, 96, 32, (1, 1, 1))])
+def test_unpool_routes_gradient_to_argmax(native_lib, cuda, H, W, C, Cg, pad):
+    """lr_unpool vs direct indexing: the arg-max position of each 2x2 window receives the pooled gradient,
+    everything else (incl. ReLU-dead units, code 4, and the odd last row/column) stays zero; d_bias = sum."""
+    from lipreading_b200 import native as N
+    g = torch.Generator().manual_seed(77)
+    B, T = 2, 5
+    PH, PW = H // 2, W // 2
+    Wp = 8
+    while Wp < W + 2 * pad[2]:
+        Wp *= 2
+    Hp = H + 2 * pad[1] + 1
+    dp = torch.randn(B, T, PH, PW, C, generator=g).to(BF)
+    am = torch.randint(0, 5, (B, T, PH, PW, C), generator=g).to(torch.uint8)
+    out = torch.zeros(C // Cg, B, T + 2, Hp, Wp, Cg, dtype=BF, device=cuda)
+    db = torch.empty(C, dtype=torch.float32, device=cuda)
+    dpc, amc = dp.to(cuda), am.to(cuda)
+    N.check(N.lib().lr_unpool(N.ptr(dpc), N.ptr(amc), N.ptr(out), N.ptr(db), B, T, H, W, C, Cg, T + 2, Hp, Wp,
+                              pad[0], pad[1], pad[2], N.stream()), "lr_unpool")
+    torch.cuda.synchronize()
+    ref = torch.zeros(B, T, H, W, C)
+    for w in range(4):
+        sel = (am == w)
+        ref[:, :, (w >> 1):2 * PH:2, (w & 1):2 * PW:2, :] = torch.where(sel, dp.float(), torch.zeros(()))
+    full = torch.zeros(C // Cg, B, T + 2, Hp, Wp, Cg)
+    for gi in range(C // Cg):
+        full[gi, :, pad[0]:pad[0] + T, pad[1]:pad[1] + H, pad[2]:pad[2] + W] = ref[..., gi * Cg:(gi + 1) * Cg]
+    assert torch.equal(out.float().cpu(), full)
+    ref_b = torch.where(am < 4, dp.float(), torch.zeros(())).sum((0, 1, 2, 3))
+    assert float((db.cpu() - ref_b).abs().max()) < 1e-3
