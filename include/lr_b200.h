@@ -165,8 +165,11 @@ int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W,
  *               arg-max byte per pooled element (0..3, 4 = ReLU-dead) into argmax (may be NULL);
  *   epi_mode 1: plain bf16 store of the valid (t,y,x) positions (used for dgrad).
  *   J = accumulators (consecutive frames) per CTA work item, 0 = choose.
- *   swap = 1: D^T = W . X^T (channels on the M lanes, the 128 tile positions on N) — the MMA then
- *   amortises its A-operand fetch over N = 128 instead of N = Cout; 0: positions on M.           */
+ *   swap (orientation) = 0: positions on M, N = Cout.  1: D^T = W . X^T (channels on the M lanes, the
+ *   128 tile positions on N).  2 (epi_mode 1, Cout = 32, 2 <= KW <= 5): positions on M and the KW
+ *   kx-taps of a filter row stacked on N = KW*Cout — one MMA per (kt,ky) instead of KW narrow ones
+ *   (an N = 32 MMA is operand-fetch bound at 40 % of the pipe); the epilogue adds the KW column
+ *   blocks with a row shift of kx each (warp shuffles + a 4-row shared-memory halo).             */
 int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
                   int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
                   int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y,

@@ -101,6 +101,7 @@ KERNEL_TIMING = None
 
 
 SWAP = False     # conv orientation: True = channels on the MMA M lanes, 128 positions on N (see lr_b200.h)
+DGRAD_KX_STACK = True   # conv2 dgrad (Cout = 32): the 5 kx-taps of a filter row share one N = 160 MMA (orientation 2)
 
 
 def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
@@ -264,7 +265,7 @@ class _ConvStack(torch.autograd.Function):
         dw2 = d2.reshape(3, 5, 5, 64, 32).permute(3, 4, 0, 1, 2)       # [tap][co][ci]
         da1 = torch.empty((B, T, H2, W2, 32), dtype=bf, device=dev)
         conv3d_native(dy2, dgrad_weight(w2.detach(), 64).to(bf), None, da1, None, B, T, H2, W2, Hp2, Wp2, 64, 1,
-                      32, (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad")
+                      32, (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad", swap=2 if DGRAD_KX_STACK else None)
         # ---- layer 1 (no input gradient: the clip is data); dY1 top-left aligned in z's geometry ----
         dy1, db1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), Hp1, Wp1)
         d1 = conv3d_wgrad_native(z, dy1, B, T, H1, W1, Hp1, Wp1, 16, 32, 1, 0, (3, 3, 3), 0)

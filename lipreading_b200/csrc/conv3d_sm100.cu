@@ -51,6 +51,10 @@ struct ConvParams {
   int n_sets;                  // TMEM accumulator sets (2 = epilogue of item i overlaps MMAs of item i+1)
   int a_set_bytes;             // bytes of one chunk set
   int a_sets;                  // chunk-set buffers (2 = next item's planes load while this item computes)
+  int kxs;                     // kx taps stacked on N (1, or KW in mode 2: one MMA per (kt,ky), N = KW*Cout; the
+                               // epilogue adds the KW column blocks with a row shift of kx each)
+  int n_eff_taps;              // weight tiles per group = KT*KH*KW / kxs
+  int smem_off_halo;           // mode 2: rows a warp's first lanes hand to the previous warp
   int swap;                    // 1: D^T = W . X^T  (M = Cout lanes, N = 128 positions): weights are the A operand
   int Mt;                      // UMMA M in swap mode (64 or 128)
   int acc_cols;                // TMEM columns per accumulator (Cout, or 128 in swap mode)
@@ -154,18 +158,21 @@ __device__ __forceinline__ void epilogue_swapped(const ConvParams& p, uint32_t t
   }
 }
 
-// KS = Cin/16 K-steps per tap (1, 2, 4); SWAP = swapped orientation (weights on M)
-template <int KS, bool SWAP>
+// KS = Cin/16 K-steps per tap (1, 2, 4); MODE 0 = positions on M, 1 = swapped orientation (weights on M),
+// 2 = positions on M with the KW kx-taps of a filter row stacked on N (plain-store epilogue only)
+template <int KS, int MODE>
 __device__ __forceinline__ void mma_tap(uint32_t d, uint64_t a, uint64_t w, uint32_t idesc, uint32_t acc) {
+  constexpr bool SWAP = MODE == 1;
   const uint64_t ma = SWAP ? w : a, mb = SWAP ? a : w;
   umma_bf16(d, ma, mb, idesc, acc);
 #pragma unroll
   for (int k = 1; k < KS; ++k) umma_bf16(d, ma + 2 * k, mb + 2 * k, idesc, 1u);
 }
 
-template <int KS, bool SWAP>
+template <int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ ConvParams p) {
+  constexpr bool SWAP = MODE == 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -180,7 +187,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   // warp index through a shuffle: tells the compiler it is warp-uniform (role dispatch, descriptor math on
   // the uniform datapath)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int n_taps = p.KT * p.KH * p.KW;
+  const int n_taps = p.n_eff_taps;          // weight tiles per channel group
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -282,8 +289,8 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             uint64_t wd = w_desc0 + (uint64_t)((uint32_t)(s * p.tps) * wtile16);
             for (int i = 0; i < nt; ++i, wd += wtile16) {
               const uint32_t off = p.tap_off[tap0 + i] + goff;
-              if (has0) mma_tap<KS, SWAP>(d0, aj0 + off, wd, p.idesc, first);
-              if (has1) mma_tap<KS, SWAP>(d1, aj1 + off, wd, p.idesc, first);
+              if (has0) mma_tap<KS, MODE>(d0, aj0 + off, wd, p.idesc, first);
+              if (has1) mma_tap<KS, MODE>(d1, aj1 + off, wd, p.idesc, first);
               first = 1u;
             }
             umma_commit(&bars[BAR_W_EMPTY + s]);    // weight stage free once these MMAs retire
@@ -347,10 +354,64 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       for (int j = 0; j < jn; ++j) {
         const int t = t0 + j;
         uint8_t* stg = stage + (size_t)((ebuf++) & (p.stage_bufs - 1)) * (128 * p.stage_pitch);
+        if (MODE == 2) {
+          // kx-stacked accumulator: lane r holds P[r][kx][n] (partial sums of filter column kx evaluated at
+          // window row r); out[r][n] = sum_kx P[r + kx][kx][n].  Rows r+kx of the same warp come by shuffle,
+          // the first kx rows of the next warp through a small shared-memory halo.  (Rows past the tile are
+          // only ever needed by junk positions x >= W.)  Cout == 32 here.
+          float* halo = reinterpret_cast<float*>(base + p.smem_off_halo);
+          const uint32_t tj = d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.acc_cols);
+          uint32_t v[32];
+          float acc[32];
+          tmem_ld32(tj, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+          for (int kx = 1; kx < p.kxs; ++kx) {
+            tmem_ld32(tj + (uint32_t)(kx * 32), v);
+            if (lane < kx) {
+              float4* h4 = reinterpret_cast<float4*>(halo + ((q * 4 + (kx - 1)) * 4 + lane) * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                h4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                    __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+            const bool in_warp = lane + kx < 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), kx);
+              if (in_warp) acc[i] += t;
+            }
+          }
+          named_bar_sync(1, 128);
+          if (q < 3) {
+            for (int kx = 1; kx < p.kxs; ++kx) {
+              if (lane + kx >= 32) {
+                const float4* h4 =
+                    reinterpret_cast<const float4*>(halo + (((q + 1) * 4 + (kx - 1)) * 4 + (lane + kx - 32)) * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 h = h4[i];
+                  acc[4 * i] += h.x; acc[4 * i + 1] += h.y; acc[4 * i + 2] += h.z; acc[4 * i + 3] += h.w;
+                }
+              }
+            }
+          }
+          uint32_t packed[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 bb = *reinterpret_cast<const float2*>(bias_s + 2 * i);
+            __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i] + bb.x, acc[2 * i + 1] + bb.y);
+            packed[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)row * p.stage_pitch);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        } else
         // TMEM -> registers -> (bias, ReLU) -> bf16 staging tile [128][Cout]
         for (int cc = 0; cc < p.Cout; cc += 32) {
           uint32_t v[32];
-          tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.Cout + cc), v);
+          tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.acc_cols + cc), v);
           uint32_t packed[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -657,20 +718,31 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   LR_CHECK_ARG(p.CH <= 256, "lr_conv3d_fwd: halo too large for one TMA box (CH=%d)", p.CH);
   p.row_bytes = Cin * 2;
   p.chunk_bytes = (p.CH * p.row_bytes + 1023) / 1024 * 1024;
-  p.wtile_bytes = Cout * p.row_bytes;
+  const int mode = swap;                       // 0 positions on M, 1 swapped, 2 kx-stacked
+  LR_CHECK_ARG(mode >= 0 && mode <= 2, "lr_conv3d_fwd: orientation must be 0, 1 or 2");
+  swap = mode == 1;
+  p.kxs = mode == 2 ? KW : 1;
+  if (mode == 2) {
+    LR_CHECK_ARG(epi_mode == 1 && Cout == 32 && KW >= 2 && KW <= 5 && KW * Cout <= 256 && (KW * Cout) % 16 == 0,
+                 "lr_conv3d_fwd: kx-stacking needs the plain-store epilogue, Cout = 32 and 2 <= KW <= 5");
+  }
+  p.n_eff_taps = KT * KH * KW / p.kxs;
+  p.wtile_bytes = p.kxs * Cout * p.row_bytes;   // one weight tile = the kxs consecutive per-tap images of a filter row
   LR_CHECK_ARG(p.wtile_bytes % 1024 == 0, "lr_conv3d_fwd: Cout*Cin*2 must be a multiple of 1024");
   p.stage_pitch = Cout * 2 + 16;
   p.swap = swap ? 1 : 0;
   p.Mt = Cout <= 64 ? 64 : 128;
-  p.acc_cols = swap ? 128 : Cout;
+  p.acc_cols = swap ? 128 : p.kxs * Cout;
   // swap mode pools in registers (no staging tile) but reads Mt weight rows per MMA: keep that many
   // bytes of slack behind the weight ring
   const int stage_bytes = swap ? p.Mt * p.row_bytes : 128 * p.stage_pitch;
-  const int smem_cap = 227 * 1024 - 1024 - 512;     // minus alignment slack and the bias copy
+  const int halo_bytes = mode == 2 ? 4 * 4 * 4 * 32 * (int)sizeof(float) : 0;
+  const int smem_cap = 227 * 1024 - 1024 - 512 - halo_bytes;     // minus alignment slack, bias copy, halo
   int fixed = 2 * p.wtile_bytes + stage_bytes + 256;      // at least a 2-deep ring of single taps
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
   int n_sets = (512 / p.acc_cols) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
   if (getenv("LR_CONV_SETS")) { int v = atoi(getenv("LR_CONV_SETS")); if (v == 1 || (v == 2 && 512 / p.acc_cols >= 2)) n_sets = v; }   // tuning hook
+  if (mode == 2) n_sets = 1;                         // wide accumulators: weight reuse (J) beats overlap
   int Jmax = 512 / p.acc_cols / n_sets;
   if (J <= 0 || J > Jmax) J = Jmax;
   if (J > 2 * kMmaWarps) J = 2 * kMmaWarps;      // each issuing warp owns at most two accumulators
@@ -694,27 +766,27 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.oTp = oTp; p.oHp = oHp; p.oWp = oWp; p.o_t = o_t; p.o_y = o_y; p.o_x = o_x;
   p.rows_per_group = (long long)B * p.Tp * p.Hp * p.Wp;
   p.idesc = swap ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(p.Mt >> 4) << 24))
-                 : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
+                 : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.acc_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
   const uint32_t layout = p.row_bytes == 32 ? 6u : (p.row_bytes == 64 ? 4u : 2u);
   const uint32_t sbo = (uint32_t)(8 * p.row_bytes) >> 4;
   p.desc_hi = sbo | (1u << 14) | (layout << 29);
   p.a_set_bytes = (J + KT - 1) * CG * p.chunk_bytes;
   // second chunk set when it still leaves room for a 2-deep ring of whole filter rows (or 2 taps)
   {
-    const int want_w = 2 * (KW < 2 ? 2 : KW) * p.wtile_bytes;
+    const int want_w = 2 * (KW < 2 || mode == 2 ? 2 : KW) * p.wtile_bytes;
     p.a_sets = (2 * p.a_set_bytes + stage_bytes + 256 + want_w <= smem_cap) ? 2 : 1;
   }
   p.smem_off_w = p.a_sets * p.a_set_bytes;
   {
-    // weight ring: as many taps per stage as fit (whole filter rows when possible), 3 stages deep
-    const int n_taps_h = KT * KH * KW;
+    // weight ring: as many tiles per stage as fit (whole filter rows when possible), 3 stages deep
+    const int n_taps_h = p.n_eff_taps;
     const int avail = smem_cap - p.smem_off_w - stage_bytes - 256;
     int stages = 3;
     int tps = avail / (stages * p.wtile_bytes);
     if (tps < 1) { stages = 2; tps = avail / (stages * p.wtile_bytes); }
     if (tps > n_taps_h) tps = n_taps_h;
     if (tps > 32) tps = 32;
-    if (tps >= KW) tps = tps / KW * KW;
+    if (mode != 2 && tps >= KW) tps = tps / KW * KW;
     LR_CHECK_ARG(tps >= 1, "lr_conv3d_fwd: weight ring does not fit shared memory");
     if (tps == n_taps_h && stages > 2) stages = 2;
     p.tps = tps;
@@ -723,7 +795,8 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.smem_off_stage = p.smem_off_w + p.w_stages * p.tps * p.wtile_bytes;
   // a second staging tile (drops one of the two named barriers per accumulator) when shared memory is left over
   p.stage_bufs = (!swap && p.smem_off_stage + 2 * stage_bytes + 256 <= smem_cap) ? 2 : 1;
-  p.smem_off_bar = p.smem_off_stage + p.stage_bufs * stage_bytes;
+  p.smem_off_halo = p.smem_off_stage + p.stage_bufs * stage_bytes;
+  p.smem_off_bar = p.smem_off_halo + halo_bytes;
   p.cg_shift = -1;
   for (int sft = 0; sft < 8; ++sft) {
     if ((Cout >> 3) == (1 << sft)) p.cg_shift = sft;
@@ -740,23 +813,26 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
 
   for (int kt = 0, tap = 0; kt < KT; ++kt)
     for (int ky = 0; ky < KH; ++ky)
-      for (int kx = 0; kx < KW; ++kx, ++tap)
+      for (int kx = 0; kx < KW; kx += p.kxs, ++tap)
         p.tap_off[tap] = (uint32_t)kt * ((uint32_t)p.chunk_bytes >> 4) +
                          (((uint32_t)(ky * Wp + kx) * (uint32_t)p.row_bytes) >> 4);
 
   int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-#define LR_LAUNCH_CONV(KS, SW)                                                                              \
+#define LR_LAUNCH_CONV(KS, MD)                                                                              \
   do {                                                                                                      \
-    LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel<KS, SW>,                                       \
+    LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel<KS, MD>,                                       \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));      \
-    conv3d_tcgen05_kernel<KS, SW><<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);             \
+    conv3d_tcgen05_kernel<KS, MD><<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);             \
+  } while (0)
+#define LR_LAUNCH_CONV_KS(MD)                                                                               \
+  do {                                                                                                      \
+    if (ks == 1) LR_LAUNCH_CONV(1, MD); else if (ks == 2) LR_LAUNCH_CONV(2, MD); else LR_LAUNCH_CONV(4, MD); \
   } while (0)
   const int ks = Cin / 16;
-  if (p.swap) {
-    if (ks == 1) LR_LAUNCH_CONV(1, true); else if (ks == 2) LR_LAUNCH_CONV(2, true); else LR_LAUNCH_CONV(4, true);
-  } else {
-    if (ks == 1) LR_LAUNCH_CONV(1, false); else if (ks == 2) LR_LAUNCH_CONV(2, false); else LR_LAUNCH_CONV(4, false);
-  }
+  if (mode == 1) LR_LAUNCH_CONV_KS(1);
+  else if (mode == 2) LR_LAUNCH_CONV_KS(2);
+  else LR_LAUNCH_CONV_KS(0);
+#undef LR_LAUNCH_CONV_KS
 #undef LR_LAUNCH_CONV
   LR_CHECK_LAUNCH();
   return LR_OK;

@@ -40,33 +40,48 @@ __global__ void rect_geometry_kernel(const int32_t* __restrict__ rects, int N, i
   reinterpret_cast<int4*>(crop)[i] = c;
 }
 
-// image/255. as the reference computes it (a float64 division): the 256 possible quotients, evaluated by
-// the host compiler at build time (IEEE round-to-nearest, the same value the device division gives)
-struct Lut255 {
-  double v[256];
-  constexpr Lut255() : v() {
-    for (int i = 0; i < 256; ++i) v[i] = (double)i / 255.0;
-  }
-};
-__device__ const Lut255 kLut255 = Lut255();
-
 // ---------------------------------------------------------------------------------------------
-// a4.  One thread per output pixel (u fastest => 12-byte stores coalesce into 384 B per warp).
+// a4.  One thread per output pixel (u fastest).
 // Source sampling follows skimage 0.14 `_warp_fast` bilinear, mode='constant', cval=0:
 //   (x,y) = T^-1 (u,v) ; floor/ceil taps ; out-of-image taps contribute 0.
 // The similarity fitted to the three crop corners is an exact axis-aligned scale + shift, so
 //   x = u*size/255 + (cx - size/2),  y = v*size/255 + (cy - size/2)
-// evaluated in fp64 like the reference (fp32 coordinates at x~1000 would already cost 1e-4).
-// Only the <= size^2 window of the frame is ever read (the reference divides the whole frame).
+// evaluated in fp64 like the reference (fp32 coordinates at x~1000 would already cost 1e-4); the one
+// fp64 division is done once per CTA.  The interpolation itself runs in fp32 on the raw bytes and is
+// scaled by 1/255 at the end: the output is float32, and this differs from the reference's float64
+// `image/255.` + interpolation by at most an ulp of that float32 (test tolerance 1e-6).
+// Only the <= size^2 window of the frame is ever read (the reference divides the whole frame); the two
+// taps of a source row are 6 adjacent bytes, fetched as aligned 32-bit words instead of 6 byte loads
+// (the kernel is LSU-bound, not HBM-bound, with byte loads).
+
+// bytes off .. off+5 of buf (zero outside [0, total)); buf is 4-byte aligned
+__device__ __forceinline__ void load6(const uint8_t* __restrict__ buf, long long off, long long total,
+                                      uint32_t (&b)[6]) {
+  const long long w = off & ~3LL;
+  const int sh = (int)(off & 3);
+  uint32_t x[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const long long wi = w + 4 * i;
+    if (wi >= 0 && wi + 4 <= total) {
+      x[i] = *reinterpret_cast<const uint32_t*>(buf + wi);
+    } else {
+      x[i] = 0;
+      for (int k = 0; k < 4; ++k)
+        if (wi + k >= 0 && wi + k < total) x[i] |= (uint32_t)buf[wi + k] << (8 * k);
+    }
+  }
+  const uint32_t lo = __funnelshift_r(x[0], x[1], 8 * sh);       // bytes sh .. sh+3
+  const uint32_t hi = __funnelshift_r(x[1], x[2], 8 * sh);       // bytes sh+4 .. sh+7
+  b[0] = lo & 0xff; b[1] = (lo >> 8) & 0xff; b[2] = (lo >> 16) & 0xff; b[3] = lo >> 24;
+  b[4] = hi & 0xff; b[5] = (hi >> 8) & 0xff;
+}
+
 __global__ void __launch_bounds__(256)
 warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ crop,
-               float* __restrict__ out, int H, int W) {
-  // image/255. exactly as the reference computes it (float64 division), once per CTA instead of 12
-  // double-precision divisions per output pixel
-  __shared__ double lut[256];
+               float* __restrict__ out, int H, int W, long long total) {
   __shared__ double geo[3];
   const int n = blockIdx.y;
-  lut[threadIdx.x] = kLut255.v[threadIdx.x];          // correctly rounded i/255. (compile-time table)
   if (threadIdx.x == 0) {                             // one fp64 division per CTA, not per pixel
     const int4 c = reinterpret_cast<const int4*>(crop)[n];
     const double size = (double)c.z;
@@ -83,24 +98,32 @@ warp256_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ c
   const double fx = floor(x), fy = floor(y);
   const int minc = (int)fx, minr = (int)fy;
   const int maxc = (int)ceil(x), maxr = (int)ceil(y);
-  const double dc = x - fx, dr = y - fy;
-  const uint8_t* img = frames + (size_t)n * H * W * 3;
+  const float dc = (float)(x - fx), dr = (float)(y - fy);
   const bool r0 = minr >= 0 && minr < H, r1 = maxr >= 0 && maxr < H;
   const bool c0 = minc >= 0 && minc < W, c1 = maxc >= 0 && maxc < W;
-  const uint8_t* p00 = img + ((size_t)minr * W + minc) * 3;
-  const uint8_t* p01 = img + ((size_t)minr * W + maxc) * 3;
-  const uint8_t* p10 = img + ((size_t)maxr * W + minc) * 3;
-  const uint8_t* p11 = img + ((size_t)maxr * W + maxc) * 3;
+  const int sel = (maxc == minc) ? 0 : 3;            // integral x: both taps are the same pixel
+  const long long frame = (long long)n * H * W * 3;
+  uint32_t top[6] = {0, 0, 0, 0, 0, 0}, bot[6] = {0, 0, 0, 0, 0, 0};
+  if (r0 && (c0 || c1)) load6(frames, frame + ((long long)minr * W + minc) * 3, total, top);
+  if (r1 && (c0 || c1)) {
+    if (maxr == minr) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) bot[i] = top[i];
+    } else {
+      load6(frames, frame + ((long long)maxr * W + minc) * 3, total, bot);
+    }
+  }
   float res[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    double v00 = (r0 && c0) ? lut[p00[ch]] : 0.0;
-    double v01 = (r0 && c1) ? lut[p01[ch]] : 0.0;
-    double v10 = (r1 && c0) ? lut[p10[ch]] : 0.0;
-    double v11 = (r1 && c1) ? lut[p11[ch]] : 0.0;
-    double top = (1.0 - dc) * v00 + dc * v01;
-    double bot = (1.0 - dc) * v10 + dc * v11;
-    res[ch] = (float)((1.0 - dr) * top + dr * bot);
+    const float v00 = c0 ? (float)top[ch] : 0.f;
+    const float v01 = c1 ? (float)(sel ? top[3 + ch] : top[ch]) : 0.f;
+    const float v10 = c0 ? (float)bot[ch] : 0.f;
+    const float v11 = c1 ? (float)(sel ? bot[3 + ch] : bot[ch]) : 0.f;
+    // lerp as a + d*(b-a): exact when the taps are equal, so a flat 255 region stays exactly 1.0
+    const float t = fmaf(dc, v01 - v00, v00);
+    const float bt = fmaf(dc, v11 - v10, v10);
+    res[ch] = __fdiv_rn(fmaf(dr, bt - t, t), 255.0f);
   }
   // stage the CTA's 256 pixels x 3 floats in shared memory and write them as 192 coalesced float4
   // (a direct 12-byte-strided store makes every warp store touch 12 partial sectors)
@@ -244,8 +267,9 @@ extern "C" int lr_warp256(const uint8_t* frames, const int32_t* crop, float* out
                           void* stream) {
   LR_CHECK_ARG(frames && crop && out && N > 0 && H > 0 && W > 0, "lr_warp256: bad args");
   LR_CHECK_ARG(N <= 65535, "lr_warp256: at most 65535 frames per call");
+  LR_CHECK_ARG((reinterpret_cast<uintptr_t>(frames) & 3) == 0, "lr_warp256: frames must be 4-byte aligned");
   dim3 grid(256, N);
-  warp256_kernel<<<grid, 256, 0, lr_stream(stream)>>>(frames, crop, out, H, W);
+  warp256_kernel<<<grid, 256, 0, lr_stream(stream)>>>(frames, crop, out, H, W, (long long)N * H * W * 3);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

@@ -32,10 +32,14 @@ def _padded(x_ndhwc, pad, Wp, Hp=None):
     (32, 1, 32, (1, 1, 1), 8, 8, 8, 3, 1),         # 1x1x1: no shifts at all
     (32, 1, 32, (1, 1, 3), 8, 6, 8, 3, 1),         # x shifts only
     (32, 1, 32, (1, 3, 1), 8, 8, 8, 3, 1),         # y shifts only
+    (64, 1, 32, (3, 5, 5), 25, 12, 16, 9, 3),      # conv2 dgrad geometry, several items per CTA
+    (16, 1, 32, (3, 3, 3), 22, 25, 32, 7, 2),      # ragged last tile (H not a multiple of the tile rows)
 ])
-@pytest.mark.parametrize("swap", [0, 1])
+@pytest.mark.parametrize("swap", [0, 1, 2])       # 0 positions on M, 1 swapped, 2 kx-taps stacked on N (Cout = 32)
 def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, T, B, swap):
     from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
+    if swap == 2 and (Cout != 32 or K[2] < 2):
+        pytest.skip("kx-stacking: Cout = 32 and KW >= 2 only")
     g = torch.Generator().manual_seed(1234)
     C = Cin * CG
     pad = tuple((k - 1) // 2 for k in K)
