@@ -169,7 +169,11 @@ int lr_clip_s2d(const uint8_t* clip, void* out_bf16, int B, int T, int H, int W,
  *   128 tile positions on N).  2 (epi_mode 1, Cout = 32, 2 <= KW <= 5): positions on M and the KW
  *   kx-taps of a filter row stacked on N = KW*Cout — one MMA per (kt,ky) instead of KW narrow ones
  *   (an N = 32 MMA is operand-fetch bound at 40 % of the pipe); the epilogue adds the KW column
- *   blocks with a row shift of kx each (warp shuffles + a 4-row shared-memory halo).             */
+ *   blocks with a row shift of kx each (warp shuffles + a 4-row shared-memory halo).
+ *   3: positions on M and the KT kt-taps of a spatial tap stacked on N: input plane c times
+ *   [W(kt=KT-1); ...; W(kt=0)] lands on the accumulators of the consecutive output frames c-KT+1 .. c
+ *   (side by side in TMEM), N = KT*Cout (<= 256) per MMA, same epilogues as 0; `w` must come from
+ *   lr_pack_conv_weights_kt.                                                                       */
 int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
                   int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
                   int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y,
@@ -183,6 +187,9 @@ int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint
 /* bf16 [Cout][CG][taps][Cin] -> [CG][taps][Cout x Cin] tile images, 16-byte chunks pre-swizzled so a
  * stage of taps is ONE contiguous bulk copy into shared memory (what lr_conv3d_fwd expects as `w`). */
 int lr_pack_conv_weights(const void* w, void* out, int Cout, int CG, int taps, int Cin, void* stream);
+/* Same tile images in the order orientation 3 reads them: [CG][KH*KW][KT, kt descending][Cout x Cin]. */
+int lr_pack_conv_weights_kt(const void* w, void* out, int Cout, int CG, int KT, int KHW, int Cin,
+                            void* stream);
 /* Weight gradient: out[tap][64][Nc] fp32 = sum_p dy[p,:] (x) x[p+shift(tap),:] on tcgen05 (M=64,
  * MN-major operands), split over CTAs and reduced in a fixed order.  x [B][T+KT-1][Hp][Wp][Cx];
  * dy [Gy][B][T+KT-1][Hp][Wp][Cy] zero except its interior, which starts dy_off rows in.
@@ -211,8 +218,22 @@ int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_b
 /* Device buffer (148*8 int64, or NULL to stop) that subsequent lr_conv3d_fwd launches fill with the
  * cycles each warp role spent waiting on its barriers (tools/conv_waits.py).                      */
 void lr_conv3d_set_debug(long long* device_buffer);
+/* Diagnostics only (results become wrong): bit 0 skips the epilogue work, bit 1 loads each weight stage once,
+ * bit 2 loads each input chunk set once — shows which role limits a layer (tools/conv_waits.py --skip). */
+void lr_conv3d_set_debug_skip(int mask);
 long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
                              int n_acc, int a_tiles, int iters, int a_shift_rows, void* stream);
+
+/* Same, for a trip of 8 MMAs (M = 128, K-major 64-byte rows) with individual N, accumulator column and B row-group
+ * offsets: what differently shaped MMAs on overlapping accumulator ranges cost (tools/umma_pattern.py);
+ * commit_every > 0 adds a tcgen05.commit after every that many MMAs (multiple of 8).             */
+long long lr_umma_pattern_bench(const int* n, const int* dcol, const int* bblk, int iters, int commit_every,
+                                void* stream);
+
+/* Cycles for tiles*n_ops*KS MMAs (M = 128, K-major 64-byte rows) issued by ONE thread of a `threads`-thread block
+ * from a loop whose descriptors advance by loop-carried adds (variant 0) or stay constant (variant 1). */
+long long lr_umma_issue_bench(int N, int KS, int tiles, int n_ops, int a_step_bytes, int d_step, int threads,
+                              int variant, void* stream);
 
 #ifdef __cplusplus
 }

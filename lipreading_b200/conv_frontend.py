@@ -24,6 +24,7 @@ N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 N.register("lr_unpool", _i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp])
 N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 21 + [_vp])
 N.register("lr_pack_conv_weights", _i, [_vp, _vp, _i, _i, _i, _i, _vp])
+N.register("lr_pack_conv_weights_kt", _i, [_vp, _vp, _i, _i, _i, _i, _i, _vp])
 N.register("lr_conv3d_wgrad_out_floats", N._sz, [_i] * 5)
 N.register("lr_conv3d_wgrad_workspace", N._sz, [_i] * 6)
 N.register("lr_conv3d_wgrad", _i, [_vp, _vp, _vp, _vp, N._sz] + [_i] * 9 + [N._i64] + [_i] * 8 + [_vp])
@@ -100,8 +101,10 @@ def feature_dim(H, W):
 KERNEL_TIMING = None
 
 
-SWAP = False     # conv orientation: True = channels on the MMA M lanes, 128 positions on N (see lr_b200.h)
-DGRAD_KX_STACK = True   # conv2 dgrad (Cout = 32): the 5 kx-taps of a filter row share one N = 160 MMA (orientation 2)
+# conv orientation (see lr_b200.h): 0 = one MMA per tap, 1 = channels on the MMA M lanes, 3 = the KT kt-taps of a
+# spatial tap stacked on N (input plane c x [W(kt=KT-1);..;W(kt=0)] -> accumulators of frames c-KT+1..c)
+SWAP = 3
+DGRAD_KX_STACK = False  # conv2 dgrad (Cout = 32): the 5 kx-taps of a filter row share one N = 160 MMA (orientation 2)
 
 
 def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
@@ -110,8 +113,15 @@ def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, e
     taps = K[0] * K[1] * K[2]
     w = N.cont(w)
     assert w.dtype == torch.bfloat16 and w.numel() == Cout * CG * taps * Cin
+    mode = int(SWAP if swap is None else swap)
+    if mode == 3 and K[0] == 1:
+        mode = 0                                   # nothing to stack
     wp = torch.empty_like(w)
-    N.check(N.lib().lr_pack_conv_weights(N.ptr(w), N.ptr(wp), Cout, CG, taps, Cin, N.stream()), "lr_pack_conv_weights")
+    if mode == 3:
+        N.check(N.lib().lr_pack_conv_weights_kt(N.ptr(w), N.ptr(wp), Cout, CG, K[0], K[1] * K[2], Cin, N.stream()),
+                "lr_pack_conv_weights_kt")
+    else:
+        N.check(N.lib().lr_pack_conv_weights(N.ptr(w), N.ptr(wp), Cout, CG, taps, Cin, N.stream()), "lr_pack_conv_weights")
     w = wp
     rec = KERNEL_TIMING
     if rec is not None:
@@ -119,7 +129,7 @@ def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, e
         e0.record()
     N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Hp, Wp,
                                   Cin, CG, Cout, K[0], K[1], K[2], epi_mode, ovol[0], ovol[1], ovol[2],
-                                  ooff[0], ooff[1], ooff[2], J, int(SWAP if swap is None else swap), N.stream()),
+                                  ooff[0], ooff[1], ooff[2], J, mode, N.stream()),
             "lr_conv3d_fwd")
     if rec is not None:
         e1.record()

@@ -112,12 +112,13 @@ __device__ __forceinline__ void lr_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ void lr_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lr_smem_u32(bar)) : "memory");
 }
-// Bounded wait: a lost transaction must become a trap (error return), never a hung GPU.
+// Bounded wait: a lost transaction must become a trap (error return), never a hung GPU.  The fast path (phase
+// already complete) is a single try_wait: no clock read, nothing else between two MMA issue bursts.
 __device__ __forceinline__ void lr_mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = lr_smem_u32(bar);
   uint32_t done = 0;
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -126,7 +127,32 @@ __device__ __forceinline__ void lr_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000LL) break;     // ~2 s at 2 GHz
+    if (spins == 0) t0 = clock64();
+    else if ((spins & 255u) == 0 && clock64() - t0 > 4000000000LL) break;     // ~2 s at 2 GHz
+  }
+  printf("lr_b200: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+         blockIdx.y, threadIdx.x, addr, parity);
+  __trap();
+}
+// Same for waiters that are not on the critical path (producer waiting for a free slot, epilogue waiting for an
+// accumulator): back off between polls so the spinning warp does not take issue slots from the MMA-issuing warp
+// that shares its scheduler.
+__device__ __forceinline__ void lr_mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = lr_smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (int spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(100);
+    if (spins == 0) t0 = clock64();
+    else if ((spins & 1023) == 0 && clock64() - t0 > 4000000000LL) break;
   }
   printf("lr_b200: mbarrier wait timed out (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
          blockIdx.y, threadIdx.x, addr, parity);

@@ -83,12 +83,24 @@ struct ConvParams {
   int cg_shift, wp_shift;      // log2(Cout/8) (or -1) and log2(Wp) for the plain-store epilogue
   uint32_t tap_off[kMaxTaps];  // per tap: descriptor offset (16-byte units) of its window inside a chunk set
                                // = kt * chunk + (ky*Wp + kx) rows — read with uniform constant loads
+  int n_issuers;               // MMA-issuing warps that take part in the barrier protocol
+  int Jg;                      // mode 3: frames per issuing warp (J split into n_issuers runs)
+  int stage_fence;             // diagnostics: tcgen05.fence::after_thread_sync after every weight-stage wait (old behaviour)
+  int skip;                    // diagnostics (lr_conv3d_set_debug_skip): 1 no epilogue work, 2 weights loaded once,
+                               // 4 input chunks loaded once — wrong results, used to find the limiting role
 };
 
 __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
   if (!on) { lr_mbar_wait(bar, parity); return; }
   const long long t = clock64();
   lr_mbar_wait(bar, parity);
+  acc += clock64() - t;
+}
+// off the critical path (producer / epilogue): polls with a back-off
+__device__ __forceinline__ void timed_wait_relaxed(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+  if (!on) { lr_mbar_wait_relaxed(bar, parity); return; }
+  const long long t = clock64();
+  lr_mbar_wait_relaxed(bar, parity);
   acc += clock64() - t;
 }
 
@@ -158,8 +170,21 @@ __device__ __forceinline__ void epilogue_swapped(const ConvParams& p, uint32_t t
   }
 }
 
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // KS = Cin/16 K-steps per tap (1, 2, 4); MODE 0 = positions on M, 1 = swapped orientation (weights on M),
-// 2 = positions on M with the KW kx-taps of a filter row stacked on N (plain-store epilogue only)
+// 2 = positions on M with the KW kx-taps of a filter row stacked on N (plain-store epilogue only),
+// 3 = positions on M with the KT kt-taps stacked on N: input plane c times [W(kt=KT-1); ...; W(kt=0)] lands on the
+//     accumulators of the consecutive output frames c-KT+1 .. c, which sit side by side in TMEM — N = KT*Cout
+//     per MMA with no epilogue change.  All MMAs accumulate; the epilogue re-zeroes each accumulator after
+//     draining it (tcgen05.st), so no "first MMA" bookkeeping exists and one thread issues everything in order.
 template <int KS, int MODE>
 __device__ __forceinline__ void mma_tap(uint32_t d, uint64_t a, uint64_t w, uint32_t idesc, uint32_t acc) {
   constexpr bool SWAP = MODE == 1;
@@ -192,13 +217,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       lr_mbar_init(&bars[BAR_A_FULL + i], 1);
-      lr_mbar_init(&bars[BAR_A_EMPTY + i], kMmaWarps);
-      lr_mbar_init(&bars[BAR_ACC_FULL + i], kMmaWarps);
+      lr_mbar_init(&bars[BAR_A_EMPTY + i], p.n_issuers);
+      lr_mbar_init(&bars[BAR_ACC_FULL + i], p.n_issuers);
       lr_mbar_init(&bars[BAR_ACC_EMPTY + i], 4);
     }
     for (int s = 0; s < kWStages; ++s) {
       lr_mbar_init(&bars[BAR_W_FULL + s], 1);
-      lr_mbar_init(&bars[BAR_W_EMPTY + s], kMmaWarps);
+      lr_mbar_init(&bars[BAR_W_EMPTY + s], p.n_issuers);
     }
     lr_fence_barrier_init();
   }
@@ -207,6 +232,16 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (MODE == 3) {
+    // every MMA accumulates: the accumulators start (and are left by the epilogue) at zero
+    if (warp > kMmaWarps) {
+      for (int c = 0; c < p.tmem_cols; c += 32) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c);
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   const bool dbg_on = p.dbg != nullptr;
   long long dbg0 = 0, dbg1 = 0, dbg2 = 0;
   const long long t_start = clock64();
@@ -223,8 +258,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int n_chunks = jn + p.KT - 1;
       const int aset = it & (p.a_sets - 1);
       uint8_t* a_set = a_smem + (size_t)aset * p.a_set_bytes;
-      timed_wait(&bars[BAR_A_EMPTY + aset], ((it / p.a_sets) & 1) ^ 1, dbg0, dbg_on);
-      if (elect_one()) {
+      timed_wait_relaxed(&bars[BAR_A_EMPTY + aset], ((it / p.a_sets) & 1) ^ 1, dbg0, dbg_on);
+      if ((p.skip & 4) && it >= p.a_sets) {
+        if (elect_one()) lr_mbar_arrive(&bars[BAR_A_FULL + aset]);
+      } else if (elect_one()) {
         lr_mbar_expect_tx(&bars[BAR_A_FULL + aset], (uint32_t)(n_chunks * p.CG * p.CH * p.row_bytes));
         for (int g = 0; g < p.CG; ++g)
           for (int c = 0; c < n_chunks; ++c) {
@@ -239,8 +276,10 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps, ++wn) {
           const int s = wn % p.w_stages;
           const int nt = min(p.tps, n_taps - tap0);
-          timed_wait(&bars[BAR_W_EMPTY + s], ((wn / p.w_stages) & 1) ^ 1, dbg1, dbg_on);
-          if (elect_one()) {
+          timed_wait_relaxed(&bars[BAR_W_EMPTY + s], ((wn / p.w_stages) & 1) ^ 1, dbg1, dbg_on);
+          if ((p.skip & 2) && wn >= (uint32_t)p.w_stages) {
+            if (elect_one()) lr_mbar_arrive(&bars[BAR_W_FULL + s]);
+          } else if (elect_one()) {
             // weights arrive as pre-swizzled tile images (lr_pack_conv_weights): one contiguous bulk copy
             // per stage instead of Cout narrow strided rows per tap
             const uint32_t bytes = (uint32_t)(nt * p.wtile_bytes);
@@ -250,6 +289,107 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           }
           __syncwarp();
         }
+    }
+  } else if (MODE == 3 && warp <= kMmaWarps) {
+    // ===================== mode 3: ONE issuing warp, kt-stacked MMAs in program order ===================
+    // A single thread feeds the tensor pipe, so the scalar work per MMA is a handful of uniform adds: no
+    // tables, no divisions, no constant-bank loads in the inner loops.  Per spatial tap the chunks c = 0 ..
+    // jn+KT-2 are walked in three phases (hi = newest kt a chunk feeds, lo = oldest):
+    //   ramp-up   c <  KT-1      : N grows by Cout, the weight window slides towards kt = 0, D stays at frame 0
+    //   steady    KT-1 <= c < jn : N = KT*Cout, whole tile, D advances one frame per chunk
+    //   ramp-down c >= jn        : N shrinks by Cout, D advances
+    // (groups with fewer than KT-1 frames — a clip's tail — fall back to one MMA per (frame, kt).)
+    // n_issuers = G warps split the J frames of an item into G runs of Jg consecutive frames; each warp stacks
+    // inside its own run and owns its accumulators, so the result does not depend on how the warps interleave, and
+    // one warp's stage-boundary bookkeeping (barrier wait, commit) is covered by the others' queued MMAs.
+    if (warp <= p.n_issuers) {
+      const int g_first = (warp - 1) * p.Jg;      // first frame (= first chunk) of this warp's run
+      int it = 0;
+      int ws = 0;                     // weight ring slot and its phase bit, advanced without divisions
+      uint32_t wphase = 0;
+      const uint64_t a_desc0 = make_desc(lr_smem_u32(a_smem), p.desc_hi);
+      const uint64_t w_desc0 = make_desc(lr_smem_u32(w_smem), p.desc_hi);
+      const uint32_t wtile16 = (uint32_t)p.wtile_bytes >> 4;
+      const uint32_t group16 = (uint32_t)(p.J + p.KT - 1) * ((uint32_t)p.chunk_bytes >> 4);
+      // (the skip bits 8..128 freeze one descriptor component each — diagnostics, wrong results)
+      const uint32_t chunk16 = (p.skip & 16) ? 0u : (uint32_t)p.chunk_bytes >> 4;
+      const uint32_t blk16 = (p.skip & 64) ? 0u : ((uint32_t)p.Cout * (uint32_t)p.row_bytes) >> 4;   // one kt block of a tile
+      const uint32_t istep = (p.skip & 128) ? 0u : ((uint32_t)p.Cout >> 3) << 17;   // +Cout on the descriptor's N
+      const uint32_t idesc1 = p.idesc;                                              // N = Cout
+      const uint32_t cout = (p.skip & 32) ? 0u : (uint32_t)p.Cout;
+      const uint32_t tapmask = (p.skip & 8) ? 0u : 0xffffffffu;
+      const int KT = p.KT;
+      const int tiles_per_group = p.n_tgroups * p.n_ytiles;
+      int rem = blockIdx.x % tiles_per_group;                                        // item index inside its clip
+      const int rem_step = gridDim.x % tiles_per_group;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int tg = rem / p.n_ytiles;
+        rem += rem_step;
+        if (rem >= tiles_per_group) rem -= tiles_per_group;
+        const int jn = min(p.Jg, min(p.J, p.T - tg * p.J) - g_first);     // frames of this warp's run (<= 0: none)
+        const int set = it & (p.n_sets - 1);
+        const uint32_t d_base = tmem_base + (uint32_t)((set * p.J + g_first) * p.acc_cols);
+        timed_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1, dbg0, dbg_on);
+        const int aset = it & (p.a_sets - 1);
+        timed_wait(&bars[BAR_A_FULL + aset], (it / p.a_sets) & 1, dbg1, dbg_on);
+        tc_fence_after();
+        const uint64_t a_item = a_desc0 + (uint64_t)(aset * (p.a_set_bytes >> 4)) +
+                                (uint64_t)((uint32_t)g_first * ((uint32_t)p.chunk_bytes >> 4));
+        const int n_steady = jn - (KT - 1);                 // chunks that feed all KT taps (< 0: tail fallback)
+        for (int g = 0; g < p.CG; ++g) {
+          const uint32_t goff = (uint32_t)g * group16;
+          for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps) {
+            const int nt = min(p.tps, n_taps - tap0);
+            // (no tcgen05 fence: the weights were written by the async proxy, the mbarrier's complete_tx orders them)
+            timed_wait(&bars[BAR_W_FULL + ws], wphase, dbg2, dbg_on);
+            if (elect_one()) {
+              uint64_t wd = w_desc0 + (uint64_t)((uint32_t)(ws * p.tps) * wtile16);
+              uint32_t off_next = p.tap_off[tap0];
+              for (int i = 0; i < nt; ++i, wd += wtile16) {
+                uint64_t a = a_item + (uint64_t)((off_next & tapmask) + goff);
+                if (i + 1 < nt) off_next = p.tap_off[tap0 + i + 1];      // fetched a tile ahead of its use
+                if (n_steady >= 0) {
+                  uint64_t b = wd + (uint64_t)((uint32_t)(KT - 1) * blk16);
+                  uint32_t d = d_base, id = idesc1;
+                  for (int c = 0; c < KT - 1; ++c) {                      // ramp-up
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
+                    a += chunk16; b -= blk16; id += istep;
+                  }
+#pragma unroll 2
+                  for (int c = 0; c < n_steady; ++c) {                    // steady: b = wd, N = KT*Cout
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
+                    a += chunk16; d += cout;
+                  }
+                  for (int c = 0; c < KT - 1; ++c) {                      // ramp-down
+                    id -= istep;
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
+                    a += chunk16; d += cout;
+                  }
+                } else {
+                  for (int j = 0; j < jn; ++j)
+                    for (int kt = 0; kt < KT; ++kt) {
+                      const uint64_t aa = a + (uint64_t)((uint32_t)(j + kt) * chunk16);
+                      const uint64_t bb = wd + (uint64_t)((uint32_t)(KT - 1 - kt) * blk16);
+#pragma unroll
+                      for (int k = 0; k < KS; ++k) umma_bf16(d_base + (uint32_t)j * cout, aa + 2 * k, bb + 2 * k, idesc1, 1u);
+                    }
+                }
+              }
+              umma_commit(&bars[BAR_W_EMPTY + ws]);
+            }
+            __syncwarp();
+            if (++ws == p.w_stages) { ws = 0; wphase ^= 1u; }
+          }
+        }
+        if (elect_one()) {
+          umma_commit(&bars[BAR_A_EMPTY + aset]);
+          umma_commit(&bars[BAR_ACC_FULL + set]);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp <= kMmaWarps) {
     // ===================== MMA issuers: warp m issues accumulators j = m and m+4 ========================
@@ -284,7 +424,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           const int s = wn % p.w_stages;
           const int nt = min(p.tps, n_taps - tap0);
           timed_wait(&bars[BAR_W_FULL + s], (wn / p.w_stages) & 1, dbg2, dbg_on);
-          tc_fence_after();
+          if (p.stage_fence) tc_fence_after();
           if (elect_one()) {
             uint64_t wd = w_desc0 + (uint64_t)((uint32_t)(s * p.tps) * wtile16);
             for (int i = 0; i < nt; ++i, wd += wtile16) {
@@ -334,8 +474,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int t0 = tg * p.J, jn = min(p.J, p.T - t0), y0 = yt * p.R;
       const int set = it & (p.n_sets - 1);
       const uint32_t d_base = tmem_base + (uint32_t)(set * p.J * p.acc_cols);
-      timed_wait(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1, dbg0, dbg_on);
+      timed_wait_relaxed(&bars[BAR_ACC_FULL + set], (it / p.n_sets) & 1, dbg0, dbg_on);
       tc_fence_after();
+      if (p.skip & 1) {
+        tc_fence_before();
+        if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
+        continue;
+      }
       if (SWAP) {
         for (int j = 0; j < jn; ++j) {
           const uint32_t tcol = d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 128);
@@ -412,6 +557,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         for (int cc = 0; cc < p.Cout; cc += 32) {
           uint32_t v[32];
           tmem_ld32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.acc_cols + cc), v);
+          if (MODE == 3) tmem_zero32(d_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.acc_cols + cc));
           uint32_t packed[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -478,6 +624,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         }
         if (p.stage_bufs == 1) named_bar_sync(1, 128);     // single staging tile: reused by the next accumulator
       }
+      if (MODE == 3) tmem_wait_st();
       tc_fence_before();
       if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
     }
@@ -502,8 +649,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 // 16-byte chunks XOR-swizzled exactly as a TMA box load with the matching swizzle mode would leave them
 // in shared memory (address bits [4:6] ^= bits [7:9] for 128 B rows, [4:5] ^= [7:8] for 64 B, [4] ^= [7]
 // for 32 B).  The conv kernel can then fetch a whole stage of taps with one contiguous bulk copy.
+// KT > 0 selects the kt-stacked order of conv mode 3: source tap (kt, s) -> tile s*KT + (KT-1-kt).
 __global__ void pack_conv_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                         int Cout, int CG, int taps, int Cin) {
+                                         int Cout, int CG, int taps, int Cin, int KT) {
   const int chunks = Cin / 8;
   const long long total = (long long)CG * taps * Cout * chunks;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -516,7 +664,9 @@ __global__ void pack_conv_weights_kernel(const __nv_bfloat16* __restrict__ w, __
     const int row_bytes = Cin * 2;
     const int sw = row_bytes == 128 ? (row & 7) : (row_bytes == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
     const uint4 v = *reinterpret_cast<const uint4*>(w + (((size_t)row * CG + g) * taps + tap) * Cin + ch * 8);
-    *reinterpret_cast<uint4*>(out + (((size_t)g * taps + tap) * Cout + row) * Cin + (ch ^ sw) * 8) = v;
+    int dtap = tap;
+    if (KT > 0) { const int khw = taps / KT, kt = tap / khw, sp = tap - kt * khw; dtap = sp * KT + (KT - 1 - kt); }
+    *reinterpret_cast<uint4*>(out + (((size_t)g * taps + dtap) * Cout + row) * Cin + (ch ^ sw) * 8) = v;
   }
 }
 
@@ -634,6 +784,8 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
 }  // namespace
 
 static long long* g_conv_dbg = nullptr;
+static int g_conv_skip = 0;
+extern "C" void lr_conv3d_set_debug_skip(int mask) { g_conv_skip = mask; }
 // diagnostics: device buffer of 148*8 int64 that the next conv launches fill with per-role wait cycles
 // [producer a_empty, producer w_empty, mma acc_empty, mma a_full, mma w_full, epilogue acc_full, -, mma total]
 extern "C" void lr_conv3d_set_debug(long long* device_buffer) { g_conv_dbg = device_buffer; }
@@ -664,7 +816,18 @@ extern "C" int lr_pack_conv_weights(const void* w, void* out, int Cout, int CG, 
                "lr_pack_conv_weights: bad args");
   const long long total = (long long)CG * taps * Cout * (Cin / 8);
   pack_conv_weights_kernel<<<lr_div_up(total, 256), 256, 0, lr_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(out), Cout, CG, taps, Cin);
+      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(out), Cout, CG, taps, Cin, 0);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
+
+extern "C" int lr_pack_conv_weights_kt(const void* w, void* out, int Cout, int CG, int KT, int KHW, int Cin,
+                                       void* stream) {
+  LR_CHECK_ARG(w && out && (Cin == 16 || Cin == 32 || Cin == 64) && Cout > 0 && CG > 0 && KT > 0 && KHW > 0,
+               "lr_pack_conv_weights_kt: bad args");
+  const long long total = (long long)CG * KT * KHW * Cout * (Cin / 8);
+  pack_conv_weights_kernel<<<lr_div_up(total, 256), 256, 0, lr_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(out), Cout, CG, KT * KHW, Cin, KT);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }
@@ -719,7 +882,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.row_bytes = Cin * 2;
   p.chunk_bytes = (p.CH * p.row_bytes + 1023) / 1024 * 1024;
   const int mode = swap;                       // 0 positions on M, 1 swapped, 2 kx-stacked
-  LR_CHECK_ARG(mode >= 0 && mode <= 2, "lr_conv3d_fwd: orientation must be 0, 1 or 2");
+  LR_CHECK_ARG(mode >= 0 && mode <= 3, "lr_conv3d_fwd: orientation must be 0, 1, 2 or 3");
   swap = mode == 1;
   p.kxs = mode == 2 ? KW : 1;
   if (mode == 2) {
@@ -728,6 +891,11 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   }
   p.n_eff_taps = KT * KH * KW / p.kxs;
   p.wtile_bytes = p.kxs * Cout * p.row_bytes;   // one weight tile = the kxs consecutive per-tap images of a filter row
+  if (mode == 3) {                              // one weight tile = the KT kt-taps of a spatial tap (kt descending)
+    p.n_eff_taps = KH * KW;
+    p.wtile_bytes = KT * Cout * p.row_bytes;
+  }
+  p.n_issuers = kMmaWarps;     // mode 3: set with J below
   LR_CHECK_ARG(p.wtile_bytes % 1024 == 0, "lr_conv3d_fwd: Cout*Cin*2 must be a multiple of 1024");
   p.stage_pitch = Cout * 2 + 16;
   p.swap = swap ? 1 : 0;
@@ -746,11 +914,25 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   int Jmax = 512 / p.acc_cols / n_sets;
   if (J <= 0 || J > Jmax) J = Jmax;
   if (J > 2 * kMmaWarps) J = 2 * kMmaWarps;      // each issuing warp owns at most two accumulators
+  int G = 1;                    // mode 3: issuing warps, each stacking inside its own run of Jg frames
+  if (mode == 3) {
+    G = 2;
+    if (getenv("LR_CONV_ISSUERS")) { const int v = atoi(getenv("LR_CONV_ISSUERS")); if (v >= 1 && v <= kMmaWarps) G = v; }   // tuning hook
+  }
   while (J > 1 && ((J + KT - 1) * CG > kMaxChunks || (J + KT - 1) * CG * p.chunk_bytes + fixed > smem_cap)) --J;
   LR_CHECK_ARG((J + KT - 1) * CG * p.chunk_bytes + fixed <= smem_cap && (J + KT - 1) * CG <= kMaxChunks,
                "lr_conv3d_fwd: tile does not fit shared memory");
   if (J > T) J = T;
   p.J = J;
+  if (mode == 3) {
+    if (G > J) G = J;
+    p.Jg = (J + G - 1) / G;
+    // a stacked MMA spans min(KT, Jg) weight blocks: N = blocks * Cout <= 256
+    while ((KT < p.Jg ? KT : p.Jg) * Cout > 256 && G < kMmaWarps && G < J) { ++G; p.Jg = (J + G - 1) / G; }
+    LR_CHECK_ARG((KT < p.Jg ? KT : p.Jg) * Cout <= 256, "lr_conv3d_fwd: kt-stacked N exceeds 256");
+    G = (J + p.Jg - 1) / p.Jg;
+    p.n_issuers = G;
+  }
   p.n_sets = n_sets;
   p.n_ytiles = lr_div_up(H, p.R);
   p.n_tgroups = lr_div_up(T, J);
@@ -773,8 +955,9 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.a_set_bytes = (J + KT - 1) * CG * p.chunk_bytes;
   // second chunk set when it still leaves room for a 2-deep ring of whole filter rows (or 2 taps)
   {
-    const int want_w = 2 * (KW < 2 || mode == 2 ? 2 : KW) * p.wtile_bytes;
+    const int want_w = 2 * (mode == 3 ? 1 : (KW < 2 || mode == 2 ? 2 : KW)) * p.wtile_bytes;
     p.a_sets = (2 * p.a_set_bytes + stage_bytes + 256 + want_w <= smem_cap) ? 2 : 1;
+    if (getenv("LR_CONV_ASETS") && atoi(getenv("LR_CONV_ASETS")) == 1) p.a_sets = 1;       // tuning hook
   }
   p.smem_off_w = p.a_sets * p.a_set_bytes;
   {
@@ -786,7 +969,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
     if (tps < 1) { stages = 2; tps = avail / (stages * p.wtile_bytes); }
     if (tps > n_taps_h) tps = n_taps_h;
     if (tps > 32) tps = 32;
-    if (mode != 2 && tps >= KW) tps = tps / KW * KW;
+    if (mode < 2 && tps >= KW) tps = tps / KW * KW;
     LR_CHECK_ARG(tps >= 1, "lr_conv3d_fwd: weight ring does not fit shared memory");
     if (tps == n_taps_h && stages > 2) stages = 2;
     p.tps = tps;
@@ -810,12 +993,19 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   if (rc != LR_OK) return rc;
   p.w_packed = reinterpret_cast<const uint8_t*>(w);
   p.dbg = g_conv_dbg;
+  p.skip = g_conv_skip;
+  p.stage_fence = getenv("LR_CONV_STAGE_FENCE") ? atoi(getenv("LR_CONV_STAGE_FENCE")) : 0;
 
   for (int kt = 0, tap = 0; kt < KT; ++kt)
     for (int ky = 0; ky < KH; ++ky)
       for (int kx = 0; kx < KW; kx += p.kxs, ++tap)
         p.tap_off[tap] = (uint32_t)kt * ((uint32_t)p.chunk_bytes >> 4) +
                          (((uint32_t)(ky * Wp + kx) * (uint32_t)p.row_bytes) >> 4);
+  if (mode == 3) {
+    for (int ky = 0, tap = 0; ky < KH; ++ky)
+      for (int kx = 0; kx < KW; ++kx, ++tap)
+        p.tap_off[tap] = ((uint32_t)(ky * Wp + kx) * (uint32_t)p.row_bytes) >> 4;
+  }
 
   int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
 #define LR_LAUNCH_CONV(KS, MD)                                                                              \
@@ -831,6 +1021,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   const int ks = Cin / 16;
   if (mode == 1) LR_LAUNCH_CONV_KS(1);
   else if (mode == 2) LR_LAUNCH_CONV_KS(2);
+  else if (mode == 3) LR_LAUNCH_CONV_KS(3);
   else LR_LAUNCH_CONV_KS(0);
 #undef LR_LAUNCH_CONV_KS
 #undef LR_LAUNCH_CONV

@@ -140,8 +140,7 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
     const uint32_t m_step = (uint32_t)(16 * p.m.row_bytes) >> 4, n_step = (uint32_t)(16 * p.n.row_bytes) >> 4;
     for (int tile = split; tile < p.n_tiles; tile += p.splits, ++n) {
       const int s = n % kStages;
-      lr_mbar_wait(&bars[BAR_FULL + s], (n / kStages) & 1);
-      tc_fence_after();
+      lr_mbar_wait(&bars[BAR_FULL + s], (n / kStages) & 1);      // TMA data: ordered by the mbarrier, no tcgen05 fence
       const uint32_t m_addr = lr_smem_u32(base + (size_t)s * p.stage_bytes);
       const uint64_t md0 = make_desc_lbo(m_addr, (uint32_t)p.m.lbo_bytes, p.m.desc_hi);
       const uint64_t nd0 = make_desc_lbo(m_addr + (uint32_t)m_bytes, (uint32_t)p.n.lbo_bytes, p.n.desc_hi);

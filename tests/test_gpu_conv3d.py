@@ -34,8 +34,12 @@ def _padded(x_ndhwc, pad, Wp, Hp=None):
     (32, 1, 32, (1, 3, 1), 8, 8, 8, 3, 1),         # y shifts only
     (64, 1, 32, (3, 5, 5), 25, 12, 16, 9, 3),      # conv2 dgrad geometry, several items per CTA
     (16, 1, 32, (3, 3, 3), 22, 25, 32, 7, 2),      # ragged last tile (H not a multiple of the tile rows)
+    (16, 1, 32, (3, 3, 3), 12, 25, 32, 21, 2),     # several full frame groups + a tail group per clip
+    (32, 1, 64, (3, 5, 5), 9, 12, 16, 11, 2),      # T = 2 full groups of 4 + tail of 3
+    (64, 1, 96, (3, 3, 3), 12, 6, 8, 1, 2),        # single frame: every chunk is an edge chunk
+    (32, 1, 64, (5, 3, 3), 8, 6, 8, 9, 1),         # KT = 5
 ])
-@pytest.mark.parametrize("swap", [0, 1, 2])       # 0 positions on M, 1 swapped, 2 kx-taps stacked on N (Cout = 32)
+@pytest.mark.parametrize("swap", [0, 1, 2, 3])    # 0 positions on M, 1 swapped, 2 kx-taps stacked on N (Cout = 32), 3 kt-taps stacked on N
 def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, T, B, swap):
     from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
     if swap == 2 and (Cout != 32 or K[2] < 2):
@@ -60,7 +64,7 @@ def test_conv3d_plain_matches_torch(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp
     assert float(err) < 2 ** -7, float(err)
 
 
-@pytest.mark.parametrize("swap", [0, 1])
+@pytest.mark.parametrize("swap", [0, 1, 3])
 @pytest.mark.parametrize("J", [0, 1, 2])
 def test_conv3d_relu_pool_epilogue(native_lib, cuda, J, swap):
     from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
@@ -99,6 +103,38 @@ def test_conv3d_relu_pool_epilogue(native_lib, cuda, J, swap):
     cc = torch.arange(Cout).view(1, 1, 1, 1, Cout).expand_as(am)
     picked = a[bb, tt, yy, xx, cc]
     assert bool((picked[~dead] == ref[~dead]).all())
+
+
+@pytest.mark.parametrize("Cin,CG,Cout,K,H,W,Wp", [
+    (16, 1, 32, (3, 3, 3), 50, 25, 32),            # conv1
+    (32, 1, 64, (3, 5, 5), 25, 12, 16),            # conv2
+    (64, 1, 96, (3, 3, 3), 12, 6, 8),              # conv3
+    (32, 3, 64, (3, 3, 3), 12, 6, 8),              # conv3 dgrad
+    (64, 1, 32, (3, 5, 5), 25, 12, 16),            # conv2 dgrad
+])
+def test_conv3d_kt_stacking_agrees_at_scale(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp):
+    """Orientation 3 issues differently shaped MMAs onto overlapping accumulator columns; a mis-ordered or lost
+    update would show up as a whole missing tap.  Compare with the one-MMA-per-tap orientation on a batch that
+    keeps every SM busy for many work items (same operands, fp32 accumulation in a different order)."""
+    from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
+    g = torch.Generator(device="cuda").manual_seed(99)
+    B, T = 24, 75
+    pad = tuple((k - 1) // 2 for k in K)
+    Hp = _plane_rows(H, K[1], Wp)
+    vol = torch.zeros((CG, B, T + 2 * pad[0], Hp, Wp, Cin), dtype=BF, device=cuda)
+    vol[:, :, pad[0]:pad[0] + T, pad[1]:pad[1] + H, pad[2]:pad[2] + W] = torch.randn(
+        (CG, B, T, H, W, Cin), generator=g, device=cuda).to(BF)
+    taps = K[0] * K[1] * K[2]
+    wk = (torch.randn((Cout, CG, taps, Cin), generator=g, device=cuda) / (Cin * CG * taps) ** 0.5).to(BF)
+    ys = []
+    for mode in (0, 3, 3):
+        y = torch.full((B, T, H, W, Cout), float("nan"), dtype=BF, device=cuda)
+        conv3d_native(vol, wk, None, y, None, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0), swap=mode)
+        ys.append(y.float())
+    torch.cuda.synchronize()
+    assert torch.isfinite(ys[1]).all()
+    assert torch.equal(ys[1], ys[2])                       # one issuing thread: run-to-run deterministic
+    assert float((ys[0] - ys[1]).abs().max() / ys[0].abs().max()) < 2 ** -8
 
 
 @pytest.mark.parametrize("name,Cx,Cy,Gy,K,H,W,Wp,m_is_x,B,T", [

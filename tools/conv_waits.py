@@ -7,6 +7,9 @@ import torch  # noqa: E402
 from lipreading_b200 import conv_frontend as CF, native as N  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+SKIPS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+if len(sys.argv) > 3:
+    CF.SWAP = int(sys.argv[3])
 dev = torch.device("cuda")
 front = CF.ConvFrontEnd().to(dev)
 clip = torch.randint(0, 256, (B, 75, 100, 50, 3), dtype=torch.uint8, device=dev)
@@ -32,6 +35,12 @@ def wrapped(*a, **k):
 
 
 CF.conv3d_native = wrapped
-feat = front(clip)
-feat.sum().backward()
-torch.cuda.synchronize()
+import ctypes
+skipf = ctypes.CDLL(N.LIB_PATH).lr_conv3d_set_debug_skip
+for sk in SKIPS:
+    print("== skip mask %d (1 epilogue, 2 weight reloads, 4 input reloads), orientation %s" % (sk, CF.SWAP))
+    skipf(sk)
+    feat = front(clip)
+    feat.sum().backward()
+    torch.cuda.synchronize()
+skipf(0)
