@@ -33,7 +33,8 @@ using namespace lr_tc;
 namespace {
 
 constexpr int kMmaWarps = 4;                      // MMA-issuing warps (accumulator j is issued by warp j % 4)
-constexpr int kThreads = 32 * (1 + kMmaWarps + 4); // producer + issuers + 4 epilogue warps
+constexpr int kEpiGroups = 2;                     // epilogue warp quartets (each covers the four TMEM lane quarters)
+constexpr int kThreads = 32 * (1 + kMmaWarps + 4 * kEpiGroups);   // producer + issuers + epilogue warps
 constexpr int kMaxChunks = 16;   // (J + KT - 1) * channel groups
 constexpr int kWStages = 4;
 constexpr int kMaxTaps = 80;
@@ -79,7 +80,8 @@ struct ConvParams {
   int row_bytes;
   int smem_off_w, smem_off_stage, smem_off_bar;
   int stage_pitch;             // bytes per staging row
-  int stage_bufs;              // 1 or 2 staging tiles (2: one named barrier per accumulator instead of two)
+  int stage_bufs;              // 1 or 2 staging tiles per epilogue group (2: one named barrier per accumulator instead of two)
+  int epi_groups;              // epilogue warp quartets in use: group e drains the accumulators j = e, e + groups, ...
   int cg_shift, wp_shift;      // log2(Cout/8) (or -1) and log2(Wp) for the plain-store epilogue
   uint32_t tap_off[kMaxTaps];  // per tap: descriptor offset (16-byte units) of its window inside a chunk set
                                // = kt * chunk + (ky*Wp + kx) rows — read with uniform constant loads
@@ -219,7 +221,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       lr_mbar_init(&bars[BAR_A_FULL + i], 1);
       lr_mbar_init(&bars[BAR_A_EMPTY + i], p.n_issuers);
       lr_mbar_init(&bars[BAR_ACC_FULL + i], p.n_issuers);
-      lr_mbar_init(&bars[BAR_ACC_EMPTY + i], 4);
+      lr_mbar_init(&bars[BAR_ACC_EMPTY + i], 4 * p.epi_groups);
     }
     for (int s = 0; s < kWStages; ++s) {
       lr_mbar_init(&bars[BAR_W_FULL + s], 1);
@@ -234,7 +236,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   if (MODE == 3) {
     // every MMA accumulates: the accumulators start (and are left by the epilogue) at zero
-    if (warp > kMmaWarps) {
+    if (warp > kMmaWarps && warp <= kMmaWarps + 4) {
       for (int c = 0; c < p.tmem_cols; c += 32) tmem_zero32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c);
       tmem_wait_st();
     }
@@ -444,10 +446,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
       __syncwarp();
     }
-  } else {
-    // ===================== epilogue (4 warps) =====================
+  } else if ((warp - 1 - kMmaWarps) >> 2 < p.epi_groups) {
+    // ===================== epilogue (quartets of warps; quartet e owns accumulators j = e mod groups) ==========
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int etid = (warp - 1 - kMmaWarps) * 32 + lane;      // 0..127 among epilogue threads
+    const int eg = (warp - 1 - kMmaWarps) >> 2;   // epilogue group (quartet)
+    const int etid = ((warp - 1 - kMmaWarps) & 3) * 32 + lane;      // 0..127 inside the quartet
+    const int bar_id = 1 + eg;                    // named barrier of this quartet
+    stage += (size_t)eg * p.stage_bufs * (128 * p.stage_pitch);
     const int row = q * 32 + lane;                // accumulator row (tile position) held by this thread
     const int PW = p.W >> 1;
     const int cgroups = p.Cout >> 3;
@@ -496,7 +501,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                                p.oWp + p.o_x;                       // output pixel of (t0, tile row 0, x 0)
       const size_t oframe = (size_t)p.oHp * p.oWp;
       const int rows_left = (p.epi_mode == 0 ? (p.H >> 1) - (y0 >> 1) : p.H - y0);   // valid output rows from y0 on
-      for (int j = 0; j < jn; ++j) {
+      for (int j = eg; j < jn; j += p.epi_groups) {
         const int t = t0 + j;
         uint8_t* stg = stage + (size_t)((ebuf++) & (p.stage_bufs - 1)) * (128 * p.stage_pitch);
         if (MODE == 2) {
@@ -527,7 +532,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               if (in_warp) acc[i] += t;
             }
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (q < 3) {
             for (int kx = 1; kx < p.kxs; ++kx) {
               if (lane + kx >= 32) {
@@ -572,7 +577,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           for (int i = 0; i < 4; ++i)
             dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         const size_t ob = obase + (size_t)j * oframe;
         if (p.epi_mode == 0) {
           // MaxPool(1,2,2) over the staged tile; 8 channels (16 B) per thread-item; the (row, x, channel
@@ -622,7 +627,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 *reinterpret_cast<const uint4*>(stg + (size_t)r * p.stage_pitch + cg * 16);
           }
         }
-        if (p.stage_bufs == 1) named_bar_sync(1, 128);     // single staging tile: reused by the next accumulator
+        if (p.stage_bufs == 1) named_bar_sync(bar_id, 128);     // single staging tile: reused by the next accumulator
       }
       if (MODE == 3) tmem_wait_st();
       tc_fence_before();
@@ -630,7 +635,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
   }
 
-  if (dbg_on && lane == 0 && (warp <= 1 || warp == 1 + kMmaWarps)) {
+  if (dbg_on && lane == 0 && (warp <= 1 || warp == 1 + kMmaWarps)) {   // (first quartet's wait is reported)
     long long* o = p.dbg + (size_t)blockIdx.x * 8;
     if (warp == 0) { o[0] = dbg0; o[1] = dbg1; }                       // producer: a_empty, w_empty
     if (warp == 1) { o[2] = dbg0; o[3] = dbg1; o[4] = dbg2; o[7] = clock64() - t_start; }   // mma: acc_empty, a_full, w_full
@@ -906,7 +911,14 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   const int stage_bytes = swap ? p.Mt * p.row_bytes : 128 * p.stage_pitch;
   const int halo_bytes = mode == 2 ? 4 * 4 * 4 * 32 * (int)sizeof(float) : 0;
   const int smem_cap = 227 * 1024 - 1024 - 512 - halo_bytes;     // minus alignment slack, bias copy, halo
-  int fixed = 2 * p.wtile_bytes + stage_bytes + 256;      // at least a 2-deep ring of single taps
+  // a second epilogue quartet when the MMA work per frame is short enough for the epilogue to be the limiter
+  // (bias/ReLU/pool of one 128 x Cout accumulator costs ~1.4 k cycles on one quartet, measured on conv1)
+  {
+    const long long mma_cycles = (long long)KT * KH * KW * (Cin / 16) * CG * (32 + Cout / 4) * 2 / (mode == 3 ? 3 : 2);
+    p.epi_groups = (mode == 0 || mode == 3) && mma_cycles < 2500 ? 2 : 1;
+    if (getenv("LR_CONV_EPI_GROUPS")) { const int v = atoi(getenv("LR_CONV_EPI_GROUPS")); if (v == 1 || (v == 2 && mode != 1 && mode != 2)) p.epi_groups = v; }
+  }
+  int fixed = 2 * p.wtile_bytes + p.epi_groups * stage_bytes + 256;      // at least a 2-deep ring of single taps
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
   int n_sets = (512 / p.acc_cols) >= 4 ? 2 : 1;      // double-buffer TMEM when >= 2 accumulators per set fit
   if (getenv("LR_CONV_SETS")) { int v = atoi(getenv("LR_CONV_SETS")); if (v == 1 || (v == 2 && 512 / p.acc_cols >= 2)) n_sets = v; }   // tuning hook
@@ -956,14 +968,14 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   // second chunk set when it still leaves room for a 2-deep ring of whole filter rows (or 2 taps)
   {
     const int want_w = 2 * (mode == 3 ? 1 : (KW < 2 || mode == 2 ? 2 : KW)) * p.wtile_bytes;
-    p.a_sets = (2 * p.a_set_bytes + stage_bytes + 256 + want_w <= smem_cap) ? 2 : 1;
+    p.a_sets = (2 * p.a_set_bytes + p.epi_groups * stage_bytes + 256 + want_w <= smem_cap) ? 2 : 1;
     if (getenv("LR_CONV_ASETS") && atoi(getenv("LR_CONV_ASETS")) == 1) p.a_sets = 1;       // tuning hook
   }
   p.smem_off_w = p.a_sets * p.a_set_bytes;
   {
     // weight ring: as many tiles per stage as fit (whole filter rows when possible), 3 stages deep
     const int n_taps_h = p.n_eff_taps;
-    const int avail = smem_cap - p.smem_off_w - stage_bytes - 256;
+    const int avail = smem_cap - p.smem_off_w - p.epi_groups * stage_bytes - 256;
     int stages = 3;
     int tps = avail / (stages * p.wtile_bytes);
     if (tps < 1) { stages = 2; tps = avail / (stages * p.wtile_bytes); }
@@ -977,8 +989,8 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   }
   p.smem_off_stage = p.smem_off_w + p.w_stages * p.tps * p.wtile_bytes;
   // a second staging tile (drops one of the two named barriers per accumulator) when shared memory is left over
-  p.stage_bufs = (!swap && p.smem_off_stage + 2 * stage_bytes + 256 <= smem_cap) ? 2 : 1;
-  p.smem_off_halo = p.smem_off_stage + p.stage_bufs * stage_bytes;
+  p.stage_bufs = (!swap && p.smem_off_stage + 2 * p.epi_groups * stage_bytes + 256 <= smem_cap) ? 2 : 1;
+  p.smem_off_halo = p.smem_off_stage + p.epi_groups * p.stage_bufs * stage_bytes;
   p.smem_off_bar = p.smem_off_halo + halo_bytes;
   p.cg_shift = -1;
   for (int sft = 0; sft < 8; ++sft) {
