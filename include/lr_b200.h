@@ -200,6 +200,9 @@ int lr_pack_conv_weights_kt(const void* w, void* out, int Cout, int CG, int KT, 
  * stack_ky = S = 128/Cy (with stack_kx): S filter rows share one M = 128 MMA (M block b = the dY tile
  * shifted by b image rows); out is [KT][ceil(KH/S)][S][Cy][KW][Cx] with block b of unit u holding
  * ky = u*S + (S-1-b) (ky >= KH: scratch).  fuse_kt: one CTA accumulates all KT planes of a tile.
+ * stack_ky = -1 with m_is_x = 1: taps 2u, 2u+1 (flat (ky,kx) order inside a kt plane) share one M = 128
+ * MMA (M block 1 = the x chunk shifted by the second tap); out is [KT][ceil(KH*KW/2)][2][64][Nc].
+ * The k-steps of a plane's last tile that lie past the last row where dy can be non-zero are skipped.
  * lr_conv3d_wgrad_out_floats = elements of `out` (and of one split of the workspace).          */
 size_t lr_conv3d_wgrad_out_floats(int KT, int KH, int KW, int Nc, int stack_ky);
 size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int splits, int stack_ky);

@@ -62,24 +62,32 @@ def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x
     Nc = Gy * Cy if m_is_x else Cx
     KT, KH, KW = K
     taps = KT * KH * KW
+    use_ky = STACK_KY if stack_ky is None else stack_ky
     stack = (STACK_KX if stack_kx is None else stack_kx) and not m_is_x and KW > 1 and KW * Cx <= 256
-    S = 128 // Cy if (stack and Gy == 1 and (STACK_KY if stack_ky is None else stack_ky)) else 1
+    S = 128 // Cy if (stack and Gy == 1 and use_ky) else 1
     U = -(-KH // S)
     if S > 1 and (128 + (U * S - 1) * Wp + KW - 1 > 256 or -(-(H + min(S, KH) - 1) // (128 // Wp)) * (128 // Wp) > Hp):
         S, U = 1, KH                                            # halo / plane height do not allow stacking
+    pair = bool(m_is_x and use_ky and KH * KW > 1)              # two taps per M = 128 MMA (M = 64 runs at half rate)
+    P = -(-KH * KW // 2)
     fuse_kt = S > 1 and KT * U * KW * Cx <= 512
     if splits <= 0:
-        if S > 1:
+        if pair:
+            groups = KT * -(-P // (512 // Nc))
+        elif S > 1:
             groups = 1 if fuse_kt else KT * -(-U // (512 // (KW * Cx)))
         else:
             units, n_mma = (KH, KW * Cx) if stack else (KH * KW, Nc)
             groups = KT * -(-units // (512 // n_mma))
         splits = max(1, 148 // groups)
-    ws = torch.empty(L.lr_conv3d_wgrad_workspace(KT, KH, KW, Nc, splits, S), dtype=torch.uint8, device=x.device)
-    out = torch.empty(L.lr_conv3d_wgrad_out_floats(KT, KH, KW, Nc, S), dtype=torch.float32, device=x.device)
+    sk = -1 if pair else S
+    ws = torch.empty(L.lr_conv3d_wgrad_workspace(KT, KH, KW, Nc, splits, sk), dtype=torch.uint8, device=x.device)
+    out = torch.empty(L.lr_conv3d_wgrad_out_floats(KT, KH, KW, Nc, sk), dtype=torch.float32, device=x.device)
     N.check(L.lr_conv3d_wgrad(N.ptr(x), N.ptr(dy), N.ptr(out), N.ptr(ws), ws.numel(), B, T, H, W, Hp, Wp, Cx, Cy,
-                              Gy, dy_off, KT, KH, KW, m_is_x, int(stack), S, int(fuse_kt), splits, N.stream()),
+                              Gy, dy_off, KT, KH, KW, m_is_x, int(stack), sk, int(fuse_kt), splits, N.stream()),
             "lr_conv3d_wgrad")
+    if pair:                        # [KT][P][2][64][Nc], flat spatial tap = 2u + b -> [taps][64][Nc]
+        return out.reshape(KT, P * 2, 64, Nc)[:, :KH * KW].reshape(taps, 64, Nc)
     if S > 1:                       # [KT][U][S(b)][Cy][KW][Cx], ky = u*S + S-1-b -> [taps][Cy][Cx]
         out = out.reshape(KT, U, S, Cy, KW, Cx).flip(2).reshape(KT, U * S, Cy, KW, Cx)[:, :KH]
         return out.permute(0, 1, 3, 2, 4).reshape(taps, Cy, Cx)

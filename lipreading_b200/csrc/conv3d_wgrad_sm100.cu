@@ -46,6 +46,9 @@ struct Side {
 struct WgradParams {
   int B, T, H, W, Tp, Hp, Wp, KH, KW;
   int R, n_ytiles, n_tiles;
+  int pair_x;             // m_is_x with two taps per M = 128 MMA: unit u = flat (ky,kx) taps 2u, 2u+1 of a kt plane;
+                          // M block 1 is the X chunk shifted by the second tap (descriptor LBO = shift difference)
+  int Hv;                 // image rows of a plane in which dY (incl. its ky-stacking shifts) can be non-zero
   int n_groups, splits;
   int group_kt[kMaxGroups], group_lo[kMaxGroups], group_n[kMaxGroups], group_tap0[kMaxGroups];
   int group_nkt;          // kt planes per group (1, or KT when the whole filter depth is fused into one CTA)
@@ -145,19 +148,30 @@ conv3d_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_m, const __g
       const uint64_t md0 = make_desc_lbo(m_addr, (uint32_t)p.m.lbo_bytes, p.m.desc_hi);
       const uint64_t nd0 = make_desc_lbo(m_addr + (uint32_t)m_bytes, (uint32_t)p.n.lbo_bytes, p.n.desc_hi);
       const uint32_t acc0 = n == 0 ? 0u : 1u;
+      // K = positions: the k-steps (16 positions = 16/Wp image rows) past the last row where dY can be non-zero
+      // multiply zeros — the last tile of a plane issues only the steps it needs
+      const int rows_here = min(p.R, p.Hv - (tile % p.n_ytiles) * p.R);
+      const int nks = min(8, (rows_here * p.Wp + 15) >> 4);
       if (elect_one()) {
         for (int j = mw; j < ntap; j += kMmaWarps) {
           const int kk = j / p.per_kt;                 // kt plane inside a fused group (else 0: groups never span)
           const int unit = p.group_nkt > 1 ? j - kk * p.per_kt : tap_lo + j;
-          const int ky = p.stack > 1 ? unit * p.m_stack : unit / p.KW, kx = p.stack > 1 ? 0 : unit - ky * p.KW;
+          const int u0 = p.pair_x ? 2 * unit : unit;
+          const int ky = p.stack > 1 ? unit * p.m_stack : u0 / p.KW, kx = p.stack > 1 ? 0 : u0 - ky * p.KW;
           const uint32_t shift = (uint32_t)(ky * p.Wp + kx);
-          const uint64_t md = md0 + (uint64_t)(p.m.shifted ? (shift * p.m.row_bytes) >> 4 : 0u);
+          uint64_t md = md0 + (uint64_t)(p.m.shifted ? (shift * p.m.row_bytes) >> 4 : 0u);
+          if (p.pair_x) {
+            const int u1 = u0 + 1, ky1 = u1 / p.KW, kx1 = u1 - ky1 * p.KW;
+            const uint32_t d = u1 < p.KH * p.KW ? (uint32_t)(ky1 * p.Wp + kx1) - shift : 0u;   // odd tap out: duplicate
+            md = make_desc_lbo(m_addr + shift * (uint32_t)p.m.row_bytes, d * (uint32_t)p.m.row_bytes, p.m.desc_hi);
+          }
           const uint64_t nd = nd0 + (uint64_t)((uint32_t)(kk * p.n_region_bytes) >> 4) +
                               (uint64_t)(p.n.shifted ? (shift * p.n.row_bytes) >> 4 : 0u);
           const uint32_t d = tmem_base + (uint32_t)(j * p.Nc);
           umma_bf16(d, md, nd, p.idesc, acc0);
 #pragma unroll
-          for (int ks = 1; ks < 8; ++ks) umma_bf16(d, md + ks * m_step, nd + ks * n_step, p.idesc, 1u);
+          for (int ks = 1; ks < 8; ++ks)
+            if (ks < nks) umma_bf16(d, md + ks * m_step, nd + ks * n_step, p.idesc, 1u);
         }
         umma_commit(&bars[BAR_EMPTY + s]);
       }
@@ -229,6 +243,7 @@ void fill_side(Side& s, int ch_per_block, int blocks, int rows, int shifted, int
 // Floats per split (= size of `out`): without ky stacking [KT*KH*KW][64][Nc] (Nc = Cx, or Gy*Cy when m_is_x);
 // with stack_ky = S > 1 (m_is_x = 0, kx stacked): [KT*ceil(KH/S)][128][KW*Cx].
 extern "C" size_t lr_conv3d_wgrad_out_floats(int KT, int KH, int KW, int Nc, int stack_ky) {
+  if (stack_ky < 0) return (size_t)KT * ((KH * KW + 1) / 2) * 128 * Nc;        // m_is_x tap pairs
   if (stack_ky > 1) return (size_t)KT * ((KH + stack_ky - 1) / stack_ky) * 128 * KW * Nc;
   return (size_t)KT * KH * KW * 64 * Nc;
 }
@@ -246,6 +261,9 @@ extern "C" size_t lr_conv3d_wgrad_workspace(int KT, int KH, int KW, int Nc, int 
 //        [KT*KH][64][KW][Cx] (the kx taps of a row are the column blocks of one accumulator);
 //        with stack_ky = S = 128/Cy as well: [KT][U = ceil(KH/S)][S][Cy][KW][Cx], where M block b of unit u
 //        holds filter row ky = u*S + (S-1-b) (rows with ky >= KH are scratch).
+//        stack_ky = -1 with m_is_x = 1: two taps (flat (ky,kx) index 2u, 2u+1 of a kt plane) share one M = 128 MMA —
+//        M block 1 is the X chunk shifted by the second tap; out is [KT][ceil(KH*KW/2)][2][64][Nc] (an odd last
+//        tap is duplicated into its second block).
 //   fuse_kt (stack_ky only): one CTA accumulates all KT planes of a position tile (needs KT*U*KW*Cx <= 512
 //        TMEM columns) instead of one tap group per kt -> the dY tile is fetched once, not KT times.
 extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* workspace, size_t ws_bytes,
@@ -257,7 +275,8 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
   LR_CHECK_ARG(Cy == 32 || Cy == 64, "lr_conv3d_wgrad: Cy must be 32/64");
   LR_CHECK_ARG(Wp == 8 || Wp == 16 || Wp == 32 || Wp == 64 || Wp == 128, "lr_conv3d_wgrad: Wp pow2 8..128");
   LR_CHECK_ARG(Wp >= W + KW - 1 && Hp >= H + KH - 1, "lr_conv3d_wgrad: padded extents too small");
-  const int S = stack_ky > 1 ? stack_ky : 1;
+  const int pair_x = (m_is_x && stack_ky == -1) ? 1 : 0;
+  const int S = (stack_ky > 1 && !pair_x) ? stack_ky : 1;
   if (S > 1) {
     LR_CHECK_ARG(!m_is_x && stack_kx && Gy == 1 && S * Cy == 128,
                  "lr_conv3d_wgrad: stack_ky needs m_is_x = 0, stack_kx and stack_ky * Cy == 128");
@@ -273,12 +292,14 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
   // exist: the tiles of a plane must reach row H-1+sh
   if (S > 1) p.n_ytiles = lr_div_up(H + (S < KH ? S : KH) - 1, p.R);
   LR_CHECK_ARG(p.n_ytiles * p.R <= Hp, "lr_conv3d_wgrad: padded plane too short for the stacked tiles");
+  p.Hv = S > 1 ? H + (S < KH ? S : KH) - 1 : H;
   p.n_tiles = B * T * p.n_ytiles;
   const int U = (KH + S - 1) / S;                       // units per kt plane when ky is stacked
   const int CH = 128 + (S > 1 ? U * S - 1 : KH - 1) * Wp + (KW - 1);
   LR_CHECK_ARG(CH <= 256, "lr_conv3d_wgrad: halo too large");
   const long long vol_rows = (long long)B * p.Tp * Hp * Wp;
-  p.Mrows = S > 1 ? 128 : 64;
+  p.Mrows = (S > 1 || pair_x) ? 128 : 64;
+  p.pair_x = pair_x;
   p.m_stack = S;
   if (m_is_x) {
     LR_CHECK_ARG(Cx == 64, "lr_conv3d_wgrad: m_is_x needs Cx = 64");
@@ -307,7 +328,7 @@ extern "C" int lr_conv3d_wgrad(const void* x, const void* dy, float* out, void* 
   LR_CHECK_ARG(S == 1 || p.stack > 1, "lr_conv3d_wgrad: stack_ky needs KW > 1");
   LR_CHECK_ARG(p.Nc % 16 == 0 && p.Nc <= 256, "lr_conv3d_wgrad: bad N (%d)", p.Nc);
   // tap groups: one kt each (or all kt when fused), at most 512/Nc accumulators
-  const int per_kt = S > 1 ? U : (p.stack > 1 ? KH : KH * KW);      // accumulator units per kt plane
+  const int per_kt = pair_x ? (KH * KW + 1) / 2 : (S > 1 ? U : (p.stack > 1 ? KH : KH * KW));   // accumulator units per kt plane
   const int max_taps = 512 / p.Nc;
   LR_CHECK_ARG(max_taps >= 1, "lr_conv3d_wgrad: N too wide for TMEM");
   p.per_kt = per_kt;
