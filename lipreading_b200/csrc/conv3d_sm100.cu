@@ -200,6 +200,7 @@ template <int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ ConvParams p) {
   constexpr bool SWAP = MODE == 1;
+  constexpr int kOpsUnroll = KS >= 4 ? 2 : 8 / KS;      // mode 3: chunk ops per unrolled group (~8 MMAs)
   extern __shared__ __align__(1024) uint8_t smem[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the 128B swizzle needs
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -351,24 +352,23 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 uint64_t a = a_item + (uint64_t)((off_next & tapmask) + goff);
                 if (i + 1 < nt) off_next = p.tap_off[tap0 + i + 1];      // fetched a tile ahead of its use
                 if (n_steady >= 0) {
+                  // one flat loop over the run's chunks; the phase only changes which increments apply.  It is
+                  // unrolled so that ~8 MMAs are issued between two rewrites of the same descriptor registers:
+                  // a tcgen05.mma holds its uniform-register operands until the tensor pipe accepts it (the next
+                  // write to them waits on the short scoreboard), so short groups serialise issue behind the pipe
                   uint64_t b = wd + (uint64_t)((uint32_t)(KT - 1) * blk16);
                   uint32_t d = d_base, id = idesc1;
-                  for (int c = 0; c < KT - 1; ++c) {                      // ramp-up
+                  const int n_chunks = jn + KT - 1;
+#pragma unroll kOpsUnroll
+                  for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
                     for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
-                    a += chunk16; b -= blk16; id += istep;
-                  }
-#pragma unroll 2
-                  for (int c = 0; c < n_steady; ++c) {                    // steady: b = wd, N = KT*Cout
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
-                    a += chunk16; d += cout;
-                  }
-                  for (int c = 0; c < KT - 1; ++c) {                      // ramp-down
-                    id -= istep;
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
-                    a += chunk16; d += cout;
+                    const bool up = c < KT - 1;               // ramp-up: the next chunk also feeds an older tap
+                    a += chunk16;
+                    b -= up ? blk16 : 0u;
+                    id += up ? istep : 0u;
+                    d += up ? 0u : cout;
+                    if (c + 1 >= jn) id -= istep;             // ramp-down: the newest taps have no frame left
                   }
                 } else {
                   for (int j = 0; j < jn; ++j)

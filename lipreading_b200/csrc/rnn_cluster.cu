@@ -131,6 +131,40 @@ __global__ void rnn_cluster_fwd_kernel(CFwd p) {
   const uint32_t b_lane = (uint32_t)(((nt * 8 + (lane & 7)) * pitch + ((lane >> 3) & 1) * 8) * 2);
   const int ksteps = H / 16;
 
+  // ---- step-invariant addressing, hoisted out of the 75-step chain --------------------------------
+  // global rows of this thread's 4 elements: pointers advance by one time step per iteration
+  const int t_first = d == 0 ? 0 : T - 1;
+  const long long tdir = d == 0 ? 1 : -1;
+  const float* gi_p[4];
+  float* hid_p[4];
+  float* sv_p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t row0 = (size_t)(bg[i] < B ? bg[i] : 0) * T + t_first;
+    gi_p[i] = p.gi + (row0 * D + d) * (size_t)G * H + ug[i];
+    hid_p[i] = p.hidden + row0 * (size_t)D * H + (size_t)d * H + ug[i];
+    sv_p[i] = S > 0 ? p.saved + (row0 * D + d) * (size_t)S * H + ug[i] : nullptr;
+  }
+  const long long gi_step = tdir * (long long)D * G * H, hid_step = tdir * (long long)D * H,
+                  sv_step = tdir * (long long)D * S * H;
+  // the per-step push of this CTA's [kBS x UH] state slice: 4 16-byte chunks per thread, source offset and
+  // remote (DSMEM) destination are the same every step (the integer divisions used to sit inside the time loop)
+  constexpr int kPush = 4;
+  uint32_t push_src[kPush], push_dst[kPush];
+  {
+    const int chunks_per_row = UH / 8;                 // 16-byte chunks
+    const int n_chunks = kBS * chunks_per_row;
+#pragma unroll
+    for (int k = 0; k < kPush; ++k) {
+      const int i = tid + k * (int)blockDim.x;
+      const int dst = i / n_chunks, c = i - dst * n_chunks;
+      const int rowb = c / chunks_per_row, ch = c - rowb * chunks_per_row;
+      push_src[k] = stage_addr + (uint32_t)((rowb * UH + ch * 8) * 2);
+      push_dst[k] = mapa(h_addr + (uint32_t)((rowb * pitch + u_base + ch * 8) * 2), (uint32_t)dst);
+    }
+  }
+  const uint32_t buf_bytes = (uint32_t)(kBS * pitch * 2);
+
   for (int step = 0; step < T; ++step) {
     const int tt = d == 0 ? step : T - 1 - step;
     const int cur = step & 1;
@@ -138,29 +172,41 @@ __global__ void rnn_cluster_fwd_kernel(CFwd p) {
     float giv[G][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float* gp = p.gi + (((size_t)(bg[i] < B ? bg[i] : 0) * T + tt) * D + d) * (size_t)G * H + ug[i];
 #pragma unroll
-      for (int g = 0; g < G; ++g) giv[g][i] = (bg[i] < B) ? gp[(size_t)g * H] : 0.f;
+      for (int g = 0; g < G; ++g) giv[g][i] = (bg[i] < B) ? gi_p[i][(size_t)g * H] : 0.f;
+      gi_p[i] += gi_step;
     }
-    // (B) gates_pre = W_slice . h_prev^T
-    float acc[G][4];
+    // (B) gates_pre = W_slice . h_prev^T; two accumulator chains per gate (even / odd k-steps) halve the
+    // dependent HMMA chain of the step
+    float acc[G][4], acc2[G][4];
 #pragma unroll
-    for (int g = 0; g < G; ++g) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+    for (int g = 0; g < G; ++g) {
+      acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f;
+      acc2[g][0] = acc2[g][1] = acc2[g][2] = acc2[g][3] = 0.f;
+    }
     if (step > 0) {
-      const uint32_t hb = h_addr + (uint32_t)(cur * kBS * pitch * 2) + b_lane;
-#pragma unroll 4
-      for (int ks = 0; ks < ksteps; ++ks) {
-        uint32_t b0r, b1r;
+      const uint32_t hb = h_addr + (uint32_t)cur * buf_bytes + b_lane;
+#pragma unroll 2
+      for (int ks = 0; ks < ksteps; ks += 2) {
+        uint32_t b0r, b1r, c0r, c1r;
         ldsm_x2(hb + ks * 32, b0r, b1r);
+        ldsm_x2(hb + ks * 32 + 32, c0r, c1r);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          uint32_t a0, a1, a2, a3;
+          uint32_t a0, a1, a2, a3, e0, e1, e2, e3;
           ldsm_x4(W_addr + (uint32_t)(g * UH * pitch * 2) + a_lane + ks * 32, a0, a1, a2, a3);
+          ldsm_x4(W_addr + (uint32_t)(g * UH * pitch * 2) + a_lane + ks * 32 + 32, e0, e1, e2, e3);
           mma_bf16(acc[g], a0, a1, a2, a3, b0r, b1r);
+          mma_bf16(acc2[g], e0, e1, e2, e3, c0r, c1r);
         }
       }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        acc[g][0] += acc2[g][0]; acc[g][1] += acc2[g][1]; acc[g][2] += acc2[g][2]; acc[g][3] += acc2[g][3];
+      }
     }
-    // (C) gate math, masking, outputs
+    // (C) gate math, masking; the outputs stay in registers until after the cluster arrive
+    float o_h[4], o_sv[5][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const bool valid = bg[i] < B;
@@ -186,38 +232,44 @@ __global__ void rnn_cluster_fwd_kernel(CFwd p) {
         hnew = tanh_(giv[0][i] + acc[0][i] + bh[0][i]);
       }
       if (active) hst[i] = hnew;
-      if (valid) {
-        const size_t row = (size_t)bg[i] * T + tt;
-        p.hidden[row * (size_t)D * H + (size_t)d * H + ug[i]] = active ? hnew : 0.f;
-        if (S > 0) {
-          float* sv = p.saved + (row * D + d) * (size_t)S * H + ug[i];
-          sv[0] = active ? sv0 : 0.f;
-          sv[H] = active ? sv1 : 0.f;
-          sv[2 * H] = active ? sv2 : 0.f;
-          sv[3 * H] = active ? sv3 : 0.f;
-          if (S > 4) sv[4 * H] = active ? sv4 : 0.f;
-        }
-      }
+      o_h[i] = active ? hnew : 0.f;
+      o_sv[0][i] = active ? sv0 : 0.f; o_sv[1][i] = active ? sv1 : 0.f; o_sv[2][i] = active ? sv2 : 0.f;
+      o_sv[3][i] = active ? sv3 : 0.f; o_sv[4][i] = active ? sv4 : 0.f;
       stage[bl[i] * UH + (ug[i] - u_base)] = __float2bfloat16(hst[i]);
     }
     __syncthreads();
     // (D) push this CTA's [kBS x UH] bf16 slice into h_s[next] of every CTA of the cluster
     if (step + 1 < T) {
-      const int nxt = cur ^ 1;
-      const int chunks_per_row = UH / 8;                 // 16-byte chunks
-      const int n_chunks = kBS * chunks_per_row;
-      for (int i = tid; i < n_chunks * kCS; i += blockDim.x) {
-        const int dst = i / n_chunks, c = i - dst * n_chunks;
-        const int rowb = c / chunks_per_row, ch = c - rowb * chunks_per_row;
-        uint4 v = *reinterpret_cast<const uint4*>(stage + rowb * UH + ch * 8);
-        const uint32_t local = h_addr + (uint32_t)(((nxt * kBS + rowb) * pitch + u_base + ch * 8) * 2);
-        st_cluster_v4(mapa(local, (uint32_t)dst), v);
+      const uint32_t nxt_off = (uint32_t)(cur ^ 1) * buf_bytes;
+#pragma unroll
+      for (int k = 0; k < kPush; ++k) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(push_src[k]));
+        st_cluster_v4(push_dst[k] + nxt_off, v);
       }
     }
-    // (E) one cluster barrier per step (also orders the stage buffer reuse)
-    cluster_sync_();
+    // (E) one cluster barrier per step (also orders the stage buffer reuse).  The release only has to cover the
+    // DSMEM pushes: this step's global stores are issued between arrive and wait, so the barrier never waits for
+    // HBM write acknowledgements (they were 14 % of the kernel's stall samples in front of the arrive)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (bg[i] < B) {
+        *hid_p[i] = o_h[i];
+        if (S > 0) {
+          float* sv = sv_p[i];
+          sv[0] = o_sv[0][i];
+          sv[H] = o_sv[1][i];
+          sv[2 * H] = o_sv[2][i];
+          sv[3 * H] = o_sv[3][i];
+          if (S > 4) sv[4 * H] = o_sv[4][i];
+        }
+      }
+      hid_p[i] += hid_step;
+      if (S > 0) sv_p[i] += sv_step;
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
-  (void)stage_addr;
   // final states
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -283,10 +335,51 @@ __global__ void rnn_cluster_bwd_kernel(CBwd p) {
     dh_dir[i] = (p.d_h_n && bg[i] < B) ? p.d_h_n[sidx] : 0.f;
     dc[i] = (MODE == LR_RNN_LSTM && p.d_c_n && bg[i] < B) ? p.d_c_n[sidx] : 0.f;
   }
-  const uint32_t WT_addr = lr_smem_u32(WT_s), g_addr = lr_smem_u32(g_s);
+  const uint32_t WT_addr = lr_smem_u32(WT_s), g_addr = lr_smem_u32(g_s), stage_addr = lr_smem_u32(stage);
   const uint32_t a_lane = (uint32_t)(((ub * 16 + (lane & 15)) * pitch + (lane >> 4) * 8) * 2);
   const uint32_t b_lane = (uint32_t)(((nt * 8 + (lane & 7)) * pitch + ((lane >> 3) & 1) * 8) * 2);
   const int ksteps = GH / 16;
+
+  // ---- step-invariant addressing (see the forward kernel) ------------------------------------------
+  const int t_first = d == 0 ? T - 1 : 0;                 // reverse of the forward order
+  const long long tdir = d == 0 ? -1 : 1;
+  const float* dh_p[4];
+  const float* sv_p[4];
+  const float* hid_p[4];
+  float* dgi_p[4];
+  float* dgh_p[4];
+  float* hp_p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t row0 = (size_t)(bg[i] < B ? bg[i] : 0) * T + t_first;
+    dh_p[i] = p.d_hidden + row0 * (size_t)D * H + (size_t)d * H + ug[i];
+    hid_p[i] = p.hidden + row0 * (size_t)D * H + (size_t)d * H + ug[i];
+    sv_p[i] = S > 0 ? p.saved + (row0 * D + d) * (size_t)S * H + ug[i] : nullptr;
+    dgi_p[i] = p.d_gi + (row0 * D + d) * (size_t)GH + ug[i];
+    dgh_p[i] = p.d_gh + (row0 * D + d) * (size_t)GH + ug[i];
+    hp_p[i] = p.h_prev_all + (row0 * D + d) * (size_t)H + ug[i];
+  }
+  const long long dh_step = tdir * (long long)D * H, sv_step = tdir * (long long)D * S * H,
+                  dg_step = tdir * (long long)D * GH;
+  // offset (in elements) from time tt to the forward-previous time step tt_in = tt -/+ 1
+  const long long prev_hid = (d == 0 ? -1 : 1) * (long long)D * H, prev_sv = (d == 0 ? -1 : 1) * (long long)D * S * H;
+  // per-step push of this CTA's [kBS x G*UH] gate-gradient slice: 4*G 16-byte chunks per thread, fixed addresses
+  constexpr int kPush = 4 * G;
+  uint32_t push_src[kPush], push_dst[kPush];
+  {
+    const int cpr = UH / 8;                              // 16-byte chunks per (clip, gate)
+    const int n_chunks = kBS * G * cpr;
+#pragma unroll
+    for (int k = 0; k < kPush; ++k) {
+      const int i = tid + k * (int)blockDim.x;
+      const int dst = i / n_chunks, c = i - dst * n_chunks;
+      const int rowb = c / (G * cpr), rem = c - rowb * (G * cpr);
+      const int g = rem / cpr, ch = rem - g * cpr;
+      push_src[k] = stage_addr + (uint32_t)((rowb * (G * UH) + g * UH + ch * 8) * 2);
+      push_dst[k] = mapa(g_addr + (uint32_t)((rowb * pitch + g * H + u_base + ch * 8) * 2), (uint32_t)dst);
+    }
+  }
+  const uint32_t buf_bytes = (uint32_t)(kBS * pitch * 2);
 
   for (int step = 0; step < T; ++step) {
     const int tt = d == 0 ? T - 1 - step : step;          // reverse of the forward order
@@ -296,31 +389,39 @@ __global__ void rnn_cluster_bwd_kernel(CBwd p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const bool valid = bg[i] < B;
-      const size_t row = (size_t)(valid ? bg[i] : 0) * T + tt;
-      dout[i] = valid ? p.d_hidden[row * (size_t)D * H + (size_t)d * H + ug[i]] : 0.f;
+      dout[i] = valid ? *dh_p[i] : 0.f;
       if (S > 0) {
-        const float* sv = p.saved + (row * D + d) * (size_t)S * H + ug[i];
 #pragma unroll
-        for (int k = 0; k < S; ++k) svv[k][i] = valid ? sv[(size_t)k * H] : 0.f;
+        for (int k = 0; k < S; ++k) svv[k][i] = valid ? sv_p[i][(size_t)k * H] : 0.f;
       }
       const int tt_in = d == 0 ? tt - 1 : tt + 1;
       const bool has_prev = valid && ((d == 0) ? (tt_in >= 0) : (tt_in < len[i]));
-      hprev[i] = has_prev ? p.hidden[((size_t)bg[i] * T + tt_in) * (size_t)D * H + (size_t)d * H + ug[i]] : 0.f;
-      cprev[i] = (MODE == LR_RNN_LSTM && has_prev)
-                     ? p.saved[((((size_t)bg[i] * T + tt_in) * D + d) * (size_t)S + 4) * H + ug[i]] : 0.f;
+      hprev[i] = has_prev ? hid_p[i][prev_hid] : 0.f;
+      cprev[i] = (MODE == LR_RNN_LSTM && has_prev) ? sv_p[i][prev_sv + (long long)4 * H] : 0.f;
     }
-    // dh contribution through W_hh: acc = WT_slice . dgh_prev^T
+    // dh contribution through W_hh: acc = WT_slice . dgh_prev^T — four independent accumulator chains
+    // (k-step mod 4): a single chain of G*H/16 dependent HMMAs was the longest latency of the step
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (step > 0) {
-      const uint32_t gb = g_addr + (uint32_t)(cur * kBS * pitch * 2) + b_lane;
-#pragma unroll 4
-      for (int ks = 0; ks < ksteps; ++ks) {
-        uint32_t b0r, b1r, a0, a1, a2, a3;
-        ldsm_x2(gb + ks * 32, b0r, b1r);
-        ldsm_x4(WT_addr + a_lane + ks * 32, a0, a1, a2, a3);
-        mma_bf16(acc, a0, a1, a2, a3, b0r, b1r);
+      float ac1[4] = {0.f, 0.f, 0.f, 0.f}, ac2[4] = {0.f, 0.f, 0.f, 0.f}, ac3[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t gb = g_addr + (uint32_t)cur * buf_bytes + b_lane;
+#pragma unroll 2
+      for (int ks = 0; ks < ksteps; ks += 4) {
+        uint32_t bq[4][2], aq[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ldsm_x2(gb + (ks + q) * 32, bq[q][0], bq[q][1]);
+          ldsm_x4(WT_addr + a_lane + (ks + q) * 32, aq[q][0], aq[q][1], aq[q][2], aq[q][3]);
+        }
+        mma_bf16(acc, aq[0][0], aq[0][1], aq[0][2], aq[0][3], bq[0][0], bq[0][1]);
+        mma_bf16(ac1, aq[1][0], aq[1][1], aq[1][2], aq[1][3], bq[1][0], bq[1][1]);
+        mma_bf16(ac2, aq[2][0], aq[2][1], aq[2][2], aq[2][3], bq[2][0], bq[2][1]);
+        mma_bf16(ac3, aq[3][0], aq[3][1], aq[3][2], aq[3][3], bq[3][0], bq[3][1]);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = (acc[i] + ac1[i]) + (ac2[i] + ac3[i]);
     }
+    float o_gi[G][4], o_gh[G][4], o_hp[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const bool valid = bg[i] < B;
@@ -355,38 +456,43 @@ __global__ void rnn_cluster_bwd_kernel(CBwd p) {
           dc[i] = dcc * fg;
           dh_dir[i] = 0.f;
         } else {
-          const float h = p.hidden[((size_t)bg[i] * T + tt) * (size_t)D * H + (size_t)d * H + ug[i]];
+          const float h = *hid_p[i];
           dgi[0] = dgh[0] = dh * (1.f - h * h);
           dh_dir[i] = 0.f;
         }
       }
-      if (valid) {
-        const size_t row = (size_t)bg[i] * T + tt;
-        float* o_gi = p.d_gi + (row * D + d) * (size_t)GH + ug[i];
-        float* o_gh = p.d_gh + (row * D + d) * (size_t)GH + ug[i];
+      o_hp[i] = hp_out;
 #pragma unroll
-        for (int g = 0; g < G; ++g) { o_gi[(size_t)g * H] = dgi[g]; o_gh[(size_t)g * H] = dgh[g]; }
-        p.h_prev_all[(row * D + d) * (size_t)H + ug[i]] = hp_out;
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g)
+      for (int g = 0; g < G; ++g) {
+        o_gi[g][i] = dgi[g];
+        o_gh[g][i] = dgh[g];
         stage[bl[i] * (G * UH) + g * UH + (ug[i] - u_base)] = __float2bfloat16(dgh[g]);
+      }
     }
     __syncthreads();
     if (step + 1 < T) {
-      const int nxt = cur ^ 1;
-      const int cpr = UH / 8;                              // 16-byte chunks per (clip, gate)
-      const int n_chunks = kBS * G * cpr;
-      for (int i = tid; i < n_chunks * kCS; i += blockDim.x) {
-        const int dst = i / n_chunks, c = i - dst * n_chunks;
-        const int rowb = c / (G * cpr), rem = c - rowb * (G * cpr);
-        const int g = rem / cpr, ch = rem - g * cpr;
-        uint4 v = *reinterpret_cast<const uint4*>(stage + rowb * (G * UH) + g * UH + ch * 8);
-        const uint32_t local = g_addr + (uint32_t)(((nxt * kBS + rowb) * pitch + g * H + u_base + ch * 8) * 2);
-        st_cluster_v4(mapa(local, (uint32_t)dst), v);
+      const uint32_t nxt_off = (uint32_t)(cur ^ 1) * buf_bytes;
+#pragma unroll
+      for (int k = 0; k < kPush; ++k) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(push_src[k]));
+        st_cluster_v4(push_dst[k] + nxt_off, v);
       }
     }
-    cluster_sync_();
+    // the global stores of the step sit between arrive and wait (see the forward kernel)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (bg[i] < B) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) { dgi_p[i][(size_t)g * H] = o_gi[g][i]; dgh_p[i][(size_t)g * H] = o_gh[g][i]; }
+        *hp_p[i] = o_hp[i];
+      }
+      dh_p[i] += dh_step; hid_p[i] += dh_step; hp_p[i] += dh_step;
+      if (S > 0) sv_p[i] += sv_step;
+      dgi_p[i] += dg_step; dgh_p[i] += dg_step;
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
@@ -427,7 +533,22 @@ int launch_cluster(K kernel, P params, int n_clusters, int threads, size_t smem,
 extern "C" int lr_rnn_cluster_supported(int mode, int H) {
   if (mode < 0 || mode > 2 || H <= 0 || H % (16 * kCS) != 0 || H / kCS > 64) return 0;
   const int G = gates_of(mode);
-  return fwd_smem(G, H) <= 220 * 1024 && bwd_smem(G, H) <= 220 * 1024;
+  if (!(fwd_smem(G, H) <= 220 * 1024 && bwd_smem(G, H) <= 220 * 1024)) return 0;
+  // the block is (H/kCS/16) * 4 warps: both kernels must fit the register file at that size
+  const int threads = (H / kCS / 16) * (kBS / 8) * 32;
+  const void* fns[2] = {
+      mode == LR_RNN_GRU ? (const void*)rnn_cluster_fwd_kernel<LR_RNN_GRU>
+                         : mode == LR_RNN_LSTM ? (const void*)rnn_cluster_fwd_kernel<LR_RNN_LSTM>
+                                               : (const void*)rnn_cluster_fwd_kernel<LR_RNN_TANH>,
+      mode == LR_RNN_GRU ? (const void*)rnn_cluster_bwd_kernel<LR_RNN_GRU>
+                         : mode == LR_RNN_LSTM ? (const void*)rnn_cluster_bwd_kernel<LR_RNN_LSTM>
+                                               : (const void*)rnn_cluster_bwd_kernel<LR_RNN_TANH>};
+  for (int i = 0; i < 2; ++i) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, fns[i]) != cudaSuccess) { cudaGetLastError(); return threads <= 256; }
+    if ((long long)fa.numRegs * threads > 65536) return 0;
+  }
+  return 1;
 }
 
 extern "C" int lr_rnn_cluster_fwd(int mode, const float* gi, const float* w_hh, const float* b_hh,
