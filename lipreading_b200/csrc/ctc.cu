@@ -276,18 +276,22 @@ ctc_alpha_beta_grad_kernel(const float* __restrict__ lp_all, const int32_t* __re
 // clip's log-probs are read twice from L2/HBM and the gradient written once — nothing else moves.
 // A CTA is a single warp: ~20 KB of shared memory per clip lets ~11 clips share an SM, which is what
 // hides the 75-step dependent chain (the kernel is latency-bound per clip, throughput-bound per SM).
-template <int P, bool FAST>
+// GA = 1 keeps the alpha lattice in a global workspace instead (written coalesced as it is produced, read back a few
+// rows ahead in the backward sweep; it is consumed ~100 us after it was written, i.e. out of L2): shared memory per
+// clip drops from ~23 KB to ~4 KB, so the SM holds 32 clips instead of 9 — the kernel is latency-bound per clip, and
+// more clips in flight is what raises its throughput.
+template <int P, bool FAST, int GA>
 __global__ void __launch_bounds__(32)
 ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
                 const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens, int B, int T, int C,
-                int Lmax, float* __restrict__ nll_out, float* __restrict__ grad) {
+                int Lmax, float* __restrict__ nll_out, float* __restrict__ grad, float* __restrict__ alpha_ws) {
   constexpr int K = 2 * P, SP = 32 * K;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, lane = threadIdx.x;
   const int Cpad = (C + 31) / 32 * 32;
   constexpr int RING = 8;                                            // log-prob rows in flight (cp.async)
-  float* alpha = reinterpret_cast<float*>(smem_raw);                 // [T][SP]
-  float* rows = alpha + (size_t)T * SP;                              // [RING][Cpad]
+  float* alpha = GA ? alpha_ws + (size_t)b * T * SP : reinterpret_cast<float*>(smem_raw);   // [T][SP]
+  float* rows = GA ? reinterpret_cast<float*>(smem_raw) : alpha + (size_t)T * SP;           // [RING][Cpad]
   float* occ = rows + RING * Cpad;                                   // [Cpad]
   float* erow = occ + Cpad;                                          // [32*P] label occupancies of a frame
   int* nxt = reinterpret_cast<int*>(erow + 32 * P);                  // [32*P]
@@ -374,7 +378,18 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
   }
   __syncwarp();
   float nll;
-  {
+  if (GA) {
+    // states S-1 = blank of label position L, S-2 = label of position L-1: pick them out of the registers
+    float l1 = LR_NEG_INF, l2 = LR_NEG_INF;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float vb = __shfl_sync(0xffffffffu, ab[i], L / P);
+      const float vl = __shfl_sync(0xffffffffu, al[i], L > 0 ? (L - 1) / P : 0);
+      if (i == L % P) l1 = vb;
+      if (L > 0 && i == (L - 1) % P) l2 = vl;
+    }
+    nll = -(FAST ? lr_lse2_fast : lr_lse2)(l1, l2);
+  } else {
     const float* last = alpha + (size_t)(Tb - 1) * SP;
     const float l1 = last[S - 1];
     const float l2 = S > 1 ? last[S - 2] : LR_NEG_INF;
@@ -394,6 +409,21 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   for (int k = 0; k < RING - 1; ++k) issue_row(Tb - 1 - k);          // prologue of the backward sweep
+  // global-alpha variant: this lane's alpha values of rows t, t-1, t-2 travel in registers (loads issued three
+  // iterations before their use cover the L2/HBM latency)
+  constexpr int AD = 3;
+  float2 apre[AD][P];
+  if (GA) {
+    __threadfence_block();
+#pragma unroll
+    for (int d = 0; d < AD; ++d)
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        const int tt = Tb - 1 - d;
+        apre[d][i] = tt >= 0 ? *reinterpret_cast<const float2*>(alpha + (size_t)tt * SP + lane * K + 2 * i)
+                             : make_float2(0.f, 0.f);
+      }
+  }
   for (int t = Tb - 1; t >= 0; --t) {
     if (t < Tb - 1) { __syncwarp(); issue_row(t - (RING - 2)); }
     wait_row();
@@ -428,7 +458,16 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
     float eb = 0.f;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      const float2 a = *reinterpret_cast<const float2*>(alpha + (size_t)t * SP + lane * K + 2 * i);
+      float2 a;
+      if (GA) {
+        a = apre[0][i];
+#pragma unroll
+        for (int d = 0; d + 1 < AD; ++d) apre[d][i] = apre[d + 1][i];
+        const int tt = t - AD;
+        if (tt >= 0) apre[AD - 1][i] = *reinterpret_cast<const float2*>(alpha + (size_t)tt * SP + lane * K + 2 * i);
+      } else {
+        a = *reinterpret_cast<const float2*>(alpha + (size_t)t * SP + lane * K + 2 * i);
+      }
       const float sb = a.x + bb[i], sl = a.y + bl[i];
       if (has_blank[i] && sb != LR_NEG_INF) eb += __expf(sb + nll - lpb);
       erow[lane * P + i] = (has_lab[i] && sl != LR_NEG_INF) ? __expf(sl + nll - row[lab[i]]) : 0.f;
@@ -451,9 +490,19 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
   }
 }
 
-size_t warp_kernel_smem(int T, int C, int P) {
+size_t warp_kernel_smem(int T, int C, int P, int global_alpha = 0) {
   const int Cpad = (C + 31) / 32 * 32;
-  return ((size_t)T * 64 * P + 9 * Cpad + 32 * P) * sizeof(float) + (size_t)2 * 32 * P * sizeof(int);
+  return ((global_alpha ? 0 : (size_t)T * 64 * P) + 9 * Cpad + 32 * P) * sizeof(float) + (size_t)2 * 32 * P * sizeof(int);
+}
+// warp-per-clip kernel: label pairs per lane for a target of up to Lmax labels (0: does not fit)
+int warp_kernel_pairs(int Lmax) {
+  const int S = 2 * Lmax + 1;
+  return S <= 64 ? 1 : (S <= 128 ? 2 : (S <= 256 ? 4 : 0));
+}
+bool warp_kernel_chosen(int B, int T, int C, int Lmax) {
+  const int P = warp_kernel_pairs(Lmax);
+  return P && warp_kernel_smem(T, C, P) <= 100 * 1024 && lr_ctc_force_block_kernel != 1 &&
+         (B >= 1024 || lr_ctc_force_block_kernel == 2);
 }
 
 // Greedy CTC decode (semantics of the reference's GreedyDecoder,
@@ -518,6 +567,9 @@ extern "C" void lr_ctc_select_kernel(int force_block) { lr_ctc_force_block_kerne
 
 extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
   if (B <= 0 || T <= 0 || C <= 0 || Lmax < 0) return 0;
+  if (Lmax == 0) Lmax = 1;
+  if (warp_kernel_chosen(B, T, C, Lmax))               // alpha lattice of the warp-per-clip kernel: [B][T][64*P] f32
+    return (size_t)B * T * 64 * warp_kernel_pairs(Lmax) * sizeof(float);
   CtcPlan p = make_plan(T, C, Lmax);
   if (p.lat_in_smem) return 16;
   return (size_t)B * 2 * T * p.Smax * sizeof(float);
@@ -532,36 +584,39 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
   LR_CHECK_ARG(B > 0 && T > 0 && C > 1 && Lmax >= 0, "lr_ctc_fwd_bwd: bad shape B=%d T=%d C=%d L=%d",
                B, T, C, Lmax);
   if (Lmax == 0) Lmax = 1;  // keep array extents non-zero; target_lens still clamp to 0
-  // warp-per-clip kernel whenever the alpha lattice of a clip fits a modest slice of shared memory
-  {
-    const int S = 2 * Lmax + 1;
-    const int P = S <= 64 ? 1 : (S <= 128 ? 2 : (S <= 256 ? 4 : 0));
-    const size_t sm = P ? warp_kernel_smem(T, C, P) : 0;
-    // one warp per clip maximises clips in flight per SM (throughput); with few clips the CTA-per-clip kernel
-    // (alpha and beta on two warps, 4-warp gradient) has the shorter critical path
-    if (P && sm <= 100 * 1024 && lr_ctc_force_block_kernel != 1 && (B >= 1024 || lr_ctc_force_block_kernel == 2)) {
-      cudaStream_t st = lr_stream(stream);
-#define LR_LAUNCH_WARP(PP)                                                                                   \
-  do {                                                                                                       \
-    if (T <= 128) {          /* fast exp/log: chains this short stay inside the 1e-4 parity bar */     \
-      LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)sm));                                                          \
-      ctc_warp_kernel<PP, true><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax,  \
-                                                    nll, grad);                                               \
-    } else {                                                                                                 \
-      LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)sm));                                                          \
-      ctc_warp_kernel<PP, false><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, \
-                                                     nll, grad);                                              \
-    }                                                                                                        \
+  // warp-per-clip kernel whenever the alpha lattice of a clip fits a modest slice of shared memory: one warp per
+  // clip maximises clips in flight per SM (throughput); with few clips the CTA-per-clip kernel (alpha and beta on two
+  // warps, 4-warp gradient) has the shorter critical path.  With a workspace for the lattice it runs the global-alpha
+  // variant (32 clips per SM instead of 9).
+  if (warp_kernel_chosen(B, T, C, Lmax)) {
+    const int P = warp_kernel_pairs(Lmax);
+    const size_t ws_need = (size_t)B * T * 64 * P * sizeof(float);
+    const int ga = (grad && workspace && ws_bytes >= ws_need) ? 1 : 0;
+    const size_t sm = warp_kernel_smem(T, C, P, ga);
+    float* aw = reinterpret_cast<float*>(workspace);
+    cudaStream_t st = lr_stream(stream);
+#define LR_LAUNCH_WARP2(PP, FF, GG)                                                                            \
+  do {                                                                                                         \
+    LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP, FF, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)sm));                                                              \
+    ctc_warp_kernel<PP, FF, GG><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, \
+                                                   nll, grad, aw);                                             \
   } while (0)
-      if (P == 1) LR_LAUNCH_WARP(1);
-      else if (P == 2) LR_LAUNCH_WARP(2);
-      else LR_LAUNCH_WARP(4);
+#define LR_LAUNCH_WARP(PP)                                                                                     \
+  do {                                                                                                         \
+    if (T <= 128) {          /* fast exp/log: chains this short stay inside the 1e-4 parity bar */            \
+      if (ga) LR_LAUNCH_WARP2(PP, true, 1); else LR_LAUNCH_WARP2(PP, true, 0);                                 \
+    } else {                                                                                                   \
+      if (ga) LR_LAUNCH_WARP2(PP, false, 1); else LR_LAUNCH_WARP2(PP, false, 0);                               \
+    }                                                                                                          \
+  } while (0)
+    if (P == 1) LR_LAUNCH_WARP(1);
+    else if (P == 2) LR_LAUNCH_WARP(2);
+    else LR_LAUNCH_WARP(4);
 #undef LR_LAUNCH_WARP
-      LR_CHECK_LAUNCH();
-      return LR_OK;
-    }
+#undef LR_LAUNCH_WARP2
+    LR_CHECK_LAUNCH();
+    return LR_OK;
   }
   CtcPlan p = make_plan(T, C, Lmax);
   if (!p.lat_in_smem) {
