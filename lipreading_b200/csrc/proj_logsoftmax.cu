@@ -3,74 +3,121 @@
 //
 //   logits = hidden @ W^T + b ;  logits += log(mask + 1e-45) ;  out = log_softmax(logits)
 //
-// C = vocab+1 = 65 is far too narrow for a tensor-core tile to pay, and the op is bound by reading
-// `hidden` once (M*K*4 bytes): fp32 SIMT with register blocking, the softmax done in the GEMM
-// epilogue so logits never round-trip through HBM.  fp32 end to end => parity 1e-4 on log-probs.
+// fp32 SIMT with register blocking (the 1e-4 parity bar on log-probs rules out a single TF32 pass), the softmax
+// done in the GEMM epilogue so logits never round-trip through HBM.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kMaxC = 68;      // 4 column groups x 17 classes
 constexpr int kCPerThread = 17;
-constexpr int kBM = 128;       // rows per CTA (2 per thread-row-slot)
+constexpr int kRows = 4;       // rows per thread
+constexpr int kBM = 64;        // rows per CTA
 constexpr int kKT = 32;        // K tile
-constexpr int kThreads = 256;
+constexpr int kThreads = 64;   // 16 row slots x 4 class groups
+constexpr int kStages = 3;     // cp.async ring depth
+constexpr int kPitch = kKT + 4;                  // floats per staged row (16-byte aligned, conflict-free float4 reads)
+
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lr_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(lr_smem_u32(dst)), "l"(src) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
+// The op is bound by reading `hidden` once (M*K*4 bytes) if the SM never waits for it.  A 3-stage cp.async ring keeps
+// two K tiles of `hidden` and `weight` in flight per CTA (16-byte copies, both operands k-contiguous in shared memory
+// exactly as in HBM), several CTAs share an SM, and the inner loop reads shared memory in float4s along k only:
+// 4 (the thread's rows) + 17 (its classes) LDS.128 per 272 FFMA.  64-row tiles give M/64 CTAs (300 at the bench shape).
 __global__ void __launch_bounds__(kThreads)
 proj_logsoftmax_fwd_kernel(const float* __restrict__ hidden, const float* __restrict__ weight,
                            const float* __restrict__ bias, const float* __restrict__ log_mask,
                            float* __restrict__ out, int M, int K, int C) {
-  __shared__ float Hs[kBM][kKT + 1];
-  __shared__ float Ws[kKT][kMaxC];
+  extern __shared__ __align__(16) float psm[];
+  float* Hs = psm;                                        // [kStages][kBM][kPitch]
+  float* Ws = psm + kStages * kBM * kPitch;               // [kStages][kMaxC][kPitch]
   const int tid = threadIdx.x;
-  const int cg = tid & 3;        // class group: classes cg, cg+4, ...
-  const int rs = tid >> 2;       // 0..63 : rows rs and rs+64 of the tile
+  const int cg = tid & 3;        // class group: classes cg*17 .. cg*17+16
+  const int rs = tid >> 2;       // 0..15 : rows rs + 16*j of the tile
   const int m0 = blockIdx.x * kBM;
+  const bool k_vec = (K % 4) == 0;
 
-  float acc0[kCPerThread], acc1[kCPerThread];
-#pragma unroll
-  for (int i = 0; i < kCPerThread; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+  // zero the staging buffers once: out-of-range rows / classes are never written again
+  for (int i = tid; i < kStages * (kBM + kMaxC) * kPitch; i += kThreads) psm[i] = 0.f;
+  __syncthreads();
 
-  for (int k0 = 0; k0 < K; k0 += kKT) {
-    // hidden tile: kBM x kKT, coalesced along k
-    for (int i = tid; i < kBM * kKT; i += kThreads) {
-      int r = i / kKT, kk = i % kKT;
-      int m = m0 + r, k = k0 + kk;
-      Hs[r][kk] = (m < M && k < K) ? hidden[(size_t)m * K + k] : 0.f;
-    }
-    // weight tile transposed: Ws[kk][c]
-    for (int i = tid; i < kMaxC * kKT; i += kThreads) {
-      int c = i / kKT, kk = i % kKT;
-      int k = k0 + kk;
-      Ws[kk][c] = (c < C && k < K) ? weight[(size_t)c * K + k] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int kk = 0; kk < kKT; ++kk) {
-      float h0 = Hs[rs][kk], h1 = Hs[rs + 64][kk];
-#pragma unroll
-      for (int i = 0; i < kCPerThread; ++i) {
-        float w = Ws[kk][cg + 4 * i];
-        acc0[i] = fmaf(h0, w, acc0[i]);
-        acc1[i] = fmaf(h1, w, acc1[i]);
+  const int n_tiles = (K + kKT - 1) / kKT;
+  auto fill = [&](float* dst, const float* src_rows, int n_rows, int row0, int row_limit, int k0) {
+    for (int i = tid; i < n_rows * (kKT / 4); i += kThreads) {
+      const int r = i / (kKT / 4), q = i - r * (kKT / 4);
+      const int k = k0 + q * 4;
+      if (row0 + r < row_limit) {
+        const float* src = src_rows + (size_t)(row0 + r) * K + k;
+        if (k_vec && k + 4 <= K) {
+          cp_async16(dst + r * kPitch + q * 4, src);
+        } else {
+          for (int e = 0; e < 4; ++e)
+            if (k + e < K) cp_async4(dst + r * kPitch + q * 4 + e, src + e);
+            else dst[r * kPitch + q * 4 + e] = 0.f;
+        }
       }
     }
-    __syncthreads();
+  };
+  auto issue = [&](int tile) {
+    if (tile < n_tiles) {
+      const int st = tile % kStages;
+      fill(Hs + st * kBM * kPitch, hidden, kBM, m0, M, tile * kKT);
+      fill(Ws + st * kMaxC * kPitch, weight, C, 0, C, tile * kKT);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[kRows][kCPerThread];
+#pragma unroll
+  for (int j = 0; j < kRows; ++j)
+#pragma unroll
+    for (int i = 0; i < kCPerThread; ++i) acc[j][i] = 0.f;
+
+  for (int t = 0; t < kStages - 1; ++t) issue(t);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
+    __syncthreads();                               // tile landed for everyone; the slot refilled below is drained
+    issue(tile + kStages - 1);
+    const float* hs = Hs + (tile % kStages) * kBM * kPitch + rs * kPitch;
+    const float* ws = Ws + (tile % kStages) * kMaxC * kPitch + cg * kCPerThread * kPitch;
+#pragma unroll 1
+    for (int kq = 0; kq < kKT; kq += 4) {
+      float4 h[kRows];
+#pragma unroll
+      for (int j = 0; j < kRows; ++j) h[j] = *reinterpret_cast<const float4*>(hs + j * 16 * kPitch + kq);
+#pragma unroll
+      for (int i = 0; i < kCPerThread; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(ws + i * kPitch + kq);
+#pragma unroll
+        for (int j = 0; j < kRows; ++j) {
+          float a = acc[j][i];
+          a = fmaf(h[j].x, w.x, a);
+          a = fmaf(h[j].y, w.y, a);
+          a = fmaf(h[j].z, w.z, a);
+          a = fmaf(h[j].w, w.w, a);
+          acc[j][i] = a;
+        }
+      }
+    }
   }
 
   // epilogue: bias + log-mask, row-wise log-softmax across the 4 lanes that share a row
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float* acc = half ? acc1 : acc0;
-    int m = m0 + rs + 64 * half;
+  for (int j = 0; j < kRows; ++j) {
+    const int m = m0 + rs + 16 * j;
     float mx = LR_NEG_INF;
 #pragma unroll
     for (int i = 0; i < kCPerThread; ++i) {
-      int c = cg + 4 * i;
+      const int c = cg * kCPerThread + i;
       if (c < C) {
-        acc[i] += bias[c] + log_mask[c];
-        mx = fmaxf(mx, acc[i]);
+        acc[j][i] += bias[c] + log_mask[c];
+        mx = fmaxf(mx, acc[j][i]);
       }
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -78,17 +125,17 @@ proj_logsoftmax_fwd_kernel(const float* __restrict__ hidden, const float* __rest
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kCPerThread; ++i) {
-      int c = cg + 4 * i;
-      if (c < C) sum += expf(acc[i] - mx);
+      const int c = cg * kCPerThread + i;
+      if (c < C) sum += expf(acc[j][i] - mx);
     }
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    float lse = mx + logf(sum);
+    const float lse = mx + logf(sum);
     if (m < M) {
 #pragma unroll
       for (int i = 0; i < kCPerThread; ++i) {
-        int c = cg + 4 * i;
-        if (c < C) out[(size_t)m * C + c] = acc[i] - lse;
+        const int c = cg * kCPerThread + i;
+        if (c < C) out[(size_t)m * C + c] = acc[j][i] - lse;
       }
     }
   }
@@ -211,7 +258,9 @@ extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, 
   LR_CHECK_ARG(hidden && weight && bias && log_mask && log_probs, "lr_proj_logsoftmax_fwd: null");
   LR_CHECK_ARG(M > 0 && K > 0 && C > 0 && C <= kMaxC, "lr_proj_logsoftmax_fwd: need 0<C<=%d (C=%d)",
                kMaxC, C);
-  proj_logsoftmax_fwd_kernel<<<lr_div_up(M, kBM), kThreads, 0, lr_stream(stream)>>>(
+  const size_t smem = (size_t)kStages * (kBM + kMaxC) * kPitch * sizeof(float);
+  LR_CHECK_CUDA(cudaFuncSetAttribute(proj_logsoftmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proj_logsoftmax_fwd_kernel<<<lr_div_up(M, kBM), kThreads, smem, lr_stream(stream)>>>(
       hidden, weight, bias, log_mask, log_probs, M, K, C);
   LR_CHECK_LAUNCH();
   return LR_OK;
