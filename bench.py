@@ -422,11 +422,11 @@ def main():
     # DRAM traffic of the largest launch (conv2.fwd) from the committed `ncu --set full` capture
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_conv_b256.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_step_b256_v3.json")) as fh:
             cap = json.load(fh)["conv2.fwd"]
         if args.batch == 256:
             traffic = {"bytes_per_launch": (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6, "launch": "conv2.fwd",
-                       "source": "profiles/r1_ncu_full_conv_b256.json"}
+                       "source": "profiles/r1_ncu_full_step_b256_v3.json"}
     except Exception:
         pass
     roofline = {"kernel": "conv3d_tcgen05_kernel (5 launches/step: conv1-3 fwd, conv3/conv2 dgrad)",
