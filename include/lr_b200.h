@@ -214,6 +214,20 @@ int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out, float* d_b
               int H, int W, int C, int Cg, int Tp, int Hp, int Wp, int pt, int ph, int pw,
               void* stream);
 
+/* -------- f1: attention core of the character decoder, all label positions at once ---------- */
+/* reference: src/models/lipreader/better_model.py:195-223 (one position per call, stock ops).
+ *   scores[b,l,t] = q[b,l,:].enc[b,t,:] ; w = allennlp masked_softmax(scores, t < lens[b]) ;
+ *   ctx[b,l,:] = sum_t w[b,l,t] enc[b,t,:].
+ * q (B,L,H) f32 is the decoder state ('dot') or attn_proj_general(state) ('general'); enc (B,T,H) f32.
+ * One CTA per clip keeps the clip's encoder states in shared memory for all L positions.
+ * weights (B,L,T), zsum (B,L) [the +1e-13 normaliser] and ctx (B,L,H) are outputs; bwd returns d_q, d_enc
+ * (fully written) from d_ctx.                                                                      */
+int lr_attn_fwd(const float* q, const float* enc, const int32_t* lens, int B, int L, int T, int H,
+                float* weights, float* zsum, float* ctx, void* stream);
+int lr_attn_bwd(const float* q, const float* enc, const int32_t* lens, const float* weights,
+                const float* zsum, const float* d_ctx, int B, int L, int T, int H, float* d_q,
+                float* d_enc, void* stream);
+
 /* -------- diagnostics ------------------------------------------------------------------------ */
 /* SM cycles for `iters` back-to-back tcgen05.mma of one shape with operands resident in shared memory
  * (tools/umma_table.py): the measured per-instruction cost that tile-orientation choices are based on.

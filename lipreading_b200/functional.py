@@ -73,6 +73,46 @@ def ctc_greedy_decode(log_probs, lens):
 
 
 # ------------------------------------------------------------------------------------------------
+# f1: attention core of the character decoder, all label positions of a clip at once
+# ------------------------------------------------------------------------------------------------
+class _AttnContext(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, enc, lens):
+        N.require_cuda(q, enc, lens)
+        q, enc = N.cont(q, torch.float32), N.cont(enc, torch.float32)
+        lens32 = N.cont(lens, torch.int32)
+        B, L, H = q.shape
+        T = enc.shape[1]
+        assert enc.shape[0] == B and enc.shape[2] == H
+        w = torch.empty((B, L, T), dtype=torch.float32, device=q.device)
+        z = torch.empty((B, L), dtype=torch.float32, device=q.device)
+        c = torch.empty((B, L, H), dtype=torch.float32, device=q.device)
+        N.check(N.lib().lr_attn_fwd(N.ptr(q), N.ptr(enc), N.ptr(lens32), B, L, T, H, N.ptr(w), N.ptr(z), N.ptr(c),
+                                    N.stream()), "lr_attn_fwd")
+        ctx.save_for_backward(q, enc, lens32, w, z)
+        ctx.mark_non_differentiable(w)
+        return c, w
+
+    @staticmethod
+    def backward(ctx, d_c, _d_w):
+        q, enc, lens32, w, z = ctx.saved_tensors
+        B, L, H = q.shape
+        T = enc.shape[1]
+        d_c = N.cont(d_c, torch.float32)
+        d_q = torch.empty_like(q)
+        d_enc = torch.empty_like(enc)
+        N.check(N.lib().lr_attn_bwd(N.ptr(q), N.ptr(enc), N.ptr(lens32), N.ptr(w), N.ptr(z), N.ptr(d_c), B, L, T, H,
+                                    N.ptr(d_q), N.ptr(d_enc), N.stream()), "lr_attn_bwd")
+        return d_q, d_enc, None
+
+
+def attn_context(q, enc, lens):
+    """Dot-product attention of L queries per clip over the clip's encoder states with allennlp's masked softmax
+    (better_model.py:195-223): q (B,L,H), enc (B,T,H), lens (B) -> (context (B,L,H), weights (B,L,T))."""
+    return _AttnContext.apply(q, enc, lens)
+
+
+# ------------------------------------------------------------------------------------------------
 # a14: Linear + masked log-softmax
 # ------------------------------------------------------------------------------------------------
 class _ProjLogSoftmax(torch.autograd.Function):

@@ -186,6 +186,45 @@ class CharDecodingStep(nn.Module):
         log_mask = (self.output_mask.to(logits.device) + 1e-45).log()
         return F.log_softmax(logits + log_mask, dim=-1), final_state
 
+    def forward_sequence(self, inputs, previous_state, encoder_lens, encoder_hidden_states):
+        """All decode steps of a teacher-forced pass at once: inputs (B,L) are the characters fed at steps 0..L-1.
+        Returns (log_probs (B,L,V), final_state) — the same numbers as L calls of `forward` chained through
+        `final_state`, because the recurrent state never depends on the attention output (better_model.py:184,
+        223-229): the L-step recurrence is one RNN call, the attention of all positions is one launch of the fused
+        kernel (`LF.attn_context`: the clip's encoder states are staged in shared memory once instead of being
+        re-read from HBM twice per position), the output projection + masked log-softmax is the encoder's kernel."""
+        B, L = inputs.shape
+        h_seq, final_state = self.rnn(self.embedding(inputs), previous_state)          # (B,L,H)
+        q = h_seq
+        enc = encoder_hidden_states
+        Te = enc.shape[1]
+        if self.attention_type != "none":
+            if self.attention_type in ("dot", "general") and enc.is_cuda:
+                qq = q if self.attention_type == "dot" else self.attn_proj_general(q)
+                context, _ = LF.attn_context(qq, enc, encoder_lens)
+            else:
+                if self.attention_type == "dot":
+                    scores = torch.einsum("bth,blh->blt", enc, q)
+                elif self.attention_type == "general":
+                    scores = torch.einsum("bth,blh->blt", enc, self.attn_proj_general(q))
+                else:
+                    both = torch.cat([enc.unsqueeze(1).expand(-1, L, -1, -1), q.unsqueeze(2).expand(-1, -1, Te, -1)], dim=3)
+                    if self.attention_type == "1_layer_nn":
+                        scores = self.attn_proj_1_layer_nn(both).squeeze(-1)
+                    else:
+                        scores = self.attn_proj_layer2(self.attn_proj_layer1(both).tanh()).squeeze(-1)
+                valid = (torch.arange(Te, device=inputs.device).unsqueeze(0) < encoder_lens.unsqueeze(1)).float().unsqueeze(1)
+                w = F.softmax(scores * valid, dim=-1) * valid            # allennlp masked_softmax
+                w = w / (w.sum(dim=-1, keepdim=True) + 1e-13)
+                context = torch.bmm(w, enc)
+            q = self.concat_layer(torch.cat([context, q], dim=2)).tanh()
+        log_mask = (self.output_mask.to(q.device) + 1e-45).log()
+        if q.is_cuda and self.vocab_size <= 68:
+            log_probs = LF.proj_masked_log_softmax(q, self.output_proj.weight, self.output_proj.bias, log_mask)
+        else:
+            log_probs = F.log_softmax(self.output_proj(q) + log_mask, dim=-1)
+        return log_probs, final_state
+
     def save_best_model(self, error, file_path):
         if error < self.best_error:
             self.best_error = error

@@ -31,6 +31,9 @@ SIGNATURES = {
     "lr_ctc_workspace": (_sz, [_i, _i, _i, _i]),
     "lr_conv3d_set_debug": (None, [_vp]),
     "lr_umma_microbench": (ctypes.c_longlong, [_i] * 10 + [_vp]),
+    "lr_umma_pattern_bench": (ctypes.c_longlong, [_vp, _vp, _vp, _i, _i, _vp]),
+    "lr_umma_issue_bench": (ctypes.c_longlong, [_i] * 8 + [_vp]),
+    "lr_conv3d_set_debug_skip": (None, [_i]),
     "lr_ctc_select_kernel": (None, [_i]),
     "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "lr_ctc_greedy_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -49,6 +52,8 @@ SIGNATURES = {
     "lr_warp256": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "lr_posmap_gather": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "lr_mouth_crop": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lr_attn_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "lr_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 

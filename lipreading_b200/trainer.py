@@ -15,6 +15,11 @@ from .ctc import ctc_loss
 from .vocab import BOS, EOS, PAD
 
 
+# True: a fully teacher-forced decode runs as one vectorised pass (CharDecodingStep.forward_sequence) instead of a
+# Python loop over label positions; False keeps the reference's step loop (used by the parity tests as the oracle path)
+SEQUENCE_DECODE = True
+
+
 def _check_batch(chars, char_lens, frame_lens, char2idx, use_ctc):
     assert bool((chars[:, 0] == char2idx[BOS]).all())
     assert bool((chars.gather(1, (char_lens - 1).unsqueeze(1)).squeeze(1) == char2idx[EOS]).all())
@@ -54,13 +59,20 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
             enc_h, prev_state = encoder(frames, frame_lens_d)
         prev_output = torch.full((batch_size,), char2idx[BOS], dtype=torch.long, device=device)
 
-        decoder_loss = 0
-        for i in range(max_label_len):
-            teacher_forcing = bool(torch.rand(1) < teacher_forcing_ratio)
-            input_ = chars[:, i] if teacher_forcing else prev_output
-            log_probs, prev_state = decoding_step(input_, prev_state, frame_lens_d, enc_h)
-            decoder_loss = decoder_loss + F.nll_loss(log_probs, labels[:, i], ignore_index=pad, reduction="sum")
-            prev_output = log_probs.exp().multinomial(1).squeeze(-1)
+        if teacher_forcing_ratio >= 1 and SEQUENCE_DECODE and hasattr(decoding_step, "forward_sequence"):
+            # always teacher forcing: no step depends on a sampled character, so the whole decode loop is one
+            # vectorised pass (the reference's per-step torch.rand / multinomial draws have no effect on the loss)
+            log_probs, prev_state = decoding_step.forward_sequence(chars[:, :max_label_len], prev_state, frame_lens_d, enc_h)
+            decoder_loss = F.nll_loss(log_probs.reshape(-1, log_probs.shape[-1]), labels[:, :max_label_len].reshape(-1),
+                                      ignore_index=pad, reduction="sum")
+        else:
+            decoder_loss = 0
+            for i in range(max_label_len):
+                teacher_forcing = bool(torch.rand(1) < teacher_forcing_ratio)
+                input_ = chars[:, i] if teacher_forcing else prev_output
+                log_probs, prev_state = decoding_step(input_, prev_state, frame_lens_d, enc_h)
+                decoder_loss = decoder_loss + F.nll_loss(log_probs, labels[:, i], ignore_index=pad, reduction="sum")
+                prev_output = log_probs.exp().multinomial(1).squeeze(-1)
         decoder_loss = decoder_loss / n_tokens
 
         opt.zero_grad()
@@ -115,11 +127,19 @@ def eval(encoder, decoding_step, data_loader, device, char2idx):
                     continue
             else:
                 enc_h, prev_state = encoder(frames, frame_lens_d)
-            for i in range(int(ll_h.max())):
-                log_probs, prev_state = decoding_step(chars[:, i], prev_state, frame_lens_d, enc_h)
-                decoder_loss += F.nll_loss(log_probs, labels[:, i], ignore_index=pad, reduction="sum")
-                sampled = log_probs.exp().multinomial(1).squeeze(-1)
-                correct += ((sampled == labels[:, i]) & (labels[:, i] != pad)).sum()
+            Lm = int(ll_h.max())
+            if SEQUENCE_DECODE and hasattr(decoding_step, "forward_sequence"):
+                log_probs, prev_state = decoding_step.forward_sequence(chars[:, :Lm], prev_state, frame_lens_d, enc_h)
+                flat, lab = log_probs.reshape(-1, log_probs.shape[-1]), labels[:, :Lm].reshape(-1)
+                decoder_loss += F.nll_loss(flat, lab, ignore_index=pad, reduction="sum")
+                sampled = flat.exp().multinomial(1).squeeze(-1)      # same distribution as the per-step draws
+                correct += ((sampled == lab) & (lab != pad)).sum()
+            else:
+                for i in range(Lm):
+                    log_probs, prev_state = decoding_step(chars[:, i], prev_state, frame_lens_d, enc_h)
+                    decoder_loss += F.nll_loss(log_probs, labels[:, i], ignore_index=pad, reduction="sum")
+                    sampled = log_probs.exp().multinomial(1).squeeze(-1)
+                    correct += ((sampled == labels[:, i]) & (labels[:, i] != pad)).sum()
             count += int(ll_h.sum())
     encoder._t_max_hint = None
     count_t = torch.tensor(float(count), device=device)
