@@ -162,10 +162,25 @@ GEMM_DTYPE = torch.float32
 RNN_CLUSTER = False
 
 
-def _mm(a, b):
+def _lowp(t):
+    """operand of a throughput-path GEMM: GEMM_DTYPE, converted at most once"""
+    return t if t.dtype == GEMM_DTYPE else t.to(GEMM_DTYPE)
+
+
+def _mm(a, b, bias=None, out_dtype=torch.float32):
+    """plain GEMM -> cuBLAS.  fp32 path: a @ b [+ bias].  bf16 path: bf16 operands, fp32 accumulation, the result
+    written once in `out_dtype` (no bf16 round trip, no separate bias pass)."""
     if GEMM_DTYPE == torch.float32:
-        return a @ b
-    return (a.to(GEMM_DTYPE) @ b.to(GEMM_DTYPE)).float()
+        r = a.float() @ b.float()
+        if bias is not None:
+            r = r + bias
+        return r if out_dtype == torch.float32 else r.to(out_dtype)
+    a, b = _lowp(a), _lowp(b)
+    if out_dtype == GEMM_DTYPE:
+        return torch.mm(a, b) if bias is None else torch.addmm(bias.to(GEMM_DTYPE), a, b)
+    if bias is None:
+        return torch.mm(a, b, out_dtype=out_dtype)
+    return torch.addmm(bias.to(out_dtype), a, b, out_dtype=out_dtype)
 
 
 class _RNNLayer(torch.autograd.Function):
@@ -178,12 +193,13 @@ class _RNNLayer(torch.autograd.Function):
         G = N.RNN_GATES[mode]
         B, T, I = x.shape
         H = weights[1].shape[1]
-        x2 = N.cont(x.reshape(B * T, I), torch.float32)
+        # throughput path: a bf16 feature tensor (conv front-end) feeds the input GEMM as it is
+        x2 = N.cont(x.reshape(B * T, I), torch.float32 if GEMM_DTYPE == torch.float32 else GEMM_DTYPE)
         w_ih = torch.cat([weights[4 * d + 0] for d in range(D)], 0)            # (D*G*H, I)
         b_ih = torch.cat([weights[4 * d + 2] for d in range(D)], 0)
         w_hh = torch.stack([weights[4 * d + 1] for d in range(D)], 0).contiguous()   # (D,G*H,H)
         b_hh = torch.stack([weights[4 * d + 3] for d in range(D)], 0).contiguous()
-        gi = _mm(x2, w_ih.t()) + b_ih                                           # plain GEMM -> cuBLAS
+        gi = _mm(x2, w_ih.t(), bias=b_ih)                                       # plain GEMM -> cuBLAS
         lens32 = N.cont(lens, torch.int32)
         dev = x.device
         hidden = torch.empty((B, T, D * H), dtype=torch.float32, device=dev)
@@ -206,6 +222,7 @@ class _RNNLayer(torch.autograd.Function):
         ctx.mode, ctx.dims = mode, (B, T, I, H, D, G)
         ctx.save_for_backward(x2, lens32, w_ih, w_hh, hidden, saved if saved is not None else torch.empty(0, device=dev))
         ctx.x_needs_grad = x.requires_grad
+        ctx.x_dtype = x.dtype
         if mode == "LSTM":
             return hidden, h_n, c_n
         return hidden, h_n
@@ -237,16 +254,20 @@ class _RNNLayer(torch.autograd.Function):
                                  ws.numel(), N.stream()), "lr_rnn_bwd")
         # weight-gradient reductions over B*T: plain GEMMs -> cuBLAS
         d_gi2 = d_gi.reshape(B * T, D * G * H)
-        d_w_ih = _mm(d_gi2.t(), x2)                                             # (D*G*H, I)
-        d_b_ih = d_gi2.sum(0)
-        d_gh3 = d_gh.reshape(B * T, D, G * H)
+        d_gh2 = d_gh.reshape(B * T, D * G * H)
         h_prev3 = h_prev.reshape(B * T, D, H)
+        d_b_ih = d_gi2.sum(0)
+        d_b_hh = d_gh2.sum(0)
+        if GEMM_DTYPE != torch.float32:                                         # one conversion per operand
+            d_gi2, d_gh2, h_prev3 = _lowp(d_gi2), _lowp(d_gh2), _lowp(h_prev3)
+        d_w_ih = _mm(d_gi2.t(), x2)                                             # (D*G*H, I)
+        d_gh3 = d_gh2.reshape(B * T, D, G * H)
         grads = []
         for d in range(D):
             d_w_hh = _mm(d_gh3[:, d].t(), h_prev3[:, d])                        # (G*H, H)
-            d_b_hh = d_gh3[:, d].sum(0)
-            grads += [d_w_ih[d * G * H:(d + 1) * G * H], d_w_hh, d_b_ih[d * G * H:(d + 1) * G * H], d_b_hh]
-        d_x = _mm(d_gi2, w_ih).reshape(B, T, I) if ctx.x_needs_grad else None
+            grads += [d_w_ih[d * G * H:(d + 1) * G * H], d_w_hh, d_b_ih[d * G * H:(d + 1) * G * H],
+                      d_b_hh[d * G * H:(d + 1) * G * H]]
+        d_x = _mm(d_gi2, w_ih, out_dtype=ctx.x_dtype).reshape(B, T, I) if ctx.x_needs_grad else None
         return (d_x, None, None) + tuple(grads)
 
 
