@@ -5,8 +5,11 @@ What runs where
   * face box: dlib's HOG detector is an un-vendored third-party model (not in the reference tree,
     not in this image) -> the box is an INPUT here: pass `rects`, or plug any detector through
     `set_detector(callable(frames)->(N,4) left,right,top,bottom)`;
-  * position-map CNN (PRNet resfcn256): the reference ships no weights (`.gitignore:5`) -> pluggable
-    `PosMapPredictor`; the default raises.  SURVEY §8f row f4;
+  * position-map CNN (PRNet resfcn256): `lipreading_b200.prnet.PosPrediction` (architecture pinned by the
+    reference's checkpoint index; convolutions through cuDNN).  The reference ships no weights (`.gitignore:5`):
+    the default predictor restores `data/weights/prnet/net/256_256_resfcn256_weight` when the data shard is
+    there (prnet.py:42-45) and asserts like the reference when it is not; any other predictor plugs in through
+    `set_posmap_predictor`.  SURVEY §8 row a5 / f4;
   * everything between and after (pad rect, crop box, /255 + similarity warp to 256x256, restore,
     68-landmark / 43 867-vertex gather, translate to the padded face frame): sm_100a kernels.
 """
@@ -109,10 +112,21 @@ class PRN:
         return LF.posmap_gather(pos, self._geom[1], rect_pad, self._kpt_flat, self._face_flat)[1][0].cpu().numpy()
 
 
+def _default_predictor():
+    """PosPrediction restored from the workspace weights, exactly where the reference looks (prnet.py:42-45)."""
+    from . import workspace as _ws
+    from .prnet import PosPrediction
+    prn_path = _ws.getRelWeightsPath("prnet", "net/256_256_resfcn256_weight")
+    assert os.path.isfile(prn_path + ".data-00000-of-00001"), "please download PRN trained model first."
+    pred = PosPrediction()
+    pred.restore(prn_path)
+    return pred.predict_batch
+
+
 def _getSharedPrn():
     global _prn
     if _prn is None:
-        _prn = PRN(predict_batch=_predictor)
+        _prn = PRN(predict_batch=_predictor if _predictor is not None else _default_predictor())
     return _prn
 
 

@@ -7,7 +7,7 @@ Writes tests/golden/seq_<case>.npz: seeded inputs, the reference modules' state_
 outputs (log-probs, hidden states, final state, CTC 'mean'/'sum' incl. the mixed-length weighting
 quirk, gradients w.r.t. every encoder parameter, one full train() step's losses and updated
 weights).  The reference is imported through oracle/ref_harness.py (two shims: allennlp.nn.util,
-spacy).  Also copies the reference's own index fixtures (uv_kpt_ind.txt, face_ind.txt).
+spacy).  Also copies the reference's own index fixtures (uv_kpt_ind.txt, face_ind.txt, the PRNet checkpoint index).
 """
 import os
 import sys
@@ -110,6 +110,10 @@ def main():
     import shutil
     shutil.copyfile(os.path.join(src, "uv_kpt_ind.txt"), os.path.join(GOLD, "uv_kpt_ind.txt"))
     np.save(os.path.join(GOLD, "face_ind.npy"), np.loadtxt(os.path.join(src, "face_ind.txt")).astype(np.int32))
+    # the PRNet checkpoint's index (variable names / shapes / offsets; the data shard is not in the reference tree)
+    shutil.copyfile(os.path.join(ref_harness.REFERENCE_ROOT,
+                                 "src/models/extern/prnet/Data/net-data/256_256_resfcn256_weight.index"),
+                    os.path.join(GOLD, "prnet_256_256_resfcn256_weight.index"))
 
 
 if __name__ == "__main__":
