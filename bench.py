@@ -266,6 +266,35 @@ def kernel_rooflines(dev, pk, char2idx):
     byts = n * (43867 + 68) * (12 + 24)
     out.append({"kernel": "posmap_gather(lmk+vtx)", "bound": "hbm", "unit": "GB/s", "achieved": byts / s / 1e9,
                 "frac": byts / s / hbm, "shape": "n=%d" % n, "ms": s * 1e3})
+    # N2 mouth crop: reads the mouth ROI of each frame, writes 100x50x3 u8
+    lmk = LF.posmap_gather(pos, crop, rp, kidx)
+    s = time_cuda(lambda: LF.mouth_crop(frames, lmk, rp), flush=flush)
+    _, roi = LF.mouth_crop(frames, lmk, rp)
+    roi_h = roi.cpu().long()
+    # roi = (x_lo, y_lo, w, h); a bilinear sample touches 4 px, so at most 4 * 5000 source px per frame are needed
+    roi_px = int((roi_h[:, 2].clamp(min=0) * roi_h[:, 3].clamp(min=0)).clamp(max=4 * 100 * 50).sum())
+    byts = roi_px * 3 + n * 100 * 50 * 3
+    out.append({"kernel": "mouth_crop", "bound": "hbm", "unit": "GB/s", "achieved": byts / s / 1e9, "frac": byts / s / hbm,
+                "shape": "n=%d, ROI px read + 15 kB written per frame" % n, "ms": s * 1e3})
+    # whole per-frame vision path (BASELINE config 2): rect geometry -> warp256 -> PRNet CNN (cuDNN, bf16, random
+    # weights: the reference ships none) -> restore + 68-landmark gather.  4.13 GMAC/frame in the CNN.
+    try:
+        from lipreading_b200.prnet import PosPrediction
+        pred = PosPrediction(device=dev, dtype=torch.bfloat16)
+        nb = 64
+
+        def vision():
+            for i in range(0, n, nb):
+                r2, c2 = LF.rect_geometry(rects[i:i + nb], H, W)
+                pm = pred.predict_batch(LF.warp256(frames[i:i + nb], c2))
+                LF.posmap_gather(pm, c2, r2, kidx)
+        s = time_cuda(vision, iters=3, warm=2)
+        out.append({"kernel": "vision_stream(frames->68 landmarks, incl. PRNet CNN via cuDNN bf16)", "bound": "tensor",
+                    "unit": "frames/s", "achieved": n / s, "frac": n * 2 * 4.13e9 / s / 1e12 / pk["bf16_tflops"],
+                    "shape": "n=%d,720p, batches of %d" % (n, nb), "ms": s * 1e3})
+        del pred
+    except Exception as e:
+        out.append({"kernel": "vision_stream", "error": repr(e)})
     # recurrent layer fwd (BiGRU-256, B=256, T=75): latency-bound; report FLOP/s of the recurrent GEMMs
     from lipreading_b200.model import NativeRNN
     rnn = NativeRNN("GRU", 1728, 256, bidirectional=True).to(dev)

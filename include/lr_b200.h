@@ -178,6 +178,16 @@ int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint
                   int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
                   int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y,
                   int o_x, int J, int swap, void* stream);
+/* dgrad of a conv layer fused with the backward of the ReLU + MaxPool(1,2,2) in front of it
+ * (= lr_conv3d_fwd with epi_mode 1 followed by lr_unpool, in one pass): `dy`/`w` as for a dgrad call of
+ * lr_conv3d_fwd (Cout = the layer's INPUT channels, 32/64/128); argmax (B,T,H,W,Cout) are the pooling
+ * layer's arg-max bytes; the un-pooled gradient is written into the interior (o_t,o_y,o_x) of the
+ * zero-padded volume dy_below (B,oTp,oHp,oWp,Cout) — only the 2x2 windows of pooled pixels, the rest
+ * must already be zero — and d_bias (Cout) f32 (or NULL) receives its per-channel sum.           */
+int lr_conv3d_dgrad_unpool(const void* dy, const void* w, const uint8_t* argmax, void* dy_below,
+                           float* d_bias, int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG,
+                           int Cout, int KT, int KH, int KW, int oTp, int oHp, int oWp, int o_t,
+                           int o_y, int o_x, int J, int swap, void* stream);
 /* Backward of ReLU+MaxPool(1,2,2): d_pooled (B,T,H/2,W/2,C) bf16 + argmax -> gradient w.r.t. the
  * conv output, written into the interior (pt,ph,pw) of a zero-padded channel-grouped volume
  * [C/Cg][B][Tp][Hp][Wp][Cg] ready to be the `x` of a dgrad pass; d_bias (C) f32 or NULL receives

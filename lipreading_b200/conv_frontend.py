@@ -23,6 +23,7 @@ N.register("lr_conv3d_supported", _i, [])
 N.register("lr_clip_s2d", _i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp])
 N.register("lr_unpool", _i, [_vp, _vp, _vp, _vp] + [_i] * 12 + [_vp])
 N.register("lr_conv3d_fwd", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 21 + [_vp])
+N.register("lr_conv3d_dgrad_unpool", _i, [_vp, _vp, _vp, _vp, _vp] + [_i] * 20 + [_vp])
 N.register("lr_pack_conv_weights", _i, [_vp, _vp, _i, _i, _i, _i, _vp])
 N.register("lr_pack_conv_weights_kt", _i, [_vp, _vp, _i, _i, _i, _i, _i, _vp])
 N.register("lr_conv3d_wgrad_out_floats", N._sz, [_i] * 5)
@@ -116,12 +117,15 @@ KERNEL_TIMING = None
 # conv orientation (see lr_b200.h): 0 = one MMA per tap, 1 = channels on the MMA M lanes, 3 = the KT kt-taps of a
 # spatial tap stacked on N (input plane c x [W(kt=KT-1);..;W(kt=0)] -> accumulators of frames c-KT+1..c)
 SWAP = 3
+FUSE_UNPOOL = True      # dgrad epilogue writes the un-pooled gradient of the layer below (+ its bias gradient) directly
 DGRAD_KX_STACK = False  # conv2 dgrad (Cout = 32): the 5 kx-taps of a filter row share one N = 160 MMA (orientation 2)
 
 
 def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, epi_mode, ovol, ooff, J=0,
-                  tag="conv", algo_macs=None, swap=None):
-    """Thin call into lr_conv3d_fwd (see include/lr_b200.h).  w: bf16 [Cout][CG][taps][Cin] (packed here)."""
+                  tag="conv", algo_macs=None, swap=None, d_bias=None):
+    """Thin call into lr_conv3d_fwd (see include/lr_b200.h).  w: bf16 [Cout][CG][taps][Cin] (packed here).
+    epi_mode 2 = lr_conv3d_dgrad_unpool: `argmax` is the INPUT arg-max map, `y` the padded dY volume of the layer
+    below, `d_bias` receives that layer's bias gradient."""
     taps = K[0] * K[1] * K[2]
     w = N.cont(w)
     assert w.dtype == torch.bfloat16 and w.numel() == Cout * CG * taps * Cin
@@ -139,10 +143,16 @@ def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, e
     if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Hp, Wp,
-                                  Cin, CG, Cout, K[0], K[1], K[2], epi_mode, ovol[0], ovol[1], ovol[2],
-                                  ooff[0], ooff[1], ooff[2], J, mode, N.stream()),
-            "lr_conv3d_fwd")
+    if epi_mode == 2:
+        N.check(N.lib().lr_conv3d_dgrad_unpool(N.ptr(x), N.ptr(w), N.ptr(argmax), N.ptr(y), N.ptr(d_bias), B, T, H, W,
+                                               Hp, Wp, Cin, CG, Cout, K[0], K[1], K[2], ovol[0], ovol[1], ovol[2],
+                                               ooff[0], ooff[1], ooff[2], J, mode, N.stream()),
+                "lr_conv3d_dgrad_unpool")
+    else:
+        N.check(N.lib().lr_conv3d_fwd(N.ptr(x), N.ptr(w), N.ptr(bias), N.ptr(y), N.ptr(argmax), B, T, H, W, Hp, Wp,
+                                      Cin, CG, Cout, K[0], K[1], K[2], epi_mode, ovol[0], ovol[1], ovol[2],
+                                      ooff[0], ooff[1], ooff[2], J, mode, N.stream()),
+                "lr_conv3d_fwd")
     if rec is not None:
         e1.record()
         macs = algo_macs if algo_macs is not None else B * T * H * W * Cout * Cin * CG * K[0] * K[1] * K[2]
@@ -279,18 +289,29 @@ class _ConvStack(torch.autograd.Function):
         dy3, db3 = unpool(dp3, am3, H3, W3, 96, 32, (1, 1, 1), Hp3, Wp3)
         d3 = conv3d_wgrad_native(a2, dy3, B, T, H3, W3, Hp3, Wp3, 64, 32, 3, (Hp3 + 1) * Wp3 + 1, (3, 3, 3), 1)
         dw3 = d3.reshape(3, 3, 3, 64, 96).permute(4, 3, 0, 1, 2)       # [tap][ci][co] -> (co,ci,kt,ky,kx)
-        da2 = torch.empty((B, T, H3, W3, 64), dtype=bf, device=dev)
-        conv3d_native(dy3, dgrad_weight(w3.detach(), 32).to(bf), None, da2, None, B, T, H3, W3, Hp3, Wp3, 32, 3,
-                      64, (3, 3, 3), 1, (T, H3, W3), (0, 0, 0), tag="conv3.dgrad")
-        # ---- layer 2 ----
-        dy2, db2 = unpool(da2, am2, H2, W2, 64, 64, (1, 2, 2), Hp2, Wp2)
+
+        def dgrad_unpool(dy, wflip, am, Hd, Wd, Hpd, Wpd, Cin, CG, C, K, pad, Hb, Wb, Hpo, Wpo, tag, swap=None):
+            """dgrad of the layer whose output gradient is `dy` (pooled resolution Hd x Wd of the layer below),
+            producing the dY volume (valid extent Hb x Wb, padded Hpo x Wpo) and bias gradient of the layer below"""
+            if FUSE_UNPOOL:
+                out = POOL.get("dy%d" % C, (1, B, T + 2, Hpo, Wpo, C), bf, dev)
+                d_bias = torch.empty(C, dtype=torch.float32, device=dev)
+                conv3d_native(dy, wflip, None, out, am, B, T, Hd, Wd, Hpd, Wpd, Cin, CG, C, K, 2, (T + 2, Hpo, Wpo),
+                              pad, tag=tag, swap=swap, d_bias=d_bias)
+                return out, d_bias
+            da = torch.empty((B, T, Hd, Wd, C), dtype=bf, device=dev)
+            conv3d_native(dy, wflip, None, da, None, B, T, Hd, Wd, Hpd, Wpd, Cin, CG, C, K, 1, (T, Hd, Wd), (0, 0, 0),
+                          tag=tag, swap=swap)
+            return unpool(da, am, Hb, Wb, C, C, pad, Hpo, Wpo)
+
+        # ---- layer 2: dgrad of conv3 fused with the un-pooling of pool2 -> dY2 (+ conv2's bias gradient) ----
+        dy2, db2 = dgrad_unpool(dy3, dgrad_weight(w3.detach(), 32).to(bf), am2, H3, W3, Hp3, Wp3, 32, 3, 64, (3, 3, 3),
+                                (1, 2, 2), H2, W2, Hp2, Wp2, "conv3.dgrad")
         d2 = conv3d_wgrad_native(a1, dy2, B, T, H2, W2, Hp2, Wp2, 32, 64, 1, (Hp2 + 2) * Wp2 + 2, (3, 5, 5), 0)
         dw2 = d2.reshape(3, 5, 5, 64, 32).permute(3, 4, 0, 1, 2)       # [tap][co][ci]
-        da1 = torch.empty((B, T, H2, W2, 32), dtype=bf, device=dev)
-        conv3d_native(dy2, dgrad_weight(w2.detach(), 64).to(bf), None, da1, None, B, T, H2, W2, Hp2, Wp2, 64, 1,
-                      32, (3, 5, 5), 1, (T, H2, W2), (0, 0, 0), tag="conv2.dgrad", swap=2 if DGRAD_KX_STACK else None)
         # ---- layer 1 (no input gradient: the clip is data); dY1 top-left aligned in z's geometry ----
-        dy1, db1 = unpool(da1, am1, H1, W1, 32, 32, (0, 0, 0), Hp1, Wp1)
+        dy1, db1 = dgrad_unpool(dy2, dgrad_weight(w2.detach(), 64).to(bf), am1, H2, W2, Hp2, Wp2, 64, 1, 32, (3, 5, 5),
+                                (0, 0, 0), H1, W1, Hp1, Wp1, "conv2.dgrad", swap=2 if DGRAD_KX_STACK else None)
         d1 = conv3d_wgrad_native(z, dy1, B, T, H1, W1, Hp1, Wp1, 16, 32, 1, 0, (3, 3, 3), 0)
         dw1_16 = d1[:, :32, :].permute(1, 0, 2).reshape(32, 3, 3, 3, 16)
         dw1 = s2d_weight_grad(dw1_16)

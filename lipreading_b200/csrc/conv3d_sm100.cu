@@ -66,7 +66,10 @@ struct ConvParams {
   int chunk_bytes;             // 1024-aligned
   int wtile_bytes;             // 1024-aligned
   int tmem_cols;
-  int epi_mode;                // 0: bias+ReLU+pool(1,2,2) ; 1: plain store of valid positions
+  int epi_mode;                // 0: bias+ReLU+pool(1,2,2) ; 1: plain store of valid positions ; 2: fused un-pooling
+                               // (dgrad output routed to the arg-max slot of its 2x2 window + bias gradient)
+  const uint8_t* am_in;        // epi_mode 2: arg-max bytes (B,T,H,W,Cout) of the pooling layer being undone
+  float* d_bias;               // epi_mode 2: per-channel sum of the routed gradient (atomically accumulated)
   int has_bias;
   int oTp, oHp, oWp, o_t, o_y, o_x;   // output volume geometry / interior offset
   long long rows_per_group;    // B*Tp*Hp*Wp
@@ -472,6 +475,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
     int ebuf = 0;
     int it = 0;
+    float bsum[8];            // epi_mode 2: this thread's 8 channels (its channel group is fixed: 128 % cgroups == 0)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int b = item / (p.n_tgroups * p.n_ytiles);
       const int rem = item - b * (p.n_tgroups * p.n_ytiles);
@@ -615,6 +621,36 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               *reinterpret_cast<uint2*>(p.argmax + (ab + e_am[k]) * p.Cout + e_cg[k] * 8) =
                   *reinterpret_cast<const uint2*>(am);
           }
+        } else if (p.epi_mode == 2) {
+          // fused un-pooling (backward of ReLU + MaxPool(1,2,2)): the gradient of pooled pixel (y,x) goes to the
+          // arg-max slot of its 2x2 window in the padded dY volume of the layer below, zeros to the other three
+          // (slot 4 = ReLU-dead: all zeros); the conv bias gradient is the per-channel sum of what was routed
+          const size_t am_base = (((size_t)b * p.T + t) * p.H + y0) * p.W;
+          const size_t oplane = ((size_t)b * p.oTp + (t + p.o_t)) * p.oHp;
+          for (int idx = etid; idx < 128 * cgroups; idx += 128) {
+            const int cg = idx & (cgroups - 1), r = idx >> p.cg_shift;
+            const int yl = r >> p.wp_shift, x = r & (p.Wp - 1);
+            if (x >= p.W || yl >= rows_left) continue;
+            const uint2 a8 = *reinterpret_cast<const uint2*>(p.am_in + (am_base + (size_t)yl * p.W + x) * p.Cout + cg * 8);
+            const uint4 v8 = *reinterpret_cast<const uint4*>(stg + (size_t)r * p.stage_pitch + cg * 16);
+            const uint32_t vw[4] = {v8.x, v8.y, v8.z, v8.w};
+            const uint32_t aw[2] = {a8.x, a8.y};
+            uint32_t o[4][4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {              // two channels per 32-bit word
+              const uint32_t a_lo = (aw[h >> 1] >> (16 * (h & 1))) & 0xffu, a_hi = (aw[h >> 1] >> (16 * (h & 1) + 8)) & 0xffu;
+              const uint32_t lo = vw[h] & 0xffffu, hi = vw[h] & 0xffff0000u;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) o[w][h] = (a_lo == (uint32_t)w ? lo : 0u) | (a_hi == (uint32_t)w ? hi : 0u);
+              bsum[2 * h] += a_lo < 4u ? __uint_as_float(lo << 16) : 0.f;
+              bsum[2 * h + 1] += a_hi < 4u ? __uint_as_float(hi) : 0.f;
+            }
+            __nv_bfloat16* orow = p.y + ((oplane + (size_t)(2 * (y0 + yl) + p.o_y)) * p.oWp + (2 * x + p.o_x)) * p.Cout + cg * 8;
+            *reinterpret_cast<uint4*>(orow) = make_uint4(o[0][0], o[0][1], o[0][2], o[0][3]);
+            *reinterpret_cast<uint4*>(orow + p.Cout) = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
+            *reinterpret_cast<uint4*>(orow + (size_t)p.oWp * p.Cout) = make_uint4(o[2][0], o[2][1], o[2][2], o[2][3]);
+            *reinterpret_cast<uint4*>(orow + (size_t)(p.oWp + 1) * p.Cout) = make_uint4(o[3][0], o[3][1], o[3][2], o[3][3]);
+          }
         } else {
           const int n_out = 128 * cgroups;
           for (int idx = etid; idx < n_out; idx += 128) {
@@ -632,6 +668,15 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       if (MODE == 3) tmem_wait_st();
       tc_fence_before();
       if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
+    }
+    if (p.epi_mode == 2 && p.d_bias) {
+      // lanes with the same (lane & (cgroups-1)) hold the same 8 channels: butterfly over the other lane bits
+      for (int o = cgroups; o < 32; o <<= 1)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bsum[e] += __shfl_xor_sync(0xffffffffu, bsum[e], o);
+      if (lane < cgroups)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(p.d_bias + lane * 8 + e, bsum[e]);
     }
   }
 
@@ -861,17 +906,20 @@ extern "C" int lr_unpool(const void* d_pooled, const uint8_t* argmax, void* out,
 // x: zero-padded, channel-grouped bf16 volume [CG][B][Tp][Hp][Wp][Cin] with Tp=T+KT-1, Hp >= H+KH-1
 // (a multiple of 128/Wp keeps tiles inside their plane), Wp = power of two >= W+KW-1.
 // w: tile images from lr_pack_conv_weights: [CG][KT*KH*KW][Cout rows x Cin] bf16, 16-byte chunks swizzled.
-extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
-                             int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
-                             int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
-                             int J, int swap, void* stream) {
+static int conv3d_launch(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
+                         const uint8_t* am_in, float* d_bias,
+                         int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
+                         int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
+                         int J, int swap, void* stream) {
   LR_CHECK_ARG(x && w && y, "lr_conv3d_fwd: null pointer");
   LR_CHECK_ARG(Cin == 16 || Cin == 32 || Cin == 64, "lr_conv3d_fwd: Cin per group must be 16/32/64 (got %d)", Cin);
   LR_CHECK_ARG(Cout % 32 == 0 && Cout >= 32 && Cout <= 128, "lr_conv3d_fwd: Cout must be 32..128, %%32 (got %d)", Cout);
   LR_CHECK_ARG(Wp == 8 || Wp == 16 || Wp == 32 || Wp == 64 || Wp == 128, "lr_conv3d_fwd: Wp must be 8..128 pow2");
   LR_CHECK_ARG(Wp >= W + KW - 1 && Hp >= H + KH - 1, "lr_conv3d_fwd: padded extents smaller than H+KH-1 / W+KW-1");
   LR_CHECK_ARG(KT >= 1 && KH >= 1 && KW >= 1 && CG >= 1 && B > 0 && T > 0 && H > 0 && W > 0, "lr_conv3d_fwd: bad shape");
-  LR_CHECK_ARG(epi_mode == 0 || epi_mode == 1, "lr_conv3d_fwd: bad epilogue mode");
+  LR_CHECK_ARG(epi_mode >= 0 && epi_mode <= 2, "lr_conv3d_fwd: bad epilogue mode");
+  LR_CHECK_ARG(epi_mode != 2 || (am_in && (Cout == 32 || Cout == 64 || Cout == 128) && swap != 1),
+               "lr_conv3d_dgrad_unpool: needs the arg-max bytes, Cout in {32,64,128}, positions on M");
   LR_CHECK_ARG(KT * KH * KW <= kMaxTaps, "lr_conv3d_fwd: more than %d taps", kMaxTaps);
   if (!lr_conv3d_supported()) { lr_set_error("lr_conv3d_fwd needs an sm_100 device"); return LR_EARCH; }
 
@@ -881,7 +929,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   p.Tp = T + KT - 1; p.Hp = Hp; p.Wp = Wp;
   p.KT = KT; p.KH = KH; p.KW = KW; p.Cin = Cin; p.CG = CG; p.Cout = Cout;
   p.R = 128 / Wp;
-  LR_CHECK_ARG(epi_mode == 1 || (p.R % 2 == 0), "lr_conv3d_fwd: pooling needs an even number of tile rows");
+  LR_CHECK_ARG(epi_mode != 0 || (p.R % 2 == 0), "lr_conv3d_fwd: pooling needs an even number of tile rows");
   p.CH = 128 + (KH - 1) * Wp + (KW - 1);
   LR_CHECK_ARG(p.CH <= 256, "lr_conv3d_fwd: halo too large for one TMA box (CH=%d)", p.CH);
   p.row_bytes = Cin * 2;
@@ -891,7 +939,7 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   swap = mode == 1;
   p.kxs = mode == 2 ? KW : 1;
   if (mode == 2) {
-    LR_CHECK_ARG(epi_mode == 1 && Cout == 32 && KW >= 2 && KW <= 5 && KW * Cout <= 256 && (KW * Cout) % 16 == 0,
+    LR_CHECK_ARG(epi_mode >= 1 && Cout == 32 && KW >= 2 && KW <= 5 && KW * Cout <= 256 && (KW * Cout) % 16 == 0,
                  "lr_conv3d_fwd: kx-stacking needs the plain-store epilogue, Cout = 32 and 2 <= KW <= 5");
   }
   p.n_eff_taps = KT * KH * KW / p.kxs;
@@ -953,6 +1001,9 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
   while (cols < n_sets * J * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   p.epi_mode = epi_mode;
+  p.am_in = am_in;
+  p.d_bias = d_bias;
+  if (epi_mode == 2 && d_bias) LR_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * Cout, lr_stream(stream)));
   p.has_bias = bias != nullptr;
   p.bias = bias;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
@@ -1039,4 +1090,27 @@ extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, vo
 #undef LR_LAUNCH_CONV
   LR_CHECK_LAUNCH();
   return LR_OK;
+}
+
+extern "C" int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint8_t* argmax,
+                             int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG, int Cout, int KT,
+                             int KH, int KW, int epi_mode, int oTp, int oHp, int oWp, int o_t, int o_y, int o_x,
+                             int J, int swap, void* stream) {
+  LR_CHECK_ARG(epi_mode == 0 || epi_mode == 1, "lr_conv3d_fwd: bad epilogue mode");
+  return conv3d_launch(x, w, bias, y, argmax, nullptr, nullptr, B, T, H, W, Hp, Wp, Cin, CG, Cout, KT, KH, KW, epi_mode,
+                       oTp, oHp, oWp, o_t, o_y, o_x, J, swap, stream);
+}
+
+// dgrad of one conv layer fused with the backward of the ReLU + MaxPool(1,2,2) in front of it: instead of the
+// pooled-resolution gradient (B,T,H,W,Cout), the epilogue writes the un-pooled gradient straight into the padded
+// dY volume (B,oTp,oHp,oWp,Cout) of the layer below (2x2 window of pooled pixel (y,x) at rows 2y+o_y.., columns
+// 2x+o_x..) and accumulates that layer's bias gradient — lr_conv3d_fwd(epi_mode 1) + lr_unpool in one pass.
+extern "C" int lr_conv3d_dgrad_unpool(const void* dy, const void* w, const uint8_t* argmax, void* dy_below,
+                                      float* d_bias, int B, int T, int H, int W, int Hp, int Wp, int Cin, int CG,
+                                      int Cout, int KT, int KH, int KW, int oTp, int oHp, int oWp, int o_t,
+                                      int o_y, int o_x, int J, int swap, void* stream) {
+  LR_CHECK_ARG(argmax && dy_below, "lr_conv3d_dgrad_unpool: null pointer");
+  LR_CHECK_ARG(oHp >= 2 * H + o_y && oWp >= 2 * W + o_x, "lr_conv3d_dgrad_unpool: output volume too small");
+  return conv3d_launch(dy, w, nullptr, dy_below, nullptr, argmax, d_bias, B, T, H, W, Hp, Wp, Cin, CG, Cout, KT, KH, KW,
+                       2, oTp, oHp, oWp, o_t, o_y, o_x, J, swap, stream);
 }

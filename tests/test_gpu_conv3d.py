@@ -195,6 +195,38 @@ def test_conv_stack_forward_backward_matches_oracle(native_lib, cuda):
         assert err < 3e-2, (name, err)
 
 
+@pytest.mark.parametrize("B,T", [(2, 6), (3, 11)])
+def test_fused_dgrad_unpool_equals_two_pass(native_lib, cuda, B, T):
+    """lr_conv3d_dgrad_unpool (dgrad epilogue routes each pooled gradient to its arg-max slot and sums the bias
+    gradient) vs lr_conv3d_fwd(epi_mode 1) + lr_unpool: the dY volumes are bit-identical, so the weight gradients of
+    the layers below are too; bias gradients differ only by fp32 summation order."""
+    from lipreading_b200 import conv_frontend as CF
+    torch.manual_seed(7)
+    front = CF.ConvFrontEnd((100, 50)).to(cuda)
+    clip = torch.randint(0, 256, (B, T, 100, 50, 3), dtype=torch.uint8).to(cuda)
+    up = torch.randn(B, T, 1728, device=cuda)
+    grads, vols = {}, {}
+    for fused in (False, True):
+        CF.FUSE_UNPOOL = fused
+        try:
+            front.zero_grad()
+            (front(clip) * up).sum().backward()
+            torch.cuda.synchronize()
+        finally:
+            CF.FUSE_UNPOOL = True
+        grads[fused] = {k: v.grad.clone() for k, v in front.named_parameters()}
+        vols[fused] = {k: v.clone() for k, v in CF.POOL.bufs.items() if k[0] in ("dy32", "dy64")}
+    assert len(vols[True]) == 2
+    for k in vols[True]:
+        assert torch.equal(vols[True][k], vols[False][k]), k[0]
+        assert float(vols[True][k].abs().max()) > 0
+    for k in ("conv1.weight", "conv2.weight", "conv3.weight"):
+        assert torch.equal(grads[True][k], grads[False][k]), k
+    for k in ("conv1.bias", "conv2.bias", "conv3.bias"):          # atomically accumulated in both paths
+        ref = grads[False][k]
+        assert float((grads[True][k] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-6, k
+
+
 @pytest.mark.parametrize("H,W,C,Cg,pad", [(50, 25, 32, 32, (0, 0, 0)), (25, 12, 64, 64, (1, 2, 2)), (12, 6, 96, 32, (1, 1, 1))])
 def test_unpool_routes_gradient_to_argmax(native_lib, cuda, H, W, C, Cg, pad):
     """lr_unpool vs direct indexing: the arg-max position of each 2x2 window receives the pooled gradient,
