@@ -238,6 +238,13 @@ int lr_attn_bwd(const float* q, const float* enc, const int32_t* lens, const flo
                 const float* zsum, const float* d_ctx, int B, int L, int T, int H, float* d_q,
                 float* d_enc, void* stream);
 
+/* Orientation 3 only (default 1).  0: every MMA-issuing warp stacks inside its own run of frames — each accumulator
+ * is written by one thread in program order (bit-reproducible), at the price of narrow ramp-up/ramp-down MMAs at
+ * both ends of every run.  1 (layers with >= 32 input channels per group): the chunks of a work item form one list shared out between the issuing warps, every
+ * input plane is multiplied once with the widest window it has; the KT-1 frames at a hand-over point receive MMAs
+ * from two threads, so their fp32 summation order (not the set of terms) depends on timing.                    */
+void lr_conv3d_set_seam(int on);
+
 /* -------- diagnostics ------------------------------------------------------------------------ */
 /* SM cycles for `iters` back-to-back tcgen05.mma of one shape with operands resident in shared memory
  * (tools/umma_table.py): the measured per-instruction cost that tile-orientation choices are based on.

@@ -90,6 +90,9 @@ struct ConvParams {
                                // = kt * chunk + (ky*Wp + kx) rows — read with uniform constant loads
   int n_issuers;               // MMA-issuing warps that take part in the barrier protocol
   int Jg;                      // mode 3: frames per issuing warp (J split into n_issuers runs)
+  int seam;                    // mode 3: 1 = the item's chunks form ONE list shared out between the issuing warps (every
+                               // input plane is multiplied once, with the widest window it has); the accumulators of the
+                               // KT-1 frames at a hand-over point then receive MMAs from two threads (sum order not fixed)
   int stage_fence;             // diagnostics: tcgen05.fence::after_thread_sync after every weight-stage wait (old behaviour)
   int skip;                    // diagnostics (lr_conv3d_set_debug_skip): 1 no epilogue work, 2 weights loaded once,
                                // 4 input chunks loaded once — wrong results, used to find the limiting role
@@ -332,16 +335,36 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int tg = rem / p.n_ytiles;
         rem += rem_step;
         if (rem >= tiles_per_group) rem -= tiles_per_group;
-        const int jn = min(p.Jg, min(p.J, p.T - tg * p.J) - g_first);     // frames of this warp's run (<= 0: none)
+        const int jn_item = min(p.J, p.T - tg * p.J);
+        // run mode: this warp's frames [g_first, g_first + jn) are a self-contained sub-item (chunks 0 .. jn+KT-2 of it);
+        // seam mode: jn = all frames of the item, this warp walks chunks [c_lo, c_hi) of the item's single chunk list
+        const int f0 = p.seam ? 0 : g_first;
+        int jn = p.seam ? jn_item : min(p.Jg, jn_item - g_first);         // (<= 0: nothing to do)
+        int c_lo = 0, c_hi = jn + KT - 1;
+        if (p.seam) {
+          if (jn >= KT - 1) {
+            const int per = (c_hi + p.n_issuers - 1) / p.n_issuers;
+            c_lo = min(c_hi, (warp - 1) * per);
+            c_hi = min(c_hi, c_lo + per);
+          } else if (warp != 1) {
+            jn = 0;                                                       // tail fallback: the first warp does it all
+          }
+        }
         const int set = it & (p.n_sets - 1);
-        const uint32_t d_base = tmem_base + (uint32_t)((set * p.J + g_first) * p.acc_cols);
+        const uint32_t d_base = tmem_base + (uint32_t)((set * p.J + f0) * p.acc_cols);
         timed_wait(&bars[BAR_ACC_EMPTY + set], ((it / p.n_sets) & 1) ^ 1, dbg0, dbg_on);
         const int aset = it & (p.a_sets - 1);
         timed_wait(&bars[BAR_A_FULL + aset], (it / p.a_sets) & 1, dbg1, dbg_on);
         tc_fence_after();
         const uint64_t a_item = a_desc0 + (uint64_t)(aset * (p.a_set_bytes >> 4)) +
-                                (uint64_t)((uint32_t)g_first * ((uint32_t)p.chunk_bytes >> 4));
+                                (uint64_t)((uint32_t)f0 * ((uint32_t)p.chunk_bytes >> 4));
         const int n_steady = jn - (KT - 1);                 // chunks that feed all KT taps (< 0: tail fallback)
+        // state of the chunk walk at its first chunk c_lo: window = frames [lo_f, hi_f]
+        const int lo_f = max(0, c_lo - (KT - 1)), hi_f = min(jn - 1, c_lo);
+        const uint32_t a_first = (uint32_t)c_lo * chunk16;
+        const uint32_t b_first = (uint32_t)(KT - 1 - (c_lo - lo_f)) * blk16;
+        const uint32_t id_first = idesc1 + (uint32_t)(hi_f - lo_f) * istep;
+        const uint32_t d_first = d_base + (uint32_t)lo_f * cout;
         for (int g = 0; g < p.CG; ++g) {
           const uint32_t goff = (uint32_t)g * group16;
           for (int tap0 = 0; tap0 < n_taps; tap0 += p.tps) {
@@ -359,11 +382,11 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                   // unrolled so that ~8 MMAs are issued between two rewrites of the same descriptor registers:
                   // a tcgen05.mma holds its uniform-register operands until the tensor pipe accepts it (the next
                   // write to them waits on the short scoreboard), so short groups serialise issue behind the pipe
-                  uint64_t b = wd + (uint64_t)((uint32_t)(KT - 1) * blk16);
-                  uint32_t d = d_base, id = idesc1;
-                  const int n_chunks = jn + KT - 1;
+                  uint64_t b = wd + (uint64_t)b_first;
+                  uint32_t d = d_first, id = id_first;
+                  a += (uint64_t)a_first;
 #pragma unroll kOpsUnroll
-                  for (int c = 0; c < n_chunks; ++c) {
+                  for (int c = c_lo; c < c_hi; ++c) {
 #pragma unroll
                     for (int k = 0; k < KS; ++k) umma_bf16(d, a + 2 * k, b + 2 * k, id, 1u);
                     const bool up = c < KT - 1;               // ramp-up: the next chunk also feeds an older tap
@@ -835,6 +858,8 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
 
 static long long* g_conv_dbg = nullptr;
 static int g_conv_skip = 0;
+static int g_conv_seam = 1;
+extern "C" void lr_conv3d_set_seam(int on) { g_conv_seam = on; }
 extern "C" void lr_conv3d_set_debug_skip(int mask) { g_conv_skip = mask; }
 // diagnostics: device buffer of 148*8 int64 that the next conv launches fill with per-role wait cycles
 // [producer a_empty, producer w_empty, mma acc_empty, mma a_full, mma w_full, epilogue acc_full, -, mma total]
@@ -992,6 +1017,12 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
     LR_CHECK_ARG((KT < p.Jg ? KT : p.Jg) * Cout <= 256, "lr_conv3d_fwd: kt-stacked N exceeds 256");
     G = (J + p.Jg - 1) / p.Jg;
     p.n_issuers = G;
+    // shared chunk list: a stacked MMA spans min(KT, J) weight blocks
+    // (not for 32-byte rows: conv1's one-k-step MMAs are bound by shared-memory bandwidth, not by the pipe, and the
+    // unequal chunk shares made it 5 % slower — measured)
+    const bool seam_ok = G > 1 && (KT < J ? KT : J) * Cout <= 256;
+    p.seam = g_conv_seam && seam_ok && Cin >= 32;
+    if (getenv("LR_CONV_SEAM")) p.seam = atoi(getenv("LR_CONV_SEAM")) != 0 && seam_ok && (Cin >= 32 || atoi(getenv("LR_CONV_SEAM")) > 1);
   }
   p.n_sets = n_sets;
   p.n_ytiles = lr_div_up(H, p.R);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "lr_umma_pattern_bench": (ctypes.c_longlong, [_vp, _vp, _vp, _i, _i, _vp]),
     "lr_umma_issue_bench": (ctypes.c_longlong, [_i] * 8 + [_vp]),
     "lr_conv3d_set_debug_skip": (None, [_i]),
+    "lr_conv3d_set_seam": (None, [_i]),
     "lr_ctc_select_kernel": (None, [_i]),
     "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "lr_ctc_greedy_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

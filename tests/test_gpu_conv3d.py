@@ -112,10 +112,12 @@ def test_conv3d_relu_pool_epilogue(native_lib, cuda, J, swap):
     (32, 3, 64, (3, 3, 3), 12, 6, 8),              # conv3 dgrad
     (64, 1, 32, (3, 5, 5), 25, 12, 16),            # conv2 dgrad
 ])
-def test_conv3d_kt_stacking_agrees_at_scale(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp):
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_conv3d_kt_stacking_agrees_at_scale(native_lib, cuda, Cin, CG, Cout, K, H, W, Wp, deterministic):
     """Orientation 3 issues differently shaped MMAs onto overlapping accumulator columns; a mis-ordered or lost
     update would show up as a whole missing tap.  Compare with the one-MMA-per-tap orientation on a batch that
     keeps every SM busy for many work items (same operands, fp32 accumulation in a different order)."""
+    from lipreading_b200 import conv_frontend as CF
     from lipreading_b200.conv_frontend import conv3d_native, _plane_rows
     g = torch.Generator(device="cuda").manual_seed(99)
     B, T = 24, 75
@@ -127,13 +129,21 @@ def test_conv3d_kt_stacking_agrees_at_scale(native_lib, cuda, Cin, CG, Cout, K, 
     taps = K[0] * K[1] * K[2]
     wk = (torch.randn((Cout, CG, taps, Cin), generator=g, device=cuda) / (Cin * CG * taps) ** 0.5).to(BF)
     ys = []
-    for mode in (0, 3, 3):
-        y = torch.full((B, T, H, W, Cout), float("nan"), dtype=BF, device=cuda)
-        conv3d_native(vol, wk, None, y, None, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0), swap=mode)
-        ys.append(y.float())
-    torch.cuda.synchronize()
+    CF.DETERMINISTIC = deterministic
+    try:
+        for mode in (0, 3, 3):
+            y = torch.full((B, T, H, W, Cout), float("nan"), dtype=BF, device=cuda)
+            conv3d_native(vol, wk, None, y, None, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, 1, (T, H, W), (0, 0, 0), swap=mode)
+            ys.append(y.float())
+        torch.cuda.synchronize()
+    finally:
+        CF.DETERMINISTIC = False
     assert torch.isfinite(ys[1]).all()
-    assert torch.equal(ys[1], ys[2])                       # one issuing thread: run-to-run deterministic
+    if deterministic:
+        assert torch.equal(ys[1], ys[2])                   # every accumulator has one writer: run-to-run identical
+    else:
+        # shared chunk list: hand-over frames are summed in a timing-dependent order -> at most a bf16 rounding flip
+        assert float((ys[1] - ys[2]).abs().max() / ys[1].abs().max()) < 2 ** -7
     assert float((ys[0] - ys[1]).abs().max() / ys[0].abs().max()) < 2 ** -8
 
 
@@ -208,14 +218,16 @@ def test_fused_dgrad_unpool_equals_two_pass(native_lib, cuda, B, T):
     grads, vols = {}, {}
     for fused in (False, True):
         CF.FUSE_UNPOOL = fused
+        CF.DETERMINISTIC = True             # bit-for-bit comparison: single-writer accumulators
         try:
             front.zero_grad()
             (front(clip) * up).sum().backward()
             torch.cuda.synchronize()
         finally:
             CF.FUSE_UNPOOL = True
+            CF.DETERMINISTIC = False
         grads[fused] = {k: v.grad.clone() for k, v in front.named_parameters()}
-        vols[fused] = {k: v.clone() for k, v in CF.POOL.bufs.items() if k[0] in ("dy32", "dy64")}
+        vols[fused] = {k: v.clone() for k, v in CF.POOL.bufs.items() if k[0] in ("dy32", "dy64") and k[1][1] == B and k[1][2] == T + 2}
     assert len(vols[True]) == 2
     for k in vols[True]:
         assert torch.equal(vols[True][k], vols[False][k]), k[0]
