@@ -180,7 +180,7 @@ int lr_conv3d_fwd(const void* x, const void* w, const float* bias, void* y, uint
                   int o_x, int J, int swap, void* stream);
 /* dgrad of a conv layer fused with the backward of the ReLU + MaxPool(1,2,2) in front of it
  * (= lr_conv3d_fwd with epi_mode 1 followed by lr_unpool, in one pass): `dy`/`w` as for a dgrad call of
- * lr_conv3d_fwd (Cout = the layer's INPUT channels, 32/64/128); argmax (B,T,H,W,Cout) are the pooling
+ * lr_conv3d_fwd (Cout = the layer's INPUT channels, 32 or 64); argmax (B,T,H,W,Cout) are the pooling
  * layer's arg-max bytes; the un-pooled gradient is written into the interior (o_t,o_y,o_x) of the
  * zero-padded volume dy_below (B,oTp,oHp,oWp,Cout) — only the 2x2 windows of pooled pixels, the rest
  * must already be zero — and d_bias (Cout) f32 (or NULL) receives its per-channel sum.           */

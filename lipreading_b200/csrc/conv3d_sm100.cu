@@ -38,6 +38,7 @@ constexpr int kThreads = 32 * (1 + kMmaWarps + 4 * kEpiGroups);   // producer + 
 constexpr int kMaxChunks = 16;   // (J + KT - 1) * channel groups
 constexpr int kWStages = 4;
 constexpr int kMaxTaps = 80;
+constexpr int kUnpoolIters = 8; // epi_mode 2: (row, channel-group) items per epilogue thread = Cout/8 <= 8
 constexpr int kEpiIters = 4;    // pooled (row,x,channel-group) items per epilogue thread: <= 32*16/128
 
 struct ConvParams {
@@ -202,7 +203,10 @@ __device__ __forceinline__ void mma_tap(uint32_t d, uint64_t a, uint64_t w, uint
   for (int k = 1; k < KS; ++k) umma_bf16(d, ma + 2 * k, mb + 2 * k, idesc, 1u);
 }
 
-template <int KS, int MODE>
+// (13 warps: the sub-partition that hosts four of them has 16 K registers -> 128 per thread is the hardware cap)
+// UNPOOL: the fused un-pooling epilogue (epi_mode 2) is a compile-time variant so that its arg-max prefetch registers and
+// bias partial sums do not weigh on the pooling epilogue of the forward layers
+template <int KS, int MODE, bool UNPOOL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ ConvParams p) {
   constexpr bool SWAP = MODE == 1;
@@ -486,7 +490,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     int e_src[kEpiIters], e_out[kEpiIters], e_am[kEpiIters], e_py[kEpiIters], e_cg[kEpiIters];
     const int epi_n = ((p.R >> 1) * PW * cgroups + 127) / 128;
 #pragma unroll
-    for (int k = 0; k < kEpiIters; ++k) {
+    for (int k = 0; k < (UNPOOL ? 0 : kEpiIters); ++k) {
       const int idx = etid + 128 * k;
       const int cg = idx % cgroups, pp = idx / cgroups;
       const int px = pp % (PW > 0 ? PW : 1), py = pp / (PW > 0 ? PW : 1);
@@ -498,9 +502,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
     int ebuf = 0;
     int it = 0;
-    float bsum[8];            // epi_mode 2: this thread's 8 channels (its channel group is fixed: 128 % cgroups == 0)
+    float bsum[UNPOOL ? 8 : 1];            // epi_mode 2: this thread's 8 channels (its channel group is fixed: 128 % cgroups == 0)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+    for (int e = 0; e < (UNPOOL ? 8 : 1); ++e) bsum[e] = 0.f;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int b = item / (p.n_tgroups * p.n_ytiles);
       const int rem = item - b * (p.n_tgroups * p.n_ytiles);
@@ -533,6 +537,21 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       for (int j = eg; j < jn; j += p.epi_groups) {
         const int t = t0 + j;
         uint8_t* stg = stage + (size_t)((ebuf++) & (p.stage_bufs - 1)) * (128 * p.stage_pitch);
+        // epi_mode 2: the arg-max bytes of this thread's (up to kUnpoolIters) items are fetched before the TMEM drain
+        // and the staging barrier, so their global-load latency is off the critical path (0x04.. = nothing to route)
+        uint2 amv[UNPOOL ? kUnpoolIters : 1];
+        if (UNPOOL) {
+          const size_t am_base = (((size_t)b * p.T + t) * p.H + y0) * p.W;
+#pragma unroll
+          for (int k = 0; k < kUnpoolIters; ++k) {
+            const int idx = etid + 128 * k;
+            const int cg = idx & (cgroups - 1), r = idx >> p.cg_shift;
+            const int yl = r >> p.wp_shift, x = r & (p.Wp - 1);
+            const bool ok = k < cgroups && x < p.W && yl < rows_left;
+            amv[k] = ok ? __ldg(reinterpret_cast<const uint2*>(p.am_in + (am_base + (size_t)yl * p.W + x) * p.Cout + cg * 8))
+                        : make_uint2(0x04040404u, 0x04040404u);
+          }
+        }
         if (MODE == 2) {
           // kx-stacked accumulator: lane r holds P[r][kx][n] (partial sums of filter column kx evaluated at
           // window row r); out[r][n] = sum_kx P[r + kx][kx][n].  Rows r+kx of the same warp come by shuffle,
@@ -597,7 +616,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           for (int i = 0; i < 16; ++i) {
             const float2 bb = *reinterpret_cast<const float2*>(bias_s + cc + 2 * i);     // smem broadcast
             float f0 = __uint_as_float(v[2 * i]) + bb.x, f1 = __uint_as_float(v[2 * i + 1]) + bb.y;
-            if (p.epi_mode == 0) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            if (!UNPOOL && p.epi_mode == 0) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
             __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
             packed[i] = *reinterpret_cast<uint32_t*>(&h);
           }
@@ -608,7 +627,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         }
         named_bar_sync(bar_id, 128);
         const size_t ob = obase + (size_t)j * oframe;
-        if (p.epi_mode == 0) {
+        if (!UNPOOL && p.epi_mode == 0) {
           // MaxPool(1,2,2) over the staged tile; 8 channels (16 B) per thread-item; the (row, x, channel
           // group) decomposition of each item was hoisted out of the item loop (no divisions here)
           const size_t ab = (((size_t)b * p.T + t) * (p.H >> 1) + (y0 >> 1)) * PW;
@@ -644,17 +663,18 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               *reinterpret_cast<uint2*>(p.argmax + (ab + e_am[k]) * p.Cout + e_cg[k] * 8) =
                   *reinterpret_cast<const uint2*>(am);
           }
-        } else if (p.epi_mode == 2) {
+        } else if (UNPOOL) {
           // fused un-pooling (backward of ReLU + MaxPool(1,2,2)): the gradient of pooled pixel (y,x) goes to the
           // arg-max slot of its 2x2 window in the padded dY volume of the layer below, zeros to the other three
           // (slot 4 = ReLU-dead: all zeros); the conv bias gradient is the per-channel sum of what was routed
-          const size_t am_base = (((size_t)b * p.T + t) * p.H + y0) * p.W;
           const size_t oplane = ((size_t)b * p.oTp + (t + p.o_t)) * p.oHp;
-          for (int idx = etid; idx < 128 * cgroups; idx += 128) {
+#pragma unroll
+          for (int k = 0; k < kUnpoolIters; ++k) {
+            const int idx = etid + 128 * k;
             const int cg = idx & (cgroups - 1), r = idx >> p.cg_shift;
             const int yl = r >> p.wp_shift, x = r & (p.Wp - 1);
-            if (x >= p.W || yl >= rows_left) continue;
-            const uint2 a8 = *reinterpret_cast<const uint2*>(p.am_in + (am_base + (size_t)yl * p.W + x) * p.Cout + cg * 8);
+            if (k >= cgroups || x >= p.W || yl >= rows_left) continue;
+            const uint2 a8 = amv[k];
             const uint4 v8 = *reinterpret_cast<const uint4*>(stg + (size_t)r * p.stage_pitch + cg * 16);
             const uint32_t vw[4] = {v8.x, v8.y, v8.z, v8.w};
             const uint32_t aw[2] = {a8.x, a8.y};
@@ -692,7 +712,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       tc_fence_before();
       if (lane == 0) lr_mbar_arrive(&bars[BAR_ACC_EMPTY + set]);
     }
-    if (p.epi_mode == 2 && p.d_bias) {
+    if (UNPOOL && p.d_bias) {
       // lanes with the same (lane & (cgroups-1)) hold the same 8 channels: butterfly over the other lane bits
       for (int o = cgroups; o < 32; o <<= 1)
 #pragma unroll
@@ -943,8 +963,8 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
   LR_CHECK_ARG(Wp >= W + KW - 1 && Hp >= H + KH - 1, "lr_conv3d_fwd: padded extents smaller than H+KH-1 / W+KW-1");
   LR_CHECK_ARG(KT >= 1 && KH >= 1 && KW >= 1 && CG >= 1 && B > 0 && T > 0 && H > 0 && W > 0, "lr_conv3d_fwd: bad shape");
   LR_CHECK_ARG(epi_mode >= 0 && epi_mode <= 2, "lr_conv3d_fwd: bad epilogue mode");
-  LR_CHECK_ARG(epi_mode != 2 || (am_in && (Cout == 32 || Cout == 64 || Cout == 128) && swap != 1),
-               "lr_conv3d_dgrad_unpool: needs the arg-max bytes, Cout in {32,64,128}, positions on M");
+  LR_CHECK_ARG(epi_mode != 2 || (am_in && (Cout == 32 || Cout == 64) && swap != 1),
+               "lr_conv3d_dgrad_unpool: needs the arg-max bytes, Cout in {32,64}, positions on M");
   LR_CHECK_ARG(KT * KH * KW <= kMaxTaps, "lr_conv3d_fwd: more than %d taps", kMaxTaps);
   if (!lr_conv3d_supported()) { lr_set_error("lr_conv3d_fwd needs an sm_100 device"); return LR_EARCH; }
 
@@ -988,7 +1008,8 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
   // (bias/ReLU/pool of one 128 x Cout accumulator costs ~1.4 k cycles on one quartet, measured on conv1)
   {
     const long long mma_cycles = (long long)KT * KH * KW * (Cin / 16) * CG * (32 + Cout / 4) * 2 / (mode == 3 ? 3 : 2);
-    p.epi_groups = (mode == 0 || mode == 3) && mma_cycles < 2500 ? 2 : 1;
+    // (the un-pooling epilogue stores four rows per position and reads the arg-max map: ~2.5x the plain one)
+    p.epi_groups = (mode == 0 || mode == 3) && mma_cycles < (epi_mode == 2 ? 6000 : 2500) ? 2 : 1;
     if (getenv("LR_CONV_EPI_GROUPS")) { const int v = atoi(getenv("LR_CONV_EPI_GROUPS")); if (v == 1 || (v == 2 && mode != 1 && mode != 2)) p.epi_groups = v; }
   }
   int fixed = 2 * p.wtile_bytes + p.epi_groups * stage_bytes + 256;      // at least a 2-deep ring of single taps
@@ -1102,21 +1123,25 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
   }
 
   int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-#define LR_LAUNCH_CONV(KS, MD)                                                                              \
+#define LR_LAUNCH_CONV(KS, MD, UP)                                                                          \
   do {                                                                                                      \
-    LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel<KS, MD>,                                       \
+    LR_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tcgen05_kernel<KS, MD, UP>,                                   \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));      \
-    conv3d_tcgen05_kernel<KS, MD><<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);             \
+    conv3d_tcgen05_kernel<KS, MD, UP><<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_x, p);         \
   } while (0)
-#define LR_LAUNCH_CONV_KS(MD)                                                                               \
+#define LR_LAUNCH_CONV_KS(MD, UP)                                                                           \
   do {                                                                                                      \
-    if (ks == 1) LR_LAUNCH_CONV(1, MD); else if (ks == 2) LR_LAUNCH_CONV(2, MD); else LR_LAUNCH_CONV(4, MD); \
+    if (ks == 1) LR_LAUNCH_CONV(1, MD, UP); else if (ks == 2) LR_LAUNCH_CONV(2, MD, UP); else LR_LAUNCH_CONV(4, MD, UP); \
   } while (0)
   const int ks = Cin / 16;
-  if (mode == 1) LR_LAUNCH_CONV_KS(1);
-  else if (mode == 2) LR_LAUNCH_CONV_KS(2);
-  else if (mode == 3) LR_LAUNCH_CONV_KS(3);
-  else LR_LAUNCH_CONV_KS(0);
+  if (epi_mode == 2) {
+    if (mode == 2) LR_LAUNCH_CONV_KS(2, true);
+    else if (mode == 3) LR_LAUNCH_CONV_KS(3, true);
+    else LR_LAUNCH_CONV_KS(0, true);
+  } else if (mode == 1) LR_LAUNCH_CONV_KS(1, false);
+  else if (mode == 2) LR_LAUNCH_CONV_KS(2, false);
+  else if (mode == 3) LR_LAUNCH_CONV_KS(3, false);
+  else LR_LAUNCH_CONV_KS(0, false);
 #undef LR_LAUNCH_CONV_KS
 #undef LR_LAUNCH_CONV
   LR_CHECK_LAUNCH();
