@@ -50,8 +50,11 @@ uint64_t    lr_launch_count(void);
  * grad (B,T,C) f32 or NULL: d nll_b / d log_probs with torch's native-CTC convention
  *   exp(lp) - exp(log(alpha*beta summed per class) + nll - lp), zero for t >= input_len.     */
 size_t lr_ctc_workspace(int B, int T, int C, int Lmax);
-/* 0 (default): warp-per-clip kernel for large batches (>= 1024 clips) whose lattice fits shared
- * memory, else CTA-per-clip; 1: always CTA-per-clip; 2: warp-per-clip whenever it fits (test hooks). */
+/* 0 (default): warp-per-clip kernels for large batches (>= 1024 clips) whose lattice fits shared
+ * memory, else CTA-per-clip.  Among the warp kernels, labels of <= 31 symbols run the linear-space
+ * (per-frame rescaled) recursion first and the log-space kernel only on the clips that one flags
+ * (underflow / infeasible).  1: always CTA-per-clip; 2: log-space warp-per-clip whenever it fits;
+ * 3: warp-per-clip whenever it fits, linear-space first (2, 3: test hooks).                          */
 void lr_ctc_select_kernel(int force_block);
 int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lens,
                    const int32_t* target_lens, int B, int T, int C, int Lmax,

@@ -16,7 +16,8 @@
 // HBM traffic is exactly the algorithmic 2*T*C*4 bytes per clip (39 000 B at T=75,C=65).
 #include "common.cuh"
 
-int lr_ctc_force_block_kernel = 0;   // 0 auto (by batch size), 1 always CTA-per-clip, 2 always warp-per-clip
+int lr_ctc_force_block_kernel = 0;   // 0 auto (by batch size), 1 always CTA-per-clip, 2 always log-space warp-per-clip,
+                                     // 3 always warp-per-clip with the linear-space kernel first (labels <= 31 symbols)
 
 namespace {
 
@@ -284,10 +285,12 @@ template <int P, bool FAST, int GA>
 __global__ void __launch_bounds__(32)
 ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
                 const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens, int B, int T, int C,
-                int Lmax, float* __restrict__ nll_out, float* __restrict__ grad, float* __restrict__ alpha_ws) {
+                int Lmax, float* __restrict__ nll_out, float* __restrict__ grad, float* __restrict__ alpha_ws,
+                const int32_t* __restrict__ redo) {
   constexpr int K = 2 * P, SP = 32 * K;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x, lane = threadIdx.x;
+  if (redo && !redo[b]) return;          // second pass behind the linear-space kernel: only the clips it gave up on
   const int Cpad = (C + 31) / 32 * 32;
   constexpr int RING = 8;                                            // log-prob rows in flight (cp.async)
   float* alpha = GA ? alpha_ws + (size_t)b * T * SP : reinterpret_cast<float*>(smem_raw);   // [T][SP]
@@ -490,6 +493,245 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Linear-space CTC for labels of up to 31 symbols and up to 96 classes (one warp per clip, one (blank, label) state
+// pair per lane).  ncu on the log-space warp kernel (profiles/r1_ncu_ctc_*.csv): 34 k warp instructions per clip at
+// 75 % issue utilisation, half of them address arithmetic, predicates and branches around the shared-memory row ring —
+// the kernel is instruction-bound, not latency- or HBM-bound.  This kernel is written for instruction count:
+//   * probabilities instead of log-probabilities, with Rabiner-style rescaling (Graves' original CTC formulation):
+//       alpha^_t = (M alpha^_{t-1}) . p_t . k_t        -log p(l|x) = -(log rho - sum_t log k_t)
+//       beta~_t  =  M' beta^_{t+1} ,  beta^_t = beta~_t . p_t . k_t   (the SAME k_t: then
+//       sum_s alpha^_t(s) beta~_t(s) = rho = alpha^_T(S-1) + alpha^_T(S-2) for every t)
+//       grad[t,c] = p_t(c) - sum_{s: l'_s = c} alpha^_t(s) beta~_t(s) / rho
+//     (torch's native-CTC gradient exp(lp) - exp(logsum(alpha+beta) + nll - lp): the division by p_t(c) cancels
+//     against the emission factor of beta, so no exp/log touches a lattice cell);
+//   * k_t = 1 on odd frames and 1 / (lattice mass two frames earlier) on even ones: any positive factor keeps the
+//     recursion exact as long as it is recorded, and the warp reduction behind it has two frames of slack instead
+//     of sitting on the frame-to-frame dependency chain; sum_t log k_t is accumulated exactly (exponent + mantissa);
+//   * a frame's C log-probs live in registers of the lanes that load them (class c in lane c % 32): one coalesced
+//     128-byte load per 32 classes, prefetched four frames ahead, exponentiated once; the blank / label emissions
+//     reach their states by shuffle, the gradient row is formed where the probabilities already are — no
+//     shared-memory row ring, no cp.async bookkeeping;
+//   * frames are walked in unrolled groups of four so all of that indexing is static.
+// A clip whose scale factors leave the fp32 range (infeasible labels, emission probabilities below e^-80, ...) is
+// flagged in `redo` and recomputed by the log-space kernel in a second launch.
+constexpr int kLinWarps = 2;      // clips per block: 64 resident warps per SM (a one-warp block caps at 32)
+
+template <int CI>                 // 32-class slabs per frame: C <= 32 * CI
+__global__ void __launch_bounds__(32 * kLinWarps)
+ctc_linear_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
+                       const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens, int B, int T, int C,
+                       int Lmax, float* __restrict__ nll_out, float* __restrict__ grad,
+                       float2* __restrict__ alpha_ws, int32_t* __restrict__ redo) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kLinWarps + wib;
+  if (b >= B) return;                                                // (no block-wide barriers below)
+  const int n_kf = (T + 1) / 2 + 1;
+  const size_t per_clip = ((size_t)(CI * 32 + 1 + 33 + n_kf) * sizeof(float) + 15) / 16 * 16;
+  float* occ = reinterpret_cast<float*>(smem_raw + (size_t)wib * per_clip);    // [CI*32] class occupancies + 1 dump slot
+  float* erow = occ + CI * 32 + 1;                                   // [32] label occupancies of a frame + 1 zero slot
+  float* kfac = erow + 33;                                           // [n_kf] scale factor of even frame 2i
+  float2* alpha = alpha_ws + (size_t)b * T * 32;
+
+  int Tb = in_lens[b];
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  int L = tgt_lens[b];
+  L = L < 0 ? 0 : (L > Lmax ? Lmax : L);
+  const float* lp_g = lp_all + (size_t)b * T * C;
+  const int32_t* tgt = targets + (size_t)b * Lmax;
+  float* g_b = grad + (size_t)b * T * C;
+  if (Tb == 0 || L > 31) {                                           // (L > 31 cannot happen: the host checks Lmax)
+    if (lane == 0) redo[b] = 1;
+    return;
+  }
+  const int j = lane;
+  const bool has_lab = j < L, has_blank = j <= L;
+  const int my = has_lab ? tgt[j] : 0;
+  const int up = __shfl_up_sync(0xffffffffu, my, 1), dn = __shfl_down_sync(0xffffffffu, my, 1);
+  const bool lab_ok = has_lab && my > 0 && my < C;                   // (an out-of-range class can never be emitted)
+  const int lab = lab_ok ? my : 0;
+  const float hl = lab_ok ? 1.f : 0.f, hb = has_blank ? 1.f : 0.f;
+  const float skipa = (has_lab && j >= 1 && my != up) ? 1.f : 0.f;   // alpha: s-2 -> s
+  const float skipb = (has_lab && j + 1 < L && dn != my) ? 1.f : 0.f;   // beta:  s+2 -> s
+  const int src_lane = lab & 31, src_slab = lab >> 5;
+  // occurrences of this lane's class further down the label: first two links in registers (slot 32 of erow is a
+  // constant zero), longer chains (a class four or more times in one label) walk the list
+  const unsigned same = __match_any_sync(0xffffffffu, has_lab ? my : -1 - lane);
+  const unsigned later = same & ~((2u << lane) - 1u);               // lanes > this one with the same class
+  const bool is_head = lab_ok && (same & ((1u << lane) - 1u)) == 0;
+  const int n1 = later ? __ffs(later) - 1 : 32;
+  const unsigned later2 = later & (later - 1);
+  const int n2 = later2 ? __ffs(later2) - 1 : 32;
+  const unsigned later3 = later2 & (later2 - 1);
+  const bool deep = __any_sync(0xffffffffu, is_head && later3 != 0);
+  const int occ_dst = is_head ? lab : CI * 32;                       // non-heads write the dump slot
+  for (int c = lane; c < CI * 32 + 1; c += 32) occ[c] = 0.f;
+  erow[lane] = 0.f;
+  if (lane == 0) erow[32] = 0.f;
+  __syncwarp();
+
+  // this lane's classes: lane + 32k; beyond C they read as log 0
+  const float* lp_lane = lp_g + lane;
+  bool cok[CI];
+#pragma unroll
+  for (int k = 0; k < CI; ++k) cok[k] = lane + 32 * k < C;
+  auto load_row = [&](float (&v)[CI], int t) {
+#pragma unroll
+    for (int k = 0; k < CI; ++k) v[k] = (cok[k] && t >= 0 && t < Tb) ? __ldg(lp_lane + (size_t)t * C + 32 * k) : LR_NEG_INF;
+  };
+  auto emissions = [&](const float (&pr)[CI], float& pb, float& pl) {
+    pb = __shfl_sync(0xffffffffu, pr[0], 0);
+    float x = __shfl_sync(0xffffffffu, pr[0], src_lane);
+#pragma unroll
+    for (int k = 1; k < CI; ++k) {
+      const float y = __shfl_sync(0xffffffffu, pr[k], src_lane);
+      x = src_slab == k ? y : x;
+    }
+    pl = x * hl;
+    pb *= hb;
+  };
+
+  // ---- alpha sweep ---------------------------------------------------------------------------------
+  float ab = lane == 0 ? 1.f : 0.f, al = 0.f;                        // "alpha_-1": makes frame 0 the generic step
+  float kmant = 1.f;          // product of the mantissas of the applied factors since the last flush (each in [0.5, 1))
+  int kexpo = 0;              // sum of their binary exponents
+  float klog = 0.f;           // log of the flushed mantissa products
+  float m_pending = 1.f, k_pending = 1.f;   // lattice mass at the last even frame and its reciprocal
+  bool bad = false;
+  float cur[4][CI], nxtv[4][CI];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) load_row(cur[u], u);
+  for (int t0 = 0; t0 < Tb; t0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_row(nxtv[u], t0 + 4 + u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      if (t < Tb) {                                                  // warp-uniform
+        float pr[CI], pb, pl;
+#pragma unroll
+        for (int k = 0; k < CI; ++k) pr[k] = __expf(cur[u][k]);
+        emissions(pr, pb, pl);
+        float prev = __shfl_up_sync(0xffffffffu, al, 1);
+        prev = lane == 0 ? 0.f : prev;
+        float nb = (ab + prev) * pb;
+        float nl = fmaf(prev, skipa, al + ab) * pl;
+        if (!(u & 1)) {                                              // even frame: rescale (k = 1 at frame 0)
+          bad = bad || !(m_pending >= 1e-24f) || !(m_pending < 1e30f);
+          const float kf = k_pending;
+          nb *= kf;
+          nl *= kf;
+          if (lane == 0) kfac[t >> 1] = kf;
+          const uint32_t kb = __float_as_uint(kf);
+          kexpo += (int)((kb >> 23) & 0xffu) - 126;
+          kmant *= __uint_as_float((kb & 0x007fffffu) | 0x3f000000u);
+          if ((t & 63) == 62) { klog += logf(kmant); kmant = 1.f; }  // 32 mantissas >= 2^-32: no underflow
+          m_pending = lr_warp_sum(nb + nl);                          // consumed two frames on
+          k_pending = __fdividef(1.f, m_pending);
+        }
+        ab = nb;
+        al = nl;
+        alpha[(size_t)t * 32 + lane] = make_float2(ab, al);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < CI; ++k) cur[u][k] = nxtv[u][k];
+  }
+  const float l1 = __shfl_sync(0xffffffffu, ab, L);
+  const float l2 = L > 0 ? __shfl_sync(0xffffffffu, al, L - 1) : 0.f;
+  const float rho = l1 + l2;
+  bad = bad || !(rho >= 1e-30f) || !(rho < 1e30f);
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) redo[b] = 1;
+    return;
+  }
+  // log p(l|x) = log rho - sum_t log k_t
+  const float nll = (klog + logf(kmant) + (float)kexpo * 0.6931471805599453f) - logf(rho);
+  const float rinv = 1.f / rho;
+  for (int t = T - 1; t >= Tb; --t)
+    for (int c = lane; c < C; c += 32) g_b[(size_t)t * C + c] = 0.f;
+  // ---- beta sweep fused with the gradient rows -------------------------------------------------------
+  __syncwarp();
+  float bb = lane == L ? 1.f : 0.f, bl = 0.f;                         // "beta_T": makes frame Tb-1 the generic step
+  float2 acur[4], anxt[4];
+  const int t_top = (Tb - 1) & ~3;
+  auto load_alpha = [&](float2& a, int t) {
+    a = (t >= 0 && t < Tb) ? alpha[(size_t)t * 32 + lane] : make_float2(0.f, 0.f);
+  };
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { load_row(cur[u], t_top + u); load_alpha(acur[u], t_top + u); }
+  float chk = 0.f;
+  for (int t0 = t_top; t0 >= 0; t0 -= 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { load_row(nxtv[u], t0 - 4 + u); load_alpha(anxt[u], t0 - 4 + u); }
+#pragma unroll
+    for (int u = 3; u >= 0; --u) {
+      const int t = t0 + u;
+      if (t < Tb) {                                                  // warp-uniform
+        float pr[CI], pb, pl;
+#pragma unroll
+        for (int k = 0; k < CI; ++k) pr[k] = __expf(cur[u][k]);
+        emissions(pr, pb, pl);
+        const float rb = __shfl_down_sync(0xffffffffu, bb, 1), rl = __shfl_down_sync(0xffffffffu, bl, 1);
+        // (lane 31 has no label state when L <= 31, so its wrapped-around neighbours are never used)
+        const float tl = hl * (fmaf(rl, skipb, bl + rb));
+        const float tb = hb * (bb + bl);
+        const float eb = acur[u].x * tb, el = acur[u].y * tl;
+        erow[lane] = el;
+        const float zb = lr_warp_sum(eb);
+        __syncwarp();
+        float acc = el + erow[n1] + erow[n2];
+        if (deep) {                                                  // warp-uniform, rare
+          if (is_head) {
+            unsigned rest = later3;
+            while (rest) { acc += erow[__ffs(rest) - 1]; rest &= rest - 1; }
+          }
+        }
+        occ[occ_dst] = acc;
+        if (lane == 0) occ[0] = zb;
+        __syncwarp();
+        float* g_row = g_b + (size_t)t * C + lane;
+#pragma unroll
+        for (int k = 0; k < CI; ++k)
+          if (cok[k]) g_row[32 * k] = fmaf(-occ[lane + 32 * k], rinv, pr[k]);
+        bb = tb * pb;
+        bl = tl * pl;
+        if (!(u & 1)) {
+          const float kf = kfac[t >> 1];
+          bb *= kf;
+          bl *= kf;
+        }
+        chk = fmaxf(chk, bb + bl);                                   // (NaN-propagating check below)
+        __syncwarp();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acur[u] = anxt[u];
+#pragma unroll
+      for (int k = 0; k < CI; ++k) cur[u][k] = nxtv[u][k];
+    }
+  }
+  // a factor that overflowed poisons bb/bl (inf or NaN) from that frame on: look at the last frame's values
+  const float fin = bb + bl;
+  if (__any_sync(0xffffffffu, !(fin < 1e30f) || !(chk < 1e30f))) {
+    if (lane == 0) redo[b] = 1;
+    return;
+  }
+  if (lane == 0) { nll_out[b] = nll; redo[b] = 0; }
+}
+
+size_t linear_kernel_smem(int T, int C) {
+  const int CI = (C + 31) / 32;
+  const int n_kf = (T + 1) / 2 + 1;
+  const size_t per_clip = ((size_t)(CI * 32 + 1 + 33 + n_kf) * sizeof(float) + 15) / 16 * 16;
+  return per_clip * kLinWarps;
+}
+
 size_t warp_kernel_smem(int T, int C, int P, int global_alpha = 0) {
   const int Cpad = (C + 31) / 32 * 32;
   return ((global_alpha ? 0 : (size_t)T * 64 * P) + 9 * Cpad + 32 * P) * sizeof(float) + (size_t)2 * 32 * P * sizeof(int);
@@ -501,8 +743,11 @@ int warp_kernel_pairs(int Lmax) {
 }
 bool warp_kernel_chosen(int B, int T, int C, int Lmax) {
   const int P = warp_kernel_pairs(Lmax);
+  // the linear-space kernel (labels <= 31 symbols, <= 96 classes) beats the CTA-per-clip kernel from a few dozen clips
+  // on (50 vs 74 us at B = 256, measured); the log-space warp kernel only pays off once the SMs are full
+  const bool linear = P == 1 && Lmax <= 31 && C <= 96 && lr_ctc_force_block_kernel != 2;
   return P && warp_kernel_smem(T, C, P) <= 100 * 1024 && lr_ctc_force_block_kernel != 1 &&
-         (B >= 1024 || lr_ctc_force_block_kernel == 2);
+         (B >= 1024 || (linear && B >= 64) || lr_ctc_force_block_kernel >= 2);
 }
 
 // Greedy CTC decode (semantics of the reference's GreedyDecoder,
@@ -569,7 +814,7 @@ extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
   if (B <= 0 || T <= 0 || C <= 0 || Lmax < 0) return 0;
   if (Lmax == 0) Lmax = 1;
   if (warp_kernel_chosen(B, T, C, Lmax))               // alpha lattice of the warp-per-clip kernel: [B][T][64*P] f32
-    return (size_t)B * T * 64 * warp_kernel_pairs(Lmax) * sizeof(float);
+    return (size_t)B * T * 64 * warp_kernel_pairs(Lmax) * sizeof(float) + (size_t)B * sizeof(int32_t);   // + redo flags
   CtcPlan p = make_plan(T, C, Lmax);
   if (p.lat_in_smem) return 16;
   return (size_t)B * 2 * T * p.Smax * sizeof(float);
@@ -595,12 +840,25 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
     const size_t sm = warp_kernel_smem(T, C, P, ga);
     float* aw = reinterpret_cast<float*>(workspace);
     cudaStream_t st = lr_stream(stream);
+    const int32_t* redo_ptr = nullptr;
+    // labels of <= 31 symbols: the linear-space kernel first, then the log-space one on the clips it flagged
+    if (P == 1 && Lmax <= 31 && C <= 96 && ga && grad && lr_ctc_force_block_kernel != 2 && ws_bytes >= ws_need + (size_t)B * sizeof(int32_t)) {
+      int32_t* redo = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + ws_need);
+      const dim3 lgrid(lr_div_up(B, kLinWarps));
+      const size_t lsm = linear_kernel_smem(T, C);
+      float2* a2 = reinterpret_cast<float2*>(aw);
+      if (C <= 32) ctc_linear_warp_kernel<1><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad, a2, redo);
+      else if (C <= 64) ctc_linear_warp_kernel<2><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad, a2, redo);
+      else ctc_linear_warp_kernel<3><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad, a2, redo);
+      LR_CHECK_LAUNCH();
+      redo_ptr = redo;
+    }
 #define LR_LAUNCH_WARP2(PP, FF, GG)                                                                            \
   do {                                                                                                         \
     LR_CHECK_CUDA(cudaFuncSetAttribute(ctc_warp_kernel<PP, FF, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        (int)sm));                                                              \
     ctc_warp_kernel<PP, FF, GG><<<B, 32, sm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, \
-                                                   nll, grad, aw);                                             \
+                                                   nll, grad, aw, redo_ptr);                                   \
   } while (0)
 #define LR_LAUNCH_WARP(PP)                                                                                     \
   do {                                                                                                         \

@@ -27,7 +27,8 @@ def test_header_symbols_exported_and_bound(native_lib):
 
 
 def test_workspace_queries_need_no_gpu(native_lib):
-    assert native_lib.lr_ctc_workspace(256, 75, 65, 30) == 16            # lattices fit shared memory
+    assert native_lib.lr_ctc_workspace(32, 75, 65, 30) == 16             # CTA-per-clip: lattices fit shared memory
+    assert native_lib.lr_ctc_workspace(256, 75, 65, 30) == 256 * 75 * 64 * 4 + 256 * 4   # warp kernels: alpha + redo flags
     assert native_lib.lr_ctc_workspace(4, 400, 65, 256) == 4 * 2 * 400 * 513 * 4
     assert native_lib.lr_rnn_workspace(1, 256, 75, 256, 2) == 3 * 2 * 256 * 256 * 4
     assert [native_lib.lr_rnn_saved_per_unit(m) for m in (0, 1, 2)] == [0, 4, 5]

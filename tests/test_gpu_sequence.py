@@ -29,10 +29,11 @@ def _relerr(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.fixture(params=["warp_per_clip", "cta_per_clip"])
+@pytest.fixture(params=["warp_per_clip", "cta_per_clip", "linear_warp"])
 def ctc_kernel(request, native_lib):
-    """Both CTC kernels: warp-per-clip (default when the lattice fits) and CTA-per-clip (any size)."""
-    native_lib.lr_ctc_select_kernel(1 if request.param == "cta_per_clip" else 2)
+    """All CTC kernels: log-space warp-per-clip, CTA-per-clip (any size), and the linear-space warp kernel (labels of
+    <= 31 symbols; longer labels and flagged clips fall through to the log-space warp kernel)."""
+    native_lib.lr_ctc_select_kernel({"cta_per_clip": 1, "warp_per_clip": 2, "linear_warp": 3}[request.param])
     yield request.param
     native_lib.lr_ctc_select_kernel(0)
 
