@@ -452,7 +452,7 @@ def main():
     # DRAM traffic of the largest launch (conv2.fwd) from the committed `ncu --set full` capture
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_step_b256_v3.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_step_b256_v4.json")) as fh:
             cap = json.load(fh)["conv2.fwd"]
         if args.batch == 256:
             traffic = (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6
@@ -461,7 +461,7 @@ def main():
     roofline = {"kernel": "conv3d_tcgen05_kernel (5 launches/step: conv1-3 fwd, conv3/conv2 dgrad)",
                 "bound": "tensor", "achieved": tot_f / tot_s / 1e12 if tot_s else None, "peak": peak,
                 "unit": "TFLOP/s", "frac": (tot_f / tot_s / 1e12 / peak) if tot_s else None, "traffic": traffic,
-                "traffic_source": "dram bytes read+written by the conv2.fwd launch, profiles/r1_ncu_full_step_b256_v3.json",
+                "traffic_source": "dram bytes read+written by the conv2.fwd launch, profiles/r1_ncu_full_step_b256_v4.json",
                 "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "share_of_step": tot_s / (ms * 1e-3),
                 "per_launch": {k: {"ms": v[0] / v[2] * 1e3, "tflops": v[1] / v[0] / 1e12} for k, v in per.items()}}
