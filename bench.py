@@ -232,7 +232,7 @@ def kernel_rooflines(dev, pk, char2idx):
     il = torch.full((B,), T, dtype=torch.int32, device=dev)
     tl = torch.randint(10, 31, (B,), generator=g).to(dev).int()
     s = time_cuda(lambda: LF.ctc_nll(lp, tg, il, tl), flush=flush)
-    out.append({"kernel": "ctc_alpha_beta_grad", "bound": "hbm", "unit": "GB/s", "achieved": B * 2 * T * C * 4 / s / 1e9,
+    out.append({"kernel": "ctc fwd+grad (linear-space warp kernel)", "bound": "hbm", "unit": "GB/s", "achieved": B * 2 * T * C * 4 / s / 1e9,
                 "frac": B * 2 * T * C * 4 / s / hbm, "shape": "B=4096,T=75,C=65,L<=30", "ms": s * 1e3})
     # proj + masked log-softmax fwd: reads M*K*4, writes M*C*4
     M, K = 256 * 75, 512
