@@ -80,6 +80,10 @@ int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, const float
 int lr_proj_logsoftmax_bwd(const float* grad_lp, const float* log_probs, const float* hidden,
                            const float* weight, float* d_logits, float* d_hidden,
                            float* d_weight, float* d_bias, int M, int K, int C, void* stream);
+/* Forward kernel choice: 0 (default) = fp32 SIMT kernel; 1 = 3xTF32 tensor-core kernel (mma.sync, W resident in
+ * shared memory) whenever C <= 68, K % 16 == 0 and K <= 688 — 1.2x faster, 3e-5 instead of 1e-5 from the exact
+ * logits (legacy TF32 mma.sync on sm_100: slow, and its accumulator adds do not round to nearest).               */
+void lr_proj_select_kernel(int use_tc);
 
 /* -------- a12/a13: (bi)directional recurrent layer, packed-sequence semantics ------------ */
 /* replaces: src/models/lipreader/better_model.py:64-89 (sort -> pack -> nn.{LSTM,GRU,RNN} ->

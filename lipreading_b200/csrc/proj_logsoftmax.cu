@@ -142,6 +142,145 @@ proj_logsoftmax_fwd_kernel(const float* __restrict__ hidden, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor-core forward for K <= 688 (the whole weight matrix fits shared memory): 3xTF32 on mma.sync.m16n8k8.
+// Each fp32 operand x is split as hi = tf32(x)
+// and lo = x - hi (exact in fp32; both rounded to nearest TF32); D += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi drops only the lo.lo term (2^-22 relative
+// per product, the same order as fp32 rounding), so the 1e-4 parity bar on the log-probs holds where a single TF32
+// pass (2^-11) would not.  One CTA per SM keeps W (C x K fp32, rows padded to dodge bank conflicts) resident; each
+// of its 16 warps takes 16-row tiles.  The k index inside a 16-wide chunk is permuted so that a thread's A and B
+// fragments of two consecutive k8 steps are ONE float4 each (A: straight from HBM, 64 contiguous bytes per row and
+// quarter-warp; B: one LDS.128 per 8 classes), prefetched four chunks ahead in registers.  Bias + log-mask +
+// log-softmax happen on the accumulator fragments (a row lives in the 4 lanes of a quad).
+// Measured (M = 19200, K = 512): 76 us against the SIMT kernel's 93 us, and 3.3e-5 from the float64 logits against
+// 1e-5: the legacy TF32 mma.sync path of sm_100 is barely faster than FFMA (3 x 1.28 GFLOP in 76 us = 50 TFLOP/s) and
+// its accumulator adds do not round to nearest, so the error grows with the 192 chained MMAs per output.  Kept as an
+// opt-in (lr_proj_select_kernel(1)) and as the measurement behind "the tcgen05 kind::tf32 route is the one to build";
+// the default forward stays the fp32 SIMT kernel.
+constexpr int kTcWarps = 16;
+constexpr int kTcNT = 9;                         // 8-class tiles: C <= 72
+constexpr int kTcPF = 4;                         // chunks of 16 k prefetched per warp
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (round-to-nearest on both parts: truncating instead biases every product the same way and the bias adds up
+// linearly over K — 3.5e-5 on the logits at K = 512, measured)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__global__ void __launch_bounds__(32 * kTcWarps, 1)
+proj_logsoftmax_fwd_tc_kernel(const float* __restrict__ hidden, const float* __restrict__ weight,
+                              const float* __restrict__ bias, const float* __restrict__ log_mask,
+                              float* __restrict__ out, int M, int K, int C) {
+  extern __shared__ __align__(16) float psm[];
+  const int pitch = K + 16;                      // floats per W row: rows 64 B apart modulo 128 B -> conflict-free LDS.128
+  float* Ws = psm;                               // [8 * kTcNT][pitch], rows >= C are zero
+  float* bm = psm + 8 * kTcNT * pitch;           // [8 * kTcNT] bias + log-mask (-inf beyond C)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 8 * kTcNT * (K / 4); i += blockDim.x) {
+    const int r = i / (K / 4), q = i - r * (K / 4);
+    const float4 v = r < C ? *reinterpret_cast<const float4*>(weight + (size_t)r * K + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Ws + (size_t)r * pitch + q * 4) = v;
+  }
+  for (int i = tid; i < 8 * kTcNT; i += blockDim.x) bm[i] = i < C ? bias[i] + log_mask[i] : LR_NEG_INF;
+  __syncthreads();
+
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = (M + 15) / 16, n_chunks = K / 16;
+  constexpr int c_begin = 0;
+  for (int tile = blockIdx.x * kTcWarps + warp; tile < n_tiles; tile += gridDim.x * kTcWarps) {
+    const int m0 = tile * 16;
+    const int r0 = min(m0 + g, M - 1), r1 = min(m0 + g + 8, M - 1);
+    const float* a0p = hidden + (size_t)r0 * K + 4 * t;
+    const float* a1p = hidden + (size_t)r1 * K + 4 * t;
+    float acc[kTcNT][4];
+#pragma unroll
+    for (int j = 0; j < kTcNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    float4 pa0[kTcPF], pa1[kTcPF];
+#pragma unroll
+    for (int s = 0; s < kTcPF; ++s) {
+      const int cix = min(c_begin + s, n_chunks - 1);
+      pa0[s] = __ldg(reinterpret_cast<const float4*>(a0p + cix * 16));
+      pa1[s] = __ldg(reinterpret_cast<const float4*>(a1p + cix * 16));
+    }
+    const float* wrow = Ws + (size_t)g * pitch + 4 * t;
+    for (int c0 = c_begin; c0 < n_chunks; c0 += kTcPF) {
+#pragma unroll
+      for (int s = 0; s < kTcPF; ++s) {
+        const int c = c0 + s;
+        if (c < n_chunks) {                                  // warp-uniform
+          const float4 x0 = pa0[s], x1 = pa1[s];
+          const int nx = min(c + kTcPF, n_chunks - 1);
+          pa0[s] = __ldg(reinterpret_cast<const float4*>(a0p + nx * 16));
+          pa1[s] = __ldg(reinterpret_cast<const float4*>(a1p + nx * 16));
+          // A fragments of the two k8 steps: (row g | g+8) x (physical k 4t, 4t+1 | 4t+2, 4t+3)
+          uint32_t ah[2][4], al[2][4];
+          split_tf32(x0.x, ah[0][0], al[0][0]); split_tf32(x1.x, ah[0][1], al[0][1]);
+          split_tf32(x0.y, ah[0][2], al[0][2]); split_tf32(x1.y, ah[0][3], al[0][3]);
+          split_tf32(x0.z, ah[1][0], al[1][0]); split_tf32(x1.z, ah[1][1], al[1][1]);
+          split_tf32(x0.w, ah[1][2], al[1][2]); split_tf32(x1.w, ah[1][3], al[1][3]);
+          const float* wc = wrow + c * 16;
+#pragma unroll
+          for (int j = 0; j < kTcNT; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(wc + (size_t)(8 * j) * pitch);
+            uint32_t bh[4], bl[4];
+            split_tf32(w.x, bh[0], bl[0]); split_tf32(w.y, bh[1], bl[1]);
+            split_tf32(w.z, bh[2], bl[2]); split_tf32(w.w, bh[3], bl[3]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              mma_tf32(acc[j], al[h][0], al[h][1], al[h][2], al[h][3], bh[2 * h], bh[2 * h + 1]);
+              mma_tf32(acc[j], ah[h][0], ah[h][1], ah[h][2], ah[h][3], bl[2 * h], bl[2 * h + 1]);
+              mma_tf32(acc[j], ah[h][0], ah[h][1], ah[h][2], ah[h][3], bh[2 * h], bh[2 * h + 1]);
+            }
+          }
+        }
+      }
+    }
+    // epilogue: element (j, i): row = g + 8*(i>>1), class = 8j + 2t + (i&1)
+    float mx0 = LR_NEG_INF, mx1 = LR_NEG_INF;
+#pragma unroll
+    for (int j = 0; j < kTcNT; ++j) {
+      const float2 b2 = *reinterpret_cast<const float2*>(bm + 8 * j + 2 * t);
+      acc[j][0] += b2.x; acc[j][1] += b2.y; acc[j][2] += b2.x; acc[j][3] += b2.y;
+      mx0 = fmaxf(mx0, fmaxf(acc[j][0], acc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(acc[j][2], acc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTcNT; ++j) {
+      s0 += expf(acc[j][0] - mx0) + expf(acc[j][1] - mx0);
+      s1 += expf(acc[j][2] - mx1) + expf(acc[j][3] - mx1);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float lse0 = mx0 + logf(s0), lse1 = mx1 + logf(s1);
+    const int row0 = m0 + g, row1 = m0 + g + 8;
+#pragma unroll
+    for (int j = 0; j < kTcNT; ++j) {
+      const int col = 8 * j + 2 * t;
+      if (row0 < M) {
+        if (col < C) out[(size_t)row0 * C + col] = acc[j][0] - lse0;
+        if (col + 1 < C) out[(size_t)row0 * C + col + 1] = acc[j][1] - lse0;
+      }
+      if (row1 < M) {
+        if (col < C) out[(size_t)row1 * C + col] = acc[j][2] - lse1;
+        if (col + 1 < C) out[(size_t)row1 * C + col + 1] = acc[j][3] - lse1;
+      }
+    }
+  }
+}
+
+int lr_proj_use_tc = 0;          // lr_proj_select_kernel: 1 = the 3xTF32 tensor-core forward where it applies (default: fp32 SIMT)
+
+// ---------------------------------------------------------------------------------------------
 // backward 1: d_logits = g - softmax * sum_c(g); d_bias partial sums (one warp per row)
 __global__ void __launch_bounds__(256)
 logsoftmax_bwd_kernel(const float* __restrict__ grad_lp, const float* __restrict__ log_probs,
@@ -258,6 +397,19 @@ extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, 
   LR_CHECK_ARG(hidden && weight && bias && log_mask && log_probs, "lr_proj_logsoftmax_fwd: null");
   LR_CHECK_ARG(M > 0 && K > 0 && C > 0 && C <= kMaxC, "lr_proj_logsoftmax_fwd: need 0<C<=%d (C=%d)",
                kMaxC, C);
+  {
+    const size_t tc_smem = ((size_t)8 * kTcNT * (K + 16) + 8 * kTcNT) * sizeof(float);
+    if (lr_proj_use_tc && C <= 8 * kTcNT && K % 16 == 0 && K >= 16 && tc_smem <= 200 * 1024) {
+      LR_CHECK_CUDA(cudaFuncSetAttribute(proj_logsoftmax_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)tc_smem));
+      int grid = lr_div_up(lr_div_up(M, 16), kTcWarps);
+      if (grid > kNumSMs) grid = kNumSMs;
+      proj_logsoftmax_fwd_tc_kernel<<<grid, 32 * kTcWarps, tc_smem, lr_stream(stream)>>>(hidden, weight, bias, log_mask,
+                                                                                        log_probs, M, K, C);
+      LR_CHECK_LAUNCH();
+      return LR_OK;
+    }
+  }
   const size_t smem = (size_t)kStages * (kBM + kMaxC) * kPitch * sizeof(float);
   LR_CHECK_CUDA(cudaFuncSetAttribute(proj_logsoftmax_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   proj_logsoftmax_fwd_kernel<<<lr_div_up(M, kBM), kThreads, smem, lr_stream(stream)>>>(
@@ -265,6 +417,8 @@ extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, 
   LR_CHECK_LAUNCH();
   return LR_OK;
 }
+
+extern "C" void lr_proj_select_kernel(int use_tc) { lr_proj_use_tc = use_tc; }
 
 extern "C" int lr_proj_logsoftmax_bwd(const float* grad_lp, const float* log_probs,
                                       const float* hidden, const float* weight, float* d_logits,

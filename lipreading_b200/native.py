@@ -41,6 +41,7 @@ SIGNATURES = {
     "lr_scale_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "lr_proj_logsoftmax_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lr_proj_logsoftmax_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lr_proj_select_kernel": (None, [_i]),
     "lr_rnn_saved_per_unit": (_i, [_i]),
     "lr_rnn_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "lr_rnn_fwd": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

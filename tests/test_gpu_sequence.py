@@ -86,9 +86,11 @@ def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda, ctc_kernel):
     assert torch.isfinite(lp.grad).all() and float(lp.grad[0].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("M,K", [(300, 512), (75, 256), (1000, 1400)])
-def test_proj_masked_log_softmax(native_lib, cuda, M, K):
+@pytest.mark.parametrize("tc", [0, 1])        # 0: fp32 SIMT forward (default), 1: 3xTF32 tensor-core forward where it applies
+@pytest.mark.parametrize("M,K", [(300, 512), (75, 256), (1000, 1400), (33, 64), (2500, 512)])
+def test_proj_masked_log_softmax(native_lib, cuda, M, K, tc):
     from lipreading_b200 import functional as LF
+    native_lib.lr_proj_select_kernel(tc)
     g = torch.Generator().manual_seed(7)
     c2i = O.build_char2idx()
     C = len(c2i) + 1
@@ -101,9 +103,17 @@ def test_proj_masked_log_softmax(native_lib, cuda, M, K):
     ref = O.masked_log_softmax(hr @ wr.t() + br, lm)
     (ref * up).sum().backward()
     hd, wd, bd = [t.to(cuda).requires_grad_(True) for t in (h, w, b)]
-    out = LF.proj_masked_log_softmax(hd, wd, bd, lm.to(cuda))
-    (out * up.to(cuda)).sum().backward()
+    try:
+        out = LF.proj_masked_log_softmax(hd, wd, bd, lm.to(cuda))
+        (out * up.to(cuda)).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        native_lib.lr_proj_select_kernel(0)
     assert float((out.cpu() - ref.detach()).abs().max()) < 1e-4
+    # against float64: fp32 SIMT ~1e-5; 3xTF32 ~3e-5 (tensor-core accumulator adds do not round to nearest; a single
+    # TF32 pass would be ~1e-3 here)
+    ref64 = O.masked_log_softmax(h.double() @ w.double().t() + b.double(), lm.double())
+    assert float((out.cpu().double() - ref64).abs().max()) < (6e-5 if tc else 2e-5)
     assert _relerr(hd.grad.cpu(), hr.grad) < 1e-4
     assert _relerr(wd.grad.cpu(), wr.grad) < 1e-4
     assert _relerr(bd.grad.cpu(), br.grad) < 1e-4
