@@ -190,7 +190,6 @@ def gemm_weight(w):
 def dgrad_weight(w, cg):
     """(Cout,Cin,KT,KH,KW) -> flipped/transposed (Cin, CG, taps, Cout/CG) for the dgrad pass."""
     co, ci = w.shape[0], w.shape[1]
-    wf = w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(ci, -1, co // cg, cg) if False else None
     taps = w.shape[2] * w.shape[3] * w.shape[4]
     wf = w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(ci, taps, co // cg, cg)
     return wf.permute(0, 2, 1, 3).contiguous()

@@ -15,6 +15,7 @@
 //
 // HBM traffic is exactly the algorithmic 2*T*C*4 bytes per clip (39 000 B at T=75,C=65).
 #include "common.cuh"
+#include <stdlib.h>
 
 int lr_ctc_force_block_kernel = 0;   // 0 auto (by batch size), 1 always CTA-per-clip, 2 always log-space warp-per-clip,
                                      // 3 always warp-per-clip with the linear-space kernel first (labels <= 31 symbols)
@@ -518,8 +519,8 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
 // flagged in `redo` and recomputed by the log-space kernel in a second launch.
 constexpr int kLinWarps = 2;      // clips per block: 64 resident warps per SM (a one-warp block caps at 32)
 
-template <int CI>                 // 32-class slabs per frame: C <= 32 * CI
-__global__ void __launch_bounds__(32 * kLinWarps)
+template <int CI, int MB>         // 32-class slabs per frame: C <= 32 * CI; MB = resident blocks per SM the registers allow
+__global__ void __launch_bounds__(32 * kLinWarps, MB)
 ctc_linear_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ targets,
                        const int32_t* __restrict__ in_lens, const int32_t* __restrict__ tgt_lens, int B, int T, int C,
                        int Lmax, float* __restrict__ nll_out, float* __restrict__ grad,
@@ -847,9 +848,19 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
       const dim3 lgrid(lr_div_up(B, kLinWarps));
       const size_t lsm = linear_kernel_smem(T, C);
       float2* a2 = reinterpret_cast<float2*>(aw);
-      if (C <= 32) ctc_linear_warp_kernel<1><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad, a2, redo);
-      else if (C <= 64) ctc_linear_warp_kernel<2><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad, a2, redo);
-      else ctc_linear_warp_kernel<3><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, C, Lmax, nll, grad, a2, redo);
+      static const int mb = getenv("LR_CTC_LIN_MB") ? atoi(getenv("LR_CTC_LIN_MB")) : 11;     // tuning hook
+#define LR_LAUNCH_LIN(CI_, MB_)                                                                                \
+  ctc_linear_warp_kernel<CI_, MB_><<<lgrid, 32 * kLinWarps, lsm, st>>>(log_probs, targets, input_lens, target_lens, B, T, \
+                                                                      C, Lmax, nll, grad, a2, redo)
+#define LR_LAUNCH_LIN_MB(CI_)                                                                                  \
+  do {                                                                                                         \
+    if (mb >= 16) LR_LAUNCH_LIN(CI_, 16); else if (mb >= 12) LR_LAUNCH_LIN(CI_, 12); else LR_LAUNCH_LIN(CI_, 11);   \
+  } while (0)
+      if (C <= 32) LR_LAUNCH_LIN_MB(1);
+      else if (C <= 64) LR_LAUNCH_LIN_MB(2);
+      else LR_LAUNCH_LIN_MB(3);
+#undef LR_LAUNCH_LIN_MB
+#undef LR_LAUNCH_LIN
       LR_CHECK_LAUNCH();
       redo_ptr = redo;
     }

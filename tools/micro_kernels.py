@@ -1,5 +1,5 @@
 """Launch each HBM-bound kernel of the path a few times at the bench shapes (for ncu captures on the GPU box):
-    ncu --set full --clock-control none --import-source on -k regex:"warp256|posmap|ctc|proj_logsoftmax_fwd" \
+    ncu --set full --clock-control none --import-source on -k regex:"warp256|posmap|ctc|proj_logsoftmax_fwd|mouth_crop" \
         -o gpurun_out/micro python tools/micro_kernels.py"""
 import os
 import sys
@@ -38,8 +38,10 @@ lp256 = lp[:256].detach().clone().requires_grad_(True)
 for _ in range(reps):
     LF.warp256(frames, crop)
     LF.posmap_gather(pos, crop, rp, kidx, fidx)
-    LF.ctc_nll(lp, tg, il, tl)                       # warp-per-clip kernel (B >= 1024)
-    LF.ctc_nll(lp256, tg[:256], il[:256], tl[:256])   # CTA-per-clip kernel
+    LF.ctc_nll(lp, tg, il, tl)                       # linear-space warp kernel (+ the log-space pass on flagged clips)
+    LF.ctc_nll(lp256, tg[:256], il[:256], tl[:256])   # the same at the training batch size
     LF.proj_masked_log_softmax(h, w, b, lm)
+    lmk = LF.posmap_gather(pos, crop, rp, kidx)
+    LF.mouth_crop(frames, lmk, rp)
 torch.cuda.synchronize()
 print("done")
