@@ -170,6 +170,10 @@ def load_dataset(pickle_dir, out_ext=".pkl"):
     return tuple(out)
 
 
+COPY_STREAMS = 1      # host->device copy streams of DevicePrefetcher (LR_H2D_STREAMS overrides).  Measured on the B200 box:
+                      # 1 -> 1.286 M frames/s end to end, 2 -> 1.285 M, 4 -> 1.108 M: the link (~19 GB/s), not the engine, limits
+
+
 class DevicePrefetcher:
     """Iterate a loader of HOST batches one step ahead: the (large) frames tensor of batch i+1 is
     copied host->device on a side stream while batch i computes.  Lengths and captions stay on the
@@ -180,14 +184,19 @@ class DevicePrefetcher:
     stream, for the event recorded when the consumer asked for the batch after the one that last
     used slot k (i.e. all work reading the slot has been enqueued)."""
 
-    def __init__(self, loader, device):
+    def __init__(self, loader, device, copy_streams=None):
         self.loader, self.device = loader, torch.device(device)
+        # the big tensor is split along the batch axis over this many copy streams: one cudaMemcpyAsync keeps a single
+        # copy engine busy, several in flight let the link's other engines work too
+        if copy_streams is None:
+            copy_streams = int(os.environ.get("LR_H2D_STREAMS", COPY_STREAMS))
+        self.copy_streams = max(1, int(copy_streams))
 
     def __len__(self):
         return len(self.loader)
 
     def __iter__(self):
-        side = torch.cuda.Stream(self.device)
+        sides = [torch.cuda.Stream(self.device) for _ in range(self.copy_streams)]
         slots = [None, None]            # device buffers
         released = [None, None]         # event: consumer is done enqueueing work on the slot
 
@@ -197,13 +206,23 @@ class DevicePrefetcher:
             if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
                 buf = torch.empty(src.shape, dtype=src.dtype, device=self.device)
                 slots[k] = buf
-            if released[k] is not None:
-                side.wait_event(released[k])
-            with torch.cuda.stream(side):
-                buf.copy_(src, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(side)
-            return buf, ev, batch[1:]
+            n = src.shape[0] if src.dim() > 0 else 1
+            parts = min(len(sides), max(1, n))
+            step = -(-n // parts)
+            evs = []
+            for p_i in range(parts):
+                lo, hi = p_i * step, min(n, (p_i + 1) * step)
+                if lo >= hi:
+                    break
+                side = sides[p_i]
+                if released[k] is not None:
+                    side.wait_event(released[k])
+                with torch.cuda.stream(side):
+                    (buf[lo:hi] if src.dim() > 0 else buf).copy_(src[lo:hi] if src.dim() > 0 else src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                evs.append(ev)
+            return buf, evs, batch[1:]
 
         it = iter(self.loader)
         try:
@@ -218,7 +237,8 @@ class DevicePrefetcher:
             except StopIteration:
                 nxt = None
             cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
+            for e in ev:
+                cur.wait_event(e)
             yield (frames,) + tuple(rest)
             # the consumer came back for the next batch: everything that reads `frames` is enqueued
             done = torch.cuda.Event()
