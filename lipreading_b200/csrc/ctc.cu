@@ -515,6 +515,8 @@ ctc_warp_kernel(const float* __restrict__ lp_all, const int32_t* __restrict__ ta
 //     reach their states by shuffle, the gradient row is formed where the probabilities already are — no
 //     shared-memory row ring, no cp.async bookkeeping;
 //   * frames are walked in unrolled groups of four so all of that indexing is static.
+// CPU restatement of exactly this recursion: oracle/sequence.py::ctc_linear_rescaled (held to the log-space recursion and
+// to torch's native CTC in tests/test_oracle_golden.py, in float64 and in float32 arithmetic).
 // A clip whose scale factors leave the fp32 range (infeasible labels, emission probabilities below e^-80, ...) is
 // flagged in `redo` and recomputed by the log-space kernel in a second launch.
 constexpr int kLinWarps = 2;      // clips per block: 64 resident warps per SM (a one-warp block caps at 32)

@@ -212,6 +212,77 @@ def ctc_alpha_beta(lp, target, want_grad=True):
     return nll, grad
 
 
+def ctc_linear_rescaled(lp, target, dtype=np.float64):
+    """The SAME quantity as ctc_alpha_beta, through the recursion ctc_linear_warp_kernel runs
+    (lipreading_b200/csrc/ctc.cu): probabilities with Rabiner-style rescaling instead of log-sum-exp.
+        alpha^_t = (M alpha^_{t-1}) . p_t . k_t ,   k_t = 1 on odd frames, 1 / (lattice mass at frame t-2) on even ones
+        beta~_t  =  M' beta^_{t+1} ,  beta^_t = beta~_t . p_t . k_t
+        rho = alpha^_T(S-1) + alpha^_T(S-2) = sum_s alpha^_t(s) beta~_t(s) for every t
+        nll = sum_t log k_t - log rho ;  grad[t,c] = p_t(c) - sum_{s: l'_s = c} alpha^_t(s) beta~_t(s) / rho
+    Returns (nll, grad, spread) where spread = max_t |sum_s alpha^_t beta~_t / rho - 1| (the invariant the kernel relies
+    on when it divides by the constant rho).  `dtype=np.float32` shows the rounding profile of the kernel's arithmetic."""
+    lp = np.asarray(lp, dtype=np.float64)
+    T, C = lp.shape
+    L = len(target)
+    S = 2 * L + 1
+    ext = np.zeros(S, dtype=np.int64)
+    ext[1::2] = target
+    f = dtype
+    p = np.exp(lp).astype(f)
+    skip = np.zeros(S, dtype=bool)                       # s-2 -> s allowed
+    for s in range(3, S, 2):
+        skip[s] = ext[s] != ext[s - 2]
+
+    def fwd(a):                                          # M a
+        out = a.copy()
+        out[1:] += a[:-1]
+        out[2:] += np.where(skip[2:], a[:-2], f(0))
+        return out
+
+    def bwd(b):                                          # M' b
+        out = b.copy()
+        out[:-1] += b[1:]
+        out[:-2] += np.where(skip[2:], b[2:], f(0))
+        return out
+
+    alpha = np.zeros((T, S), dtype=f)
+    kf = np.ones(T, dtype=f)
+    a = np.zeros(S, dtype=f)
+    a[0] = 1                                             # "alpha_-1": frame 0 is then the generic step
+    first = np.zeros(S, dtype=f)
+    first[0] = p[0, 0]
+    if S > 1:
+        first[1] = p[0, ext[1]]
+    mass = {}
+    for t in range(T):
+        new = first if t == 0 else fwd(a) * p[t, ext]
+        if t >= 2 and t % 2 == 0:
+            kf[t] = f(1) / mass[t - 2]
+        a = (new * kf[t]).astype(f)
+        alpha[t] = a
+        if t % 2 == 0:
+            mass[t] = a.sum(dtype=f)
+    rho = alpha[T - 1, S - 1] + (alpha[T - 1, S - 2] if S > 1 else f(0))
+    nll = float(np.sum(np.log(kf.astype(np.float64))) - math.log(float(rho)))
+    grad = p.astype(np.float64).copy()
+    b = np.zeros(S, dtype=f)                             # "beta_T"
+    spread = 0.0
+    for t in range(T - 1, -1, -1):
+        if t == T - 1:
+            bt = np.zeros(S, dtype=f)
+            bt[S - 1] = 1
+            if S > 1:
+                bt[S - 2] = 1
+        else:
+            bt = bwd(b)
+        e = alpha[t] * bt
+        spread = max(spread, abs(float(e.sum(dtype=np.float64)) / float(rho) - 1.0))
+        for s in range(S):
+            grad[t, ext[s]] -= float(e[s]) / float(rho)
+        b = (bt * p[t, ext] * kf[t]).astype(f)
+    return nll, grad, spread
+
+
 def ctc_nll_torch(log_probs_btc, targets_padded, in_lens, tgt_lens):
     """Per-sample nll through the same torch entry point the reference calls (ctc_loss.py:85)."""
     concat = torch.cat([targets_padded[i, : int(tgt_lens[i])] for i in range(len(tgt_lens))])

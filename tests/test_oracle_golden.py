@@ -118,3 +118,31 @@ def test_oracle_matches_live_reference_including_inf_paths():
         a, sa = mine(inp, st, el, eh)
         b, sb = dec(inp, st, el, eh)
         assert float((a - b).abs().max()) < 1e-5 and float((sa - sb).abs().max()) < 1e-6, attn
+
+
+@pytest.mark.parametrize("T,L,seed", [(20, 6, 0), (75, 30, 1), (75, 1, 2), (300, 31, 3), (9, 0, 4)])
+def test_linear_rescaled_ctc_recursion_equals_log_space(T, L, seed):
+    """The recursion ctc_linear_warp_kernel runs (probabilities, even-frame rescaling, constant normaliser rho,
+    gradient without a division by p) is the same function as the published log-space recursion and torch's native CTC:
+    float64 restatement against both; in float32 arithmetic it stays inside the 1e-4 parity bar."""
+    g = torch.Generator().manual_seed(100 + seed)
+    C = 65
+    lp = torch.randn(T, C, generator=g).log_softmax(-1)
+    lp[:, 1:3] -= 100.0                                   # the two masked classes of the encoder (log(1e-45))
+    tgt = torch.randint(3, C, (L,), generator=g)
+    if L >= 4:
+        tgt[2] = tgt[1]                                   # a repeat: no s-2 -> s transition there
+        tgt[-1] = tgt[0]                                  # the same class twice, apart
+    n_log, g_log = O.ctc_alpha_beta(lp.numpy(), tgt.numpy())
+    n_lin, g_lin, spread = O.ctc_linear_rescaled(lp.numpy(), tgt.numpy())
+    assert abs(n_lin - n_log) < 1e-9 * max(1.0, abs(n_log))
+    assert np.abs(g_lin - g_log).max() < 1e-9
+    assert spread < 1e-9
+    lp_t = lp.double().clone().requires_grad_(True)
+    nll_t = O.ctc_nll_torch(lp_t[None], tgt[None], torch.tensor([T]), torch.tensor([L]))
+    nll_t.sum().backward()
+    assert abs(float(nll_t) - n_lin) < 1e-8 * max(1.0, abs(n_lin))
+    assert np.abs(lp_t.grad.numpy() - g_lin).max() < 1e-8
+    n32, g32, spread32 = O.ctc_linear_rescaled(lp.numpy(), tgt.numpy(), dtype=np.float32)
+    assert abs(n32 - n_log) < 1e-4 * max(1.0, abs(n_log))
+    assert np.abs(g32 - g_log).max() < 1e-4 and spread32 < 1e-4
