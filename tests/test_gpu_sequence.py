@@ -39,7 +39,8 @@ def ctc_kernel(request, native_lib):
 
 
 @pytest.mark.parametrize("B,T,C,Lmax", [(7, 20, 65, 8), (3, 75, 65, 30), (2, 300, 65, 120), (1, 5, 65, 1),
-                                        (5, 75, 65, 31), (4, 90, 65, 63), (3, 40, 33, 40)])
+                                        (5, 75, 65, 31), (4, 90, 65, 63), (3, 40, 33, 40),
+                                        (6, 50, 33, 12), (6, 37, 20, 8), (5, 64, 96, 31)])   # 2 / 1 / 3 class slabs
 def test_ctc_nll_and_grad(native_lib, cuda, ctc_kernel, B, T, C, Lmax):
     from lipreading_b200 import functional as LF
     g = torch.Generator().manual_seed(123456 + B * T)
