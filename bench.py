@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="clips per step of the CPU baseline sample")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel micro rooflines")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity columns (GPU step vs the fp32 CPU port)")
+    ap.add_argument("--no-ref-shape", action="store_true", help="skip the reference-shape (B,T,68,3) train() block")
     return ap.parse_args()
 
 
@@ -117,32 +119,26 @@ class ClockSampler:
 # CPU path: the oracle port of the same step (torch CPU fp32: conv3d -> nn.GRU packed -> CTC)
 # ------------------------------------------------------------------------------------------------
 def cpu_step_fn(hidden, rnn, char2idx):
-    from oracle import conv3d as OC
-    from oracle import sequence as O
-    torch.manual_seed(SEED)
-    convs = torch.nn.ModuleDict({"conv1": torch.nn.Conv3d(3, 32, (3, 5, 5), (1, 2, 2), (1, 2, 2)),
-                                 "conv2": torch.nn.Conv3d(32, 64, (3, 5, 5), 1, (1, 2, 2)),
-                                 "conv3": torch.nn.Conv3d(64, 96, (3, 3, 3), 1, (1, 1, 1))})
-    rnn_m = getattr(torch.nn, rnn)(1728, hidden, bidirectional=True, batch_first=True)
-    proj = torch.nn.Linear(2 * hidden, len(char2idx) + 1)
-    params = list(convs.parameters()) + list(rnn_m.parameters()) + list(proj.parameters())
-    opt = torch.optim.Adam(params, lr=1e-4)
-    log_mask = O.log_mask_vector(len(char2idx), char2idx)
+    """fp32 CPU port of the step (oracle/train_step.py: F.conv3d -> packed nn.GRU -> masked log-softmax -> the
+    ctc_loss wrapper -> clip -> Adam)"""
+    from oracle import train_step as TS
+    port = TS.CpuStep(TS.random_state(hidden, rnn, char2idx, conv=True, seed=SEED), rnn, char2idx, lr=1e-4, grad_norm=50)
+    return lambda batch: port.step(batch)[0]
 
-    def step(batch):
-        clips, lens, chars, char_lens = batch
-        cp = {k + "." + n: p for k, m in convs.items() for n, p in m.named_parameters()}
-        feat, _ = OC.stcnn_forward(clips, cp, quantize=False)
-        weights = dict(rnn_m.named_parameters())
-        hidden_states, _ = O.rnn_packed(feat, lens, weights, rnn, True)
-        lp = O.masked_log_softmax(proj(hidden_states), log_mask)
-        loss = O.ctc_loss_wrapper(lp, chars[:, 1:], lens, char_lens - 1, "mean")
-        opt.zero_grad()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 50)
-        opt.step()
-        return float(loss)
-    return step
+
+def configure_throughput_path():
+    """The three switches of the configuration this benchmark times (BASELINE config 3: "bf16"); returns a function
+    that restores the parity-path defaults.  tests/test_gpu_bench_config.py holds exactly this configuration to the
+    fp32 CPU port."""
+    from lipreading_b200 import conv_frontend, functional as LF
+    saved = (LF.GEMM_DTYPE, LF.RNN_CLUSTER, conv_frontend.OUT_DTYPE)
+    LF.GEMM_DTYPE = torch.bfloat16              # plain GEMMs: bf16 operands, fp32 accumulate
+    LF.RNN_CLUSTER = True                       # persistent cluster recurrence (bf16 operands, fp32 state)
+    conv_frontend.OUT_DTYPE = torch.bfloat16    # the conv3 epilogue's bf16 features feed the bf16 input GEMM directly
+
+    def restore():
+        LF.GEMM_DTYPE, LF.RNN_CLUSTER, conv_frontend.OUT_DTYPE = saved
+    return restore
 
 
 def usable_cores():
@@ -197,6 +193,106 @@ def run_cpu(args, char2idx, steps, warmup, budget_s=150.0):
         step(batch)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return n_clips * T_FRAMES / dt, dt, cores, n_clips
+
+
+# ------------------------------------------------------------------------------------------------
+# parity columns and the reference-shape block, rank 0 at N=1 only
+# ------------------------------------------------------------------------------------------------
+def parity_block(dev, clips=64):
+    """The timed configuration held to the fp32 CPU port on `clips` clips of the bench's own synthetic batch, in
+    this very run: the same function tests/test_gpu_bench_config.py asserts on (B = 32 and 256 there)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_bench_config import throughput_step_parity
+    r = throughput_step_parity(clips, dev)
+    g = r.pop("grad_rel_fro_err")
+    r["grad_rel_fro_err_max"] = max(g.values())
+    r["bars"] = {"logprob_max_abs_err": 2e-2, "ctc_loss_rel_err": 1e-2, "grad_rel_fro_err": 8e-2}
+    r["within_bars"] = bool(r["logprob_max_abs_err"] <= 2e-2 and r["ctc_loss_rel_err"] <= 1e-2 and
+                            r["grad_rel_fro_err_max"] <= 8e-2)
+    r["also"] = ("fp32 path: log-probs / CTC loss / gradients <= 1e-4 vs the unmodified reference's golden vectors and at "
+                 "B=256 BiGRU-256 / B=128 BiLSTM-768 (tests/test_gpu_train_step.py, test_gpu_bench_config.py); padded rect, "
+                 "crop size, gather indices bit-exact (tests/test_gpu_vision.py); CER under the seeded host-sampling "
+                 "protocol equal to the reference's eval() (tests/test_gpu_train_step.py)")
+    return r
+
+
+def _ref_shape_batch(B, T, mixed, seed, char2idx):
+    """BASELINE.md §3.1 inputs: randn(B,T,68,3) f32, labels [BOS]+randint(4,64,(L,))+[EOS], L in [10,30];
+    all T=75 or ascending mixed T in [40,75]."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(40, T + 1, (B,), generator=g).sort().values if mixed else torch.full((B,), T, dtype=torch.long)
+    lens[-1] = T
+    frames = torch.randn(B, T, 68, 3, generator=g)
+    for b in range(B):
+        frames[b, int(lens[b]):] = 0
+    L = torch.randint(10, 31, (B,), generator=g)
+    chars = torch.zeros(B, int(L.max()) + 2, dtype=torch.long)
+    for b in range(B):
+        n = int(L[b])
+        chars[b, 0], chars[b, 1 + n] = char2idx["<BOS>"], char2idx["<EOS>"]
+        chars[b, 1:1 + n] = torch.randint(4, 64, (n,), generator=g)
+    return frames, lens, chars, L + 2
+
+
+def ref_shape_block(dev, char2idx, steps=3):
+    """The reference's own `train()` (encoder + CTC aux + teacher-forced decoder, clip 50, Adam) on ref-shape batches:
+    GPU arm = lipreading_b200.trainer.train on pinned host batches (fp32 parity path for the kernels, H2D inside the
+    timed region); CPU arm = the oracle port of train() (oracle/train_step.CpuReferenceTrain, pinned against the
+    unmodified reference's golden train step) on a bounded sample of the same batch."""
+    from lipreading_b200 import functional as LF, trainer
+    from lipreading_b200.model import CharDecodingStep, VideoEncoder
+    from oracle import sequence as O
+    from oracle import train_step as TS
+    saved = (LF.GEMM_DTYPE, LF.RNN_CLUSTER)
+    out = []
+    try:
+        for rnn, H, B, cpu_B in (("GRU", 256, 256, 64), ("LSTM", 768, 128, 16)):
+            for mixed in (False, True):
+                LF.GEMM_DTYPE, LF.RNN_CLUSTER = torch.float32, False
+                torch.manual_seed(SEED)
+                enc = VideoEncoder(204, H, rnn_type=rnn, bidirectional=True, enable_ctc=True, vocab_size=len(char2idx),
+                                   char2idx=char2idx, device=dev).to(dev)
+                dec = CharDecodingStep(enc, char_dim=256, vocab_size=len(char2idx), char2idx=char2idx,
+                                       attention_type="none", device=dev).to(dev)
+                batch = tuple(t.pin_memory() for t in _ref_shape_batch(B, T_FRAMES, mixed, SEED, char2idx))
+                opt = torch.optim.Adam(list(enc.parameters()) + list(dec.parameters()), lr=1e-4)
+                import contextlib
+                import io
+                with contextlib.redirect_stdout(io.StringIO()):
+                    trainer.train(enc, dec, [batch], opt, dev, char2idx, teacher_forcing_ratio=1, grad_norm=50)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    dl, cl = trainer.train(enc, dec, [batch] * steps, opt, dev, char2idx, teacher_forcing_ratio=1, grad_norm=50)
+                    e1.record()
+                    torch.cuda.synchronize()
+                s_gpu = e0.elapsed_time(e1) * 1e-3 / steps
+                n_frames = int(batch[1].sum())
+                row = {"config": "bi%s%d B=%d T=%s ref-shape (B,T,68,3), train() with decoder, attention none"
+                                 % (rnn.lower(), H, B, "40..75 mixed" if mixed else "75"),
+                       "gpu_frames_per_s": n_frames / s_gpu, "gpu_ms_per_step": s_gpu * 1e3, "gpu_path": "fp32 parity path",
+                       "decoder_loss": dl, "ctc_loss": cl}
+                if not mixed:
+                    # CPU arm on a bounded sample (first cpu_B clips of the same batch), all usable host threads
+                    sample = tuple(t[:cpu_B].clone() for t in batch)
+                    sample = (sample[0], sample[1], sample[2][:, : int(sample[3].max())], sample[3])
+                    enc_state = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+                    dec_o = O.OracleDecoder(2 * H, rnn, 256, len(char2idx), char2idx, attention_type="none")
+                    dec_o.load_state_dict({k: v.detach().cpu() for k, v in dec.state_dict().items()})
+                    port = TS.CpuReferenceTrain(enc_state, dec_o, rnn, char2idx, lr=1e-4, grad_norm=50)
+                    torch.set_num_threads(min(usable_cores(), 32))
+                    port.step(sample)
+                    t0 = time.perf_counter()
+                    port.step(sample)
+                    s_cpu = time.perf_counter() - t0
+                    row["cpu_frames_per_s"] = int(sample[1].sum()) / s_cpu
+                    row["cpu_sample"] = "%d clips/step, 1 warm-up + 1 timed, %d threads, oracle port of train()" % (
+                        cpu_B, torch.get_num_threads())
+                out.append(row)
+                del enc, dec, opt
+    finally:
+        LF.GEMM_DTYPE, LF.RNN_CLUSTER = saved
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,7 +407,9 @@ def kernel_rooflines(dev, pk, char2idx):
 
 # ------------------------------------------------------------------------------------------------
 def main():
-    os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: exactly one JSON line
+    # NCCL's own log lines (NCCL_DEBUG=INFO when the driver sets it) must not mix with the ONE JSON line on stdout:
+    # send them to stderr instead of silencing them
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     from lipreading_b200.vocab import build_char2idx
     char2idx = build_char2idx()
@@ -329,7 +427,9 @@ def main():
         line = {"impl": "reference", "metric": "frames/sec end-to-end (3Dconv+BiGRU+CTC train step)", "value": value,
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "dtype": "f32", "data": "synthetic", "config": cfg, "sample_clips_per_step": n_clips,
+                "note": "CPU arm = oracle/train_step.py (fp32 port of the same step; the reference itself has no conv "
+                        "front-end) on a bounded sample of the workload: %d clips per step instead of %d" % (n_clips, args.batch),
                 "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d clips/step (same shapes), %d steps" % (n_clips, args.steps)},
                 "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -337,9 +437,7 @@ def main():
         return
 
     from lipreading_b200 import conv_frontend, dist as ldist, functional as LF, native, trainer
-    LF.GEMM_DTYPE = torch.bfloat16          # BASELINE config: bf16 operands, fp32 accumulate
-    LF.RNN_CLUSTER = True                   # persistent cluster recurrence (bf16 operands, fp32 state)
-    conv_frontend.OUT_DTYPE = torch.bfloat16   # the conv3 epilogue's bf16 features feed the bf16 input GEMM directly
+    configure_throughput_path()
     from lipreading_b200.model import VideoEncoder
     rank, local_rank, world = ldist.init()
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
@@ -438,7 +536,9 @@ def main():
             torch.distributed.destroy_process_group()
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (conv3d_tcgen05_kernel) -----------------------------
+    # ---- roofline of the dominant kernels: ALL EIGHT tensor-core conv launches of a step ------------
+    # (conv1-3 fwd, conv3/conv2 dgrad: conv3d_tcgen05_kernel; conv1-3 wgrad: conv3d_wgrad_tcgen05_kernel), each timed
+    # with CUDA events on the launching stream inside the timed region; achieved = algorithmic FLOPs / time.
     torch.cuda.synchronize()
     per = {}
     for tag, a, b, fl in ktimes:
@@ -448,23 +548,32 @@ def main():
         d[2] += 1
     tot_s = sum(v[0] for v in per.values())
     tot_f = sum(v[1] for v in per.values())
-    peak = pk["bf16_tflops_sustained"]
-    # DRAM traffic of the largest launch (conv2.fwd) from the committed `ncu --set full` capture
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_step_b256_v4.json")) as fh:
-            cap = json.load(fh)["conv2.fwd"]
-        if args.batch == 256:
-            traffic = (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6
-    except Exception:
-        pass
-    roofline = {"kernel": "conv3d_tcgen05_kernel (5 launches/step: conv1-3 fwd, conv3/conv2 dgrad)",
+    # the timed region is a fraction of a second at boost clocks: the burst figure is the honest denominator
+    peak = pk["bf16_tflops"]
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the same command (profiles/), if any
+    traffic, traffic_src = None, None
+    for name in ("r2_ncu_full_step_b256.json", "r1_ncu_full_step_b256_v4.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                cap = json.load(fh)
+            if args.batch == 256:
+                traffic = {k: (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for k, v in cap.items()
+                           if isinstance(v, dict) and "dram_read_MB" in v}
+                traffic_src = "dram bytes read+written per launch, profiles/" + name + " (ncu --set full; not measured in this run)"
+            break
+        except Exception:
+            continue
+    roofline = {"kernel": "conv3d_tcgen05_kernel + conv3d_wgrad_tcgen05_kernel (8 launches/step: conv1-3 fwd, conv3/conv2 "
+                          "dgrad, conv1-3 wgrad)",
                 "bound": "tensor", "achieved": tot_f / tot_s / 1e12 if tot_s else None, "peak": peak,
-                "unit": "TFLOP/s", "frac": (tot_f / tot_s / 1e12 / peak) if tot_s else None, "traffic": traffic,
-                "traffic_source": "dram bytes read+written by the conv2.fwd launch, profiles/r1_ncu_full_step_b256_v4.json",
-                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "unit": "TFLOP/s", "frac": (tot_f / tot_s / 1e12 / peak) if tot_s else None,
+                "frac_of_sustained": (tot_f / tot_s / 1e12 / pk["bf16_tflops_sustained"]) if tot_s else None,
+                "traffic": (traffic or {}).get("conv2.fwd"), "traffic_per_launch": traffic, "traffic_source": traffic_src,
+                "peak_source": pk["source"] + " (burst bf16 cuBLAS; sustained %.1f)" % pk["bf16_tflops_sustained"],
                 "share_of_step": tot_s / (ms * 1e-3),
-                "per_launch": {k: {"ms": v[0] / v[2] * 1e3, "tflops": v[1] / v[0] / 1e12} for k, v in per.items()}}
+                "whole_step_tflops": tot_f / args.steps / (ms / args.steps * 1e-3) / 1e12 if tot_s else None,
+                "per_launch": {k: {"ms": v[0] / v[2] * 1e3, "tflops": v[1] / v[0] / 1e12,
+                                   "frac": v[1] / v[0] / 1e12 / peak} for k, v in per.items()}}
     line = {"metric": "frames/sec end-to-end (3Dconv+BiGRU+CTC train step)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -475,7 +584,18 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, dt, cores, n_clips = run_cpu(args, char2idx, 2, 1, budget_s=25.0)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "%d clips/step (same shapes), 1 warm-up + 2 timed steps" % n_clips}
+                                "sample": "%d clips/step (same shapes; the GPU arm runs %d), 1 warm-up + 2 timed steps"
+                                          % (n_clips, args.batch)}
+    if world == 1 and not args.no_parity:
+        try:
+            line["parity"] = parity_block(dev)
+        except Exception as e:
+            line["parity_error"] = repr(e)
+    if world == 1 and not args.no_ref_shape:
+        try:
+            line["ref_shape"] = ref_shape_block(dev, char2idx)
+        except Exception as e:
+            line["ref_shape_error"] = repr(e)
     if world == 1 and not args.no_kernels:
         try:
             # BASELINE config 5: frames -> characters inference stream (conv front-end -> BiGRU -> greedy CTC)

@@ -56,7 +56,7 @@ STACK_KY = True      # wgrad: also fold 128/Cy filter rows into one M = 128 MMA 
 
 
 def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x, splits=0, stack_kx=None,
-                        stack_ky=None):
+                        stack_ky=None, tag="wgrad", algo_macs=None):
     """Thin call into lr_conv3d_wgrad -> fp32 [taps][rows][Nc]: rows = 64 input channels, Nc = Gy*Cy if
     m_is_x; else rows = output channels (64, or Cy when ky-stacked) and Nc = Cx."""
     L = N.lib()
@@ -84,9 +84,17 @@ def conv3d_wgrad_native(x, dy, B, T, H, W, Hp, Wp, Cx, Cy, Gy, dy_off, K, m_is_x
     sk = -1 if pair else S
     ws = torch.empty(L.lr_conv3d_wgrad_workspace(KT, KH, KW, Nc, splits, sk), dtype=torch.uint8, device=x.device)
     out = torch.empty(L.lr_conv3d_wgrad_out_floats(KT, KH, KW, Nc, sk), dtype=torch.float32, device=x.device)
+    rec = KERNEL_TIMING
+    if rec is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        macs = algo_macs if algo_macs is not None else B * T * H * W * Cx * Cy * Gy * taps
+        rec.append((tag, e0, e1, 2.0 * macs))
     N.check(L.lr_conv3d_wgrad(N.ptr(x), N.ptr(dy), N.ptr(out), N.ptr(ws), ws.numel(), B, T, H, W, Hp, Wp, Cx, Cy,
                               Gy, dy_off, KT, KH, KW, m_is_x, int(stack), sk, int(fuse_kt), splits, N.stream()),
             "lr_conv3d_wgrad")
+    if rec is not None:
+        e1.record()
     if pair:                        # [KT][P][2][64][Nc], flat spatial tap = 2u + b -> [taps][64][Nc]
         return out.reshape(KT, P * 2, 64, Nc)[:, :KH * KW].reshape(taps, 64, Nc)
     if S > 1:                       # [KT][U][S(b)][Cy][KW][Cx], ky = u*S + S-1-b -> [taps][Cy][Cx]
@@ -197,9 +205,12 @@ def dgrad_weight(w, cg):
 
 class _VolumePool:
     """Zero-padded activation volumes are large (GBs at B=256) and only their INTERIOR is rewritten
-    every step; re-zeroing them per step costs ~1 ms of pure memset.  The pool hands out one cached
-    buffer per (tag, shape): borders are zeroed once at allocation and never written again.  A
-    generation counter catches the one unsafe pattern (two forwards before a backward)."""
+    every step; re-zeroing them per step costs ~1 ms of pure memset.  The pool hands out ONE cached
+    buffer per tag: borders are zeroed once at allocation and never written again.  The reference's
+    length-sorted batches give a new T for almost every batch, so the pool must not keep one set of volumes
+    per shape: a tag's storage is allocated for the largest volume seen so far and smaller volumes are carved
+    from it (re-zeroed only when the geometry — and with it the border pattern — changes).  A generation
+    counter catches the one unsafe pattern (two forwards before a backward)."""
 
     def __init__(self):
         self.bufs = {}
@@ -209,12 +220,21 @@ class _VolumePool:
     def get(self, tag, shape, dtype, device):
         if not self.enabled:
             return torch.zeros(shape, dtype=dtype, device=device)
-        key = (tag, tuple(shape), dtype, str(device))
-        buf = self.bufs.get(key)
-        if buf is None:
-            buf = torch.zeros(shape, dtype=dtype, device=device)
-            self.bufs[key] = buf
-        return buf
+        key = (tag, dtype, str(device))
+        n = 1
+        for d in shape:
+            n *= int(d)
+        ent = self.bufs.get(key)
+        if ent is None or ent[0].numel() < n:
+            if ent is not None:
+                self.bufs.pop(key)                   # release the smaller storage before asking for the larger
+                del ent
+            ent = [torch.zeros(n, dtype=dtype, device=device), tuple(shape)]
+            self.bufs[key] = ent
+        elif ent[1] != tuple(shape):
+            ent[0][:n].zero_()                       # same storage, new geometry: old interior is in the new borders
+            ent[1] = tuple(shape)
+        return ent[0][:n].view(shape)
 
 
 POOL = _VolumePool()
@@ -291,7 +311,8 @@ class _ConvStack(torch.autograd.Function):
         # ---- layer 3: d_feat -> dY3 (3 groups x 32 ch, interior at (1,1,1)) ----
         dp3 = N.cont(d_feat.reshape(B, T, H4, W4, 96).to(bf))
         dy3, db3 = unpool(dp3, am3, H3, W3, 96, 32, (1, 1, 1), Hp3, Wp3)
-        d3 = conv3d_wgrad_native(a2, dy3, B, T, H3, W3, Hp3, Wp3, 64, 32, 3, (Hp3 + 1) * Wp3 + 1, (3, 3, 3), 1)
+        d3 = conv3d_wgrad_native(a2, dy3, B, T, H3, W3, Hp3, Wp3, 64, 32, 3, (Hp3 + 1) * Wp3 + 1, (3, 3, 3), 1,
+                                 tag="conv3.wgrad")
         dw3 = d3.reshape(3, 3, 3, 64, 96).permute(4, 3, 0, 1, 2)       # [tap][ci][co] -> (co,ci,kt,ky,kx)
 
         def dgrad_unpool(dy, wflip, am, Hd, Wd, Hpd, Wpd, Cin, CG, C, K, pad, Hb, Wb, Hpo, Wpo, tag, swap=None):
@@ -311,12 +332,14 @@ class _ConvStack(torch.autograd.Function):
         # ---- layer 2: dgrad of conv3 fused with the un-pooling of pool2 -> dY2 (+ conv2's bias gradient) ----
         dy2, db2 = dgrad_unpool(dy3, dgrad_weight(w3.detach(), 32).to(bf), am2, H3, W3, Hp3, Wp3, 32, 3, 64, (3, 3, 3),
                                 (1, 2, 2), H2, W2, Hp2, Wp2, "conv3.dgrad")
-        d2 = conv3d_wgrad_native(a1, dy2, B, T, H2, W2, Hp2, Wp2, 32, 64, 1, (Hp2 + 2) * Wp2 + 2, (3, 5, 5), 0)
+        d2 = conv3d_wgrad_native(a1, dy2, B, T, H2, W2, Hp2, Wp2, 32, 64, 1, (Hp2 + 2) * Wp2 + 2, (3, 5, 5), 0,
+                                 tag="conv2.wgrad")
         dw2 = d2.reshape(3, 5, 5, 64, 32).permute(3, 4, 0, 1, 2)       # [tap][co][ci]
         # ---- layer 1 (no input gradient: the clip is data); dY1 top-left aligned in z's geometry ----
         dy1, db1 = dgrad_unpool(dy2, dgrad_weight(w2.detach(), 64).to(bf), am1, H2, W2, Hp2, Wp2, 64, 1, 32, (3, 5, 5),
                                 (0, 0, 0), H1, W1, Hp1, Wp1, "conv2.dgrad", swap=2 if DGRAD_KX_STACK else None)
-        d1 = conv3d_wgrad_native(z, dy1, B, T, H1, W1, Hp1, Wp1, 16, 32, 1, 0, (3, 3, 3), 0)
+        d1 = conv3d_wgrad_native(z, dy1, B, T, H1, W1, Hp1, Wp1, 16, 32, 1, 0, (3, 3, 3), 0, tag="conv1.wgrad",
+                                 algo_macs=B * T * H1 * W1 * 32 * 3 * 75)     # the true 3x5x5x3 stride-2 conv
         dw1_16 = d1[:, :32, :].permute(1, 0, 2).reshape(32, 3, 3, 3, 16)
         dw1 = s2d_weight_grad(dw1_16)
         return None, dw1.contiguous(), db1, dw2.contiguous(), db2, dw3.contiguous(), db3

@@ -105,6 +105,73 @@ def collate_gpu(batch, device):
     return out.reshape((len(frames), int(lens.max())) + tuple(np.shape(frames[0])[1:])), lens, tgt, tgt_lens
 
 
+def collate_clips_pinned(batch):
+    """Mouth-clip rows (T_i,H,W,3) u8 -> zero-padded (B,Tmax,H,W,3) u8 in PINNED host memory (the DevicePrefetcher
+    copies it to the GPU one step ahead), captions like `_collate_fn`."""
+    frames, captions = zip(*batch)
+    lens = torch.LongTensor([len(x) for x in frames])
+    shape = (len(frames), int(lens.max())) + tuple(np.shape(frames[0])[1:])
+    out = torch.zeros(shape, dtype=torch.uint8)
+    if torch.cuda.is_available():
+        out = out.pin_memory()
+    for i, f in enumerate(frames):
+        out[i, : len(f)] = torch.from_numpy(np.ascontiguousarray(f, dtype=np.uint8))
+    tgt, tgt_lens = _pad(captions, torch.long)
+    return out, lens, tgt, tgt_lens
+
+
+class GpuBatchLoader:
+    """The loader `train(**flags)` iterates: consecutive `batch_size` rows of the (length-sorted) dataset, no
+    shuffling (train.py:209-211), each batch collated FOR the device —
+      * landmark rows (T,68,3) f64: one pinned copy of the ragged rows + `lr_collate_pad_f64` (cast + zero pad);
+      * mouth-clip rows (T,H,W,3) u8: zero-padded in pinned memory, copied one batch ahead on a side stream;
+    lengths and captions stay on the host (the trainer wants them there).  Under data parallelism `batch_size` is
+    the GLOBAL batch and every rank collates only its contiguous slice (`dist.shard_slice`); a tail batch with
+    fewer rows than ranks is dropped on every rank."""
+
+    def __init__(self, dataset, batch_size, device, rank=0, world=1, prefetch=True):
+        self.dataset, self.batch_size, self.device = dataset, int(batch_size), torch.device(device)
+        self.rank, self.world, self.prefetch = rank, world, prefetch
+
+    def _batches(self):
+        n = len(self.dataset)
+        out = []
+        for lo in range(0, n, self.batch_size):
+            hi = min(n, lo + self.batch_size)
+            if hi - lo < self.world:
+                continue
+            out.append((lo, hi))
+        return out
+
+    def __len__(self):
+        return len(self._batches())
+
+    def _host_iter(self, clips):
+        from .dist import shard_slice
+        for lo, hi in self._batches():
+            a, b = shard_slice(hi - lo, self.rank, self.world)
+            rows = [self.dataset[i] for i in range(lo + a, lo + b)]
+            yield collate_clips_pinned(rows) if clips else collate_gpu(rows, self.device)
+
+    def __iter__(self):
+        clips = len(self.dataset) > 0 and np.ndim(self.dataset[0][0]) == 4
+        it = self._host_iter(clips)
+        if clips and self.prefetch and self.device.type == "cuda":
+            return iter(DevicePrefetcher(_Sized(it, len(self)), self.device))
+        return it
+
+
+class _Sized:
+    def __init__(self, it, n):
+        self.it, self.n = it, n
+
+    def __len__(self):
+        return self.n
+
+    def __iter__(self):
+        return iter(self.it)
+
+
 class FrameCaptionDataset(_data.Dataset):
     """Rows = (landmark sequence (T,68,3), parsed caption ids) (data_loader.py:154-257)."""
 
@@ -113,9 +180,12 @@ class FrameCaptionDataset(_data.Dataset):
                  in_ext=".npy", out_ext=".pkl", refresh=False):
         super().__init__()
         assert all(os.path.isdir(x) for x in vid_ids)
-        assert frame_type in ("face_lmk_seq", "face_vtx_seq")
+        assert frame_type in ("face_lmk_seq", "face_vtx_seq", "mouth_clip_seq")     # mouth clips: row N2 -> N1
         assert not sentence_dataset, "--sentence_dataset needs spaCy (out of scope, SURVEY §2 row 6)"
+        self.frame_type = frame_type
         pickle_dir = _ws.getRelPicklesPath(dataset_name, "non-sentence", split_name)
+        if frame_type != "face_lmk_seq":
+            pickle_dir = os.path.join(pickle_dir, frame_type)     # one cache per column (the reference has one column)
         if refresh or not os.path.isdir(pickle_dir):
             self.char2idx, self.frames, self.captions = self.construct_dataset(
                 dataset_name, pickle_dir, vid_ids, labels=labels, start_end=start_end, cap=cap,
@@ -125,14 +195,13 @@ class FrameCaptionDataset(_data.Dataset):
         assert len(self.frames) == len(self.captions) > 0
         self.idx2char = {v: k for k, v in self.char2idx.items()}
         self.num_elements = len(self.captions)
-        self.frame_type = frame_type
 
     def __len__(self):
         return self.num_elements
 
     def __getitem__(self, index):
         frames = self.frames[index]
-        assert len(frames.shape) == 3
+        assert len(frames.shape) == (4 if self.frame_type == "mouth_clip_seq" else 3)
         return frames, parse_caption(self.captions[index], self.char2idx)
 
     def parse_caption(self, cap):
@@ -149,7 +218,7 @@ class FrameCaptionDataset(_data.Dataset):
         captions = [str(x) for arr in col(cap) for x in arr]
         start_ends = [x for arr in col(start_end) for x in arr]
         assert len(frames) == len(captions) == len(start_ends)
-        assert all(len(x.shape) == 3 for x in frames)
+        assert all(len(x.shape) == (4 if frame_type == "mouth_clip_seq" else 3) for x in frames)
         frames, captions = filter_occlusions(frames, captions, start_ends, fps=fps, threshold=threshold)
         frames, captions = sort_by_seqlen(frames, captions)
         char2idx = build_vocab(dataset_name, labels)

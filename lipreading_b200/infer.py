@@ -28,6 +28,6 @@ class Recognizer:
         tok, n = tok.cpu(), n.cpu()
         out = []
         for b in range(tok.shape[0]):
-            chars = [self.idx2char.get(int(i), "") for i in tok[b, : int(n[b])]]
-            out.append("".join(c for c in chars if not c.startswith("<")))
+            # drop the four markers by ID (PAD, BOS, EOS, UNK = 0..3); '<' and '>' are ordinary characters
+            out.append("".join(self.idx2char.get(int(i), "") for i in tok[b, : int(n[b])] if int(i) >= 4))
         return out

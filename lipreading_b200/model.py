@@ -57,6 +57,20 @@ class NativeRNN(nn.Module):
         return inp, ((h_n, torch.cat(c_all, 0)) if self.mode == "LSTM" else h_n)
 
 
+_FUSED_PROJ_MAX_CLASSES = 68          # kMaxC of csrc/proj_logsoftmax.cu (4 class groups x 17)
+
+
+def _proj_log_softmax(hidden, proj, log_mask):
+    """Linear + masked log-softmax (better_model.py:91-94, 231-233).  Up to 68 classes (the reference's 64-entry
+    vocabulary + blank and then some) this is the fused kernel; a larger labels.json takes the wide-vocabulary
+    route: a plain library GEMM followed by torch's row log-softmax, on the same device (the reference accepts any
+    vocabulary, so must this)."""
+    LF.N.require_cuda(hidden)
+    if proj.out_features <= _FUSED_PROJ_MAX_CLASSES:
+        return LF.proj_masked_log_softmax(hidden, proj.weight, proj.bias, log_mask)
+    return F.log_softmax(F.linear(hidden, proj.weight, proj.bias) + log_mask, dim=-1)
+
+
 class VideoEncoder(nn.Module):
     """Drop-in for better_model.VideoEncoder (:13-122)."""
 
@@ -112,8 +126,7 @@ class VideoEncoder(nn.Module):
             final = self._cat_directions(final)
         if not self.enable_ctc:
             return hidden, final
-        log_probs = LF.proj_masked_log_softmax(hidden, self.output_proj.weight, self.output_proj.bias,
-                                               self._log_mask(hidden.device))
+        log_probs = _proj_log_softmax(hidden, self.output_proj, self._log_mask(hidden.device))
         return log_probs, hidden, final
 
     def _cat_directions(self, final_state):
@@ -219,11 +232,7 @@ class CharDecodingStep(nn.Module):
                 context = torch.bmm(w, enc)
             q = self.concat_layer(torch.cat([context, q], dim=2)).tanh()
         log_mask = (self.output_mask.to(q.device) + 1e-45).log()
-        if q.is_cuda and self.vocab_size <= 68:
-            log_probs = LF.proj_masked_log_softmax(q, self.output_proj.weight, self.output_proj.bias, log_mask)
-        else:
-            log_probs = F.log_softmax(self.output_proj(q) + log_mask, dim=-1)
-        return log_probs, final_state
+        return _proj_log_softmax(q, self.output_proj, log_mask), final_state
 
     def save_best_model(self, error, file_path):
         if error < self.best_error:

@@ -13,7 +13,6 @@ import time
 
 import numpy as np
 import torch
-import torch.utils.data as _data
 
 from . import data as _data_loader
 from . import dist as _dist
@@ -41,10 +40,11 @@ class _ScalarLog:
 
 
 def _get_datasets(dataset_name, train_split, sentence_dataset, threshold=0.8, labels="labels.json", rand=None,
-                  refresh=False):
+                  refresh=False, frame_type="face_lmk_seq"):
     ids = _data_loader.split_dataset(dataset_name, train_split=train_split, rand=rand)
     sets = [_data_loader.FrameCaptionDataset(dataset_name, split, vids, labels=labels, threshold=threshold,
-                                             sentence_dataset=sentence_dataset, refresh=refresh)
+                                             sentence_dataset=sentence_dataset, refresh=refresh,
+                                             frame_type=frame_type)
             for split, vids in zip(("train", "val", "test"), ids)]
     print("\nDataset Information:")
     for name, ds in zip(("Train", "Val", "Test"), sets):
@@ -136,12 +136,22 @@ def train(
     print("Device: ", device)
 
     print("Initializing dataset '{}'".format(data))
+    # the conv front-end eats the mouth-clip column (rows N2 -> N1), the reference's encoder the landmark column
+    frame_type = "mouth_clip_seq" if frame_processing == "conv3d" else "face_lmk_seq"
+    if world > 1 and refresh:
+        # only rank 0 rebuilds the pickle cache; the others read it once it is complete
+        if rank == 0:
+            _get_datasets(data, train_split, sentence_dataset, threshold=occlussion_threshold, labels=labels,
+                          rand=np.random.RandomState(seed=seed), refresh=True, frame_type=frame_type)
+        _dist.barrier()
+        refresh = False
     train_ds, val_ds, test_ds = _get_datasets(data, train_split, sentence_dataset, threshold=occlussion_threshold,
-                                              labels=labels, rand=rand, refresh=refresh)
+                                              labels=labels, rand=rand, refresh=refresh, frame_type=frame_type)
+
     def loader(ds):
-        ld = _data.DataLoader(ds, batch_size=batch_size * world, num_workers=num_workers,
-                              collate_fn=_data_loader._collate_fn)        # no shuffle, no sampler (:209-211)
-        return _dist.ShardedLoader(ld, rank, world) if world > 1 else ld
+        # no shuffle, no sampler (:209-211); batches are collated for the device (pad kernel / pinned prefetch) and
+        # `batch_size` clips per GPU make a global batch of batch_size * world
+        return _data_loader.GpuBatchLoader(ds, batch_size * world, device, rank=rank, world=world)
     train_loader, val_loader, test_loader = loader(train_ds), loader(val_ds), loader(test_ds)
     reducer = _dist.GradAllReducer(world) if world > 1 else None
 
@@ -149,14 +159,21 @@ def train(
     encoder, decoding_step = _init_models(train_ds.char2idx, num_layers, frame_dim, hidden_size, char_dim,
                                           enable_ctc, rnn_type, attention_type, attn_hidden_size, bidirectional,
                                           rnn_dropout, device, frame_processing)
-    weights_dir = _util.getRelWeightsPath(data, use_existing=False)
+    # one run directory for the whole job: rank 0 picks the first free index, the others are told
+    weights_dir = _dist.broadcast_object(_util.getRelWeightsPath(data, use_existing=False) if rank == 0 else None)
+    if rank == 0:
+        _util.mkdirP(weights_dir)
+    _dist.barrier()
     writer = _ScalarLog(weights_dir) if rank == 0 else None
     encoder_path = os.path.join(weights_dir, "best_encoder.pth")
     decoder_path = os.path.join(weights_dir, "best_decoder.pth")
 
     def cer_of(loader_):
+        # every rank evaluates its shard; the hit / character counts are summed over the ranks BEFORE the ratio, so
+        # val_cer — which drives the loop condition, the annealing and the checkpoints — is identical everywhere
         _, correct, count = _train.eval(encoder, decoding_step, loader_, device, train_ds.char2idx)
-        return (count - correct).float() / count
+        correct, count = _dist.allreduce_counts(correct, count, device=device)
+        return ((count - correct) / count).float()
 
     print("Initial evaluation...")
     val_cer = cer_of(val_loader)
@@ -175,6 +192,7 @@ def train(
             num_annealings += 1
             learning_rate /= 5
             print(f"\tAnnealing to {learning_rate}")
+            _dist.barrier()                          # rank 0 has finished writing the checkpoints
             if os.path.isfile(encoder_path):
                 restore(encoder, encoder_path)
                 restore(decoding_step, decoder_path)
@@ -196,6 +214,10 @@ def train(
             writer.add_scalar(os.path.join(data, "avg CTC loss"), avg_ctc, global_step=num_epochs)
             writer.add_scalars(os.path.join(data, "CER"), {"Train": train_cer, "Val": val_cer}, global_step=num_epochs)
             writer.add_scalar(os.path.join(data, "learning rate"), learning_rate, global_step=num_epochs)
+        else:
+            # keep best_error in step with rank 0 (it gates the next save there and nothing here)
+            encoder.best_error = min(encoder.best_error, float(val_cer))
+            decoding_step.best_error = min(decoding_step.best_error, float(val_cer))
         print(f"\tTrain CER: {train_cer}\n\tVal CER: {val_cer}")
         with torch.no_grad():
             print(f"\tTest CER: {cer_of(test_loader)}")

@@ -19,6 +19,16 @@ from .vocab import BOS, EOS, PAD
 # Python loop over label positions; False keeps the reference's step loop (used by the parity tests as the oracle path)
 SEQUENCE_DECODE = True
 
+# Where the decoder's characters are sampled (train: the non-teacher-forced input; eval: the CER hits).
+#   "device": one multinomial on the GPU (fast; its random stream is the CUDA generator's, so CER is only
+#             statistically comparable with a reference run);
+#   "cpu":    the CER-parity protocol of SURVEY §7 — the log-probs computed on the GPU are brought to the host and
+#             sampled there with the reference's calls in the reference's order (per label position one
+#             `torch.rand(1)` in train, one `(B,V)` `multinomial(1)` in train and eval:
+#             train_better_model.py:56-63,130), so after `torch.manual_seed(seed)` the draws — and with them
+#             `correct`, CER and the fed-back characters — equal those of the reference running on its CPU device.
+SAMPLING = "device"
+
 
 def _check_batch(chars, char_lens, frame_lens, char2idx, use_ctc):
     assert bool((chars[:, 0] == char2idx[BOS]).all())
@@ -28,14 +38,17 @@ def _check_batch(chars, char_lens, frame_lens, char2idx, use_ctc):
 
 
 def train(encoder, decoding_step, data_loader, opt, device, char2idx,
-          teacher_forcing_ratio=1, grad_norm=None, dist=None):
+          teacher_forcing_ratio=1, grad_norm=None, dist=None, sampling=None):
     """Same contract as the reference `train`: returns (avg_decoder_loss, avg_ctc_loss)."""
     use_ctc = encoder.enable_ctc
+    sampling = sampling or SAMPLING
+    assert sampling in ("device", "cpu")
     dec_sum = torch.zeros((), device=device)
     ctc_sum = torch.zeros((), device=device)
     encoder.train()
     decoding_step.train()
     pad = char2idx[PAD]
+    params_all = list(encoder.parameters()) + list(decoding_step.parameters())
     for frames, frame_lens, chars, char_lens in data_loader:
         fl_h, cl_h, chars_h = frame_lens.cpu(), char_lens.cpu(), chars.cpu()
         _check_batch(chars_h, cl_h, fl_h, char2idx, use_ctc)
@@ -54,17 +67,31 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
             enc_out, enc_h, prev_state = encoder(frames, frame_lens_d)
             cur_ctc = ctc_loss(enc_out, labels, frame_lens_d, ll_h, "mean", device, host_lens=(fl_h, ll_h))
             if cur_ctc is None:
+                # the reference skips the batch (train_better_model.py:41-42).  Under data parallelism the other
+                # ranks are about to all-reduce: join them with zero gradients so the collectives stay paired
+                if dist is not None:
+                    opt.zero_grad()
+                    dist.allreduce_grads(params_all, valid=False)
+                    if grad_norm is not None:
+                        torch.nn.utils.clip_grad_norm_(encoder.parameters(), grad_norm)
+                        torch.nn.utils.clip_grad_norm_(decoding_step.parameters(), grad_norm)
+                    opt.step()
                 continue
         else:
             enc_h, prev_state = encoder(frames, frame_lens_d)
         prev_output = torch.full((batch_size,), char2idx[BOS], dtype=torch.long, device=device)
 
         if teacher_forcing_ratio >= 1 and SEQUENCE_DECODE and hasattr(decoding_step, "forward_sequence"):
-            # always teacher forcing: no step depends on a sampled character, so the whole decode loop is one
-            # vectorised pass (the reference's per-step torch.rand / multinomial draws have no effect on the loss)
             log_probs, prev_state = decoding_step.forward_sequence(chars[:, :max_label_len], prev_state, frame_lens_d, enc_h)
             decoder_loss = F.nll_loss(log_probs.reshape(-1, log_probs.shape[-1]), labels[:, :max_label_len].reshape(-1),
                                       ignore_index=pad, reduction="sum")
+            if sampling == "cpu":
+                # leave the host generator where the reference leaves it: per position one rand(1) and one (B,V)
+                # multinomial draw (their values feed nothing when every step is teacher forced)
+                lp_h = log_probs.detach().cpu()
+                for i in range(max_label_len):
+                    torch.rand(1)
+                    lp_h[:, i].exp().multinomial(1)
         else:
             decoder_loss = 0
             for i in range(max_label_len):
@@ -72,7 +99,10 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
                 input_ = chars[:, i] if teacher_forcing else prev_output
                 log_probs, prev_state = decoding_step(input_, prev_state, frame_lens_d, enc_h)
                 decoder_loss = decoder_loss + F.nll_loss(log_probs, labels[:, i], ignore_index=pad, reduction="sum")
-                prev_output = log_probs.exp().multinomial(1).squeeze(-1)
+                if sampling == "cpu":
+                    prev_output = log_probs.detach().cpu().exp().multinomial(1).squeeze(-1).to(device)
+                else:
+                    prev_output = log_probs.detach().exp().multinomial(1).squeeze(-1)
         decoder_loss = decoder_loss / n_tokens
 
         opt.zero_grad()
@@ -82,7 +112,7 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
             cur_ctc.backward()
             ctc_sum += cur_ctc.detach()
         if dist is not None:
-            dist.allreduce_grads(list(encoder.parameters()) + list(decoding_step.parameters()))
+            dist.allreduce_grads(params_all)
         if grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(encoder.parameters(), grad_norm)
             torch.nn.utils.clip_grad_norm_(decoding_step.parameters(), grad_norm)
@@ -99,11 +129,17 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
     return avg_decoder_loss, avg_ctc_loss
 
 
-def eval(encoder, decoding_step, data_loader, device, char2idx):
+def eval(encoder, decoding_step, data_loader, device, char2idx, sampling=None, details=None):
     """Teacher-forced decode; returns (decoder_loss, correct, count) like the reference (:89-143).
     `correct` comes from a multinomial sample of the decoder distribution, as in the reference, so
-    CER is stochastic unless the generator is seeded."""
+    CER is stochastic unless the generator is seeded: `sampling="cpu"` (or trainer.SAMPLING) draws the samples
+    on the host exactly as the reference does (see SAMPLING).  `details`, when a dict, additionally receives the
+    deterministic protocol: 'correct_argmax' (hits of the arg-max character) and 'samples' (list of (B,L) tensors)."""
     use_ctc = encoder.enable_ctc
+    sampling = sampling or SAMPLING
+    assert sampling in ("device", "cpu")
+    hit_argmax = torch.zeros((), dtype=torch.long, device=device)
+    all_samples = []
     encoder.eval()
     decoding_step.eval()
     pad = char2idx[PAD]
@@ -132,17 +168,34 @@ def eval(encoder, decoding_step, data_loader, device, char2idx):
                 log_probs, prev_state = decoding_step.forward_sequence(chars[:, :Lm], prev_state, frame_lens_d, enc_h)
                 flat, lab = log_probs.reshape(-1, log_probs.shape[-1]), labels[:, :Lm].reshape(-1)
                 decoder_loss += F.nll_loss(flat, lab, ignore_index=pad, reduction="sum")
-                sampled = flat.exp().multinomial(1).squeeze(-1)      # same distribution as the per-step draws
+                if sampling == "cpu":
+                    lp_h = log_probs.cpu()
+                    sampled = torch.stack([lp_h[:, i].exp().multinomial(1).squeeze(-1) for i in range(Lm)], 1)
+                    sampled = sampled.to(device).reshape(-1)
+                else:
+                    sampled = flat.exp().multinomial(1).squeeze(-1)      # same distribution as the per-step draws
                 correct += ((sampled == lab) & (lab != pad)).sum()
+                hit_argmax += ((flat.argmax(-1) == lab) & (lab != pad)).sum()
+                all_samples.append(sampled.reshape(batch_size, Lm))
             else:
+                step_samples = []
                 for i in range(Lm):
                     log_probs, prev_state = decoding_step(chars[:, i], prev_state, frame_lens_d, enc_h)
                     decoder_loss += F.nll_loss(log_probs, labels[:, i], ignore_index=pad, reduction="sum")
-                    sampled = log_probs.exp().multinomial(1).squeeze(-1)
+                    if sampling == "cpu":
+                        sampled = log_probs.cpu().exp().multinomial(1).squeeze(-1).to(device)
+                    else:
+                        sampled = log_probs.exp().multinomial(1).squeeze(-1)
                     correct += ((sampled == labels[:, i]) & (labels[:, i] != pad)).sum()
+                    hit_argmax += ((log_probs.argmax(-1) == labels[:, i]) & (labels[:, i] != pad)).sum()
+                    step_samples.append(sampled)
+                all_samples.append(torch.stack(step_samples, 1))
             count += int(ll_h.sum())
     encoder._t_max_hint = None
     count_t = torch.tensor(float(count), device=device)
+    if details is not None:
+        details["correct_argmax"] = hit_argmax
+        details["samples"] = all_samples
     return decoder_loss / count_t, correct, count_t
 
 
@@ -157,6 +210,11 @@ def train_ctc(encoder, data_loader, opt, device, char2idx=None, grad_norm=None, 
     encoder.train()
     total = torch.zeros((), device=device)
     n = 0
+    params = list(encoder.parameters())
+    # with a conv front-end, the recurrent layer's and the projection's gradients are complete while the front-end's
+    # backward (most of the step) still runs: they form the early all-reduce bucket
+    early = (list(encoder.rnn.parameters()) + list(encoder.output_proj.parameters())) \
+        if (dist is not None and hasattr(dist, "arm") and getattr(encoder, "frame_processing", "") == "conv3d") else None
     for frames, frame_lens, chars, char_lens in data_loader:
         fl_h, cl_h = frame_lens.cpu(), char_lens.cpu()
         ll_h = cl_h - 1
@@ -166,14 +224,22 @@ def train_ctc(encoder, data_loader, opt, device, char2idx=None, grad_norm=None, 
         encoder._t_max_hint = int(fl_h.max())
         log_probs, _, _ = encoder(frames, fl_d)
         loss = ctc_loss(log_probs, labels, fl_d, ll_h, "mean", device, host_lens=(fl_h, ll_h))
-        if loss is None:
-            continue
         opt.zero_grad(set_to_none=True)
+        if loss is None:
+            if dist is None:
+                continue
+            dist.allreduce_grads(params, valid=False)        # keep the collectives paired across ranks
+            if grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(params, grad_norm)
+            opt.step()
+            continue
+        if dist is not None and early:
+            dist.arm(early)                                  # recurrent + projection gradients reduce during conv backward
         loss.backward()
         if dist is not None:
-            dist.allreduce_grads(list(encoder.parameters()))
+            dist.allreduce_grads(params)
         if grad_norm is not None:
-            torch.nn.utils.clip_grad_norm_(encoder.parameters(), grad_norm)
+            torch.nn.utils.clip_grad_norm_(params, grad_norm)
         opt.step()
         total += loss.detach()
         n += 1

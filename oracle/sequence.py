@@ -70,7 +70,8 @@ def rnn_packed(x, lens, weights, rnn_type, bidirectional):
     weights: dict with torch-default names weight_ih_l0[_reverse], weight_hh_l0..., bias_*."""
     H = weights["weight_hh_l0"].shape[1]
     I = weights["weight_ih_l0"].shape[1]
-    rnn = getattr(torch.nn, rnn_type)(I, H, num_layers=1, bidirectional=bidirectional, batch_first=True)
+    with torch.random.fork_rng(devices=[]):        # the throw-away module's initialiser must not advance the generator
+        rnn = getattr(torch.nn, rnn_type)(I, H, num_layers=1, bidirectional=bidirectional, batch_first=True)
     sorted_lens, perm = lens.sort(0, descending=True)
     _, inv = perm.sort(0)
     packed = torch.nn.utils.rnn.pack_padded_sequence(x.index_select(0, perm), sorted_lens.cpu(), batch_first=True)

@@ -80,6 +80,64 @@ def test_one_train_step_matches_reference_golden(native_lib, cuda, path):
         check(k, v.cpu().numpy(), z["dec_after." + k])
 
 
+def _models_after(z, cuda):
+    enc, dec, c2i = _models(z, cuda)
+    enc.load_state_dict({k[10:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("enc_after.")})
+    dec.load_state_dict({k[10:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("dec_after.")})
+    return enc, dec, c2i
+
+
+@pytest.mark.parametrize("sequence_decode", [True, False])
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
+def test_eval_cer_protocol_matches_reference_golden(native_lib, cuda, path, sequence_decode, monkeypatch):
+    """Row a17, SURVEY §7's CER protocol: GPU log-probs, characters sampled on the host with the reference's seed
+    and call sequence (`sampling="cpu"`).  Golden: the unmodified reference's eval() after torch.manual_seed(SEED+2)
+    (tests/golden/make_golden_eval.py): decoder loss, `correct`, `count`, the sampled characters themselves, and
+    the deterministic arg-max hit count."""
+    from lipreading_b200 import trainer
+    monkeypatch.setattr(trainer, "SEQUENCE_DECODE", sequence_decode)
+    z, ze = np.load(path), np.load(path.replace("seq_", "eval_"))
+    enc, dec, c2i = _models_after(z, cuda)
+    batch = tuple(torch.from_numpy(z[k]) for k in ("frames", "frame_lens", "chars", "char_lens"))
+    torch.manual_seed(123456 + 2)
+    details = {}
+    loss, correct, count = trainer.eval(enc, dec, [batch], cuda, c2i, sampling="cpu", details=details)
+    assert int(count) == int(ze["eval_count"])
+    assert abs(float(loss) - float(ze["eval_dec_loss"])) < 1e-4
+    samples = details["samples"][0].cpu().numpy()
+    assert np.array_equal(samples, ze["eval_samples"][:, : samples.shape[1]])
+    assert int(correct) == int(ze["eval_correct"])
+    assert int(details["correct_argmax"]) == int(ze["eval_correct_argmax"])
+    cer = (float(count) - float(correct)) / float(count)              # train.py:248
+    assert cer == (int(ze["eval_count"]) - int(ze["eval_correct"])) / int(ze["eval_count"])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
+def test_teacher_forcing_half_train_step_matches_reference_golden(native_lib, cuda, path):
+    """train() with teacher_forcing_ratio=0.5 (the reference default is 0.9 decaying, train.py:161,275): which
+    positions are teacher forced (`torch.rand(1)`) and which characters are fed back (multinomial) come from the
+    host generator exactly as in the reference when `sampling="cpu"`."""
+    from lipreading_b200 import trainer
+    z, ze = np.load(path), np.load(path.replace("seq_", "eval_"))
+    enc, dec, c2i = _models_after(z, cuda)
+    batch = tuple(torch.from_numpy(z[k]) for k in ("frames", "frame_lens", "chars", "char_lens"))
+    torch.manual_seed(123456 + 3)
+    opt = torch.optim.Adam(list(enc.parameters()) + list(dec.parameters()), lr=1e-3)
+    d_loss, c_loss = trainer.train(enc, dec, [batch], opt, cuda, c2i, teacher_forcing_ratio=0.5, grad_norm=50,
+                                   sampling="cpu")
+    assert abs(d_loss - float(ze["tfr_dec_loss"])) < 1e-4
+    assert abs(c_loss - float(ze["tfr_ctc_loss"])) < 1e-4 * max(1.0, abs(float(ze["tfr_ctc_loss"])))
+
+    def check(name, got, ref):
+        diff = np.abs(got - ref)
+        assert diff.max() <= 2.1e-3, name
+        assert int((diff > 2e-4).sum()) <= max(2, int(5e-3 * diff.size)), (name, int((diff > 2e-4).sum()), diff.size)
+    for k, v in enc.state_dict().items():
+        check(k, v.cpu().numpy(), ze["enc_tfr." + k])
+    for k, v in dec.state_dict().items():
+        check(k, v.cpu().numpy(), ze["dec_tfr." + k])
+
+
 def test_eval_counts_and_checkpoint_roundtrip(native_lib, cuda, tmp_path):
     from lipreading_b200 import trainer
     from lipreading_b200.train_script import restore

@@ -146,3 +146,32 @@ def test_linear_rescaled_ctc_recursion_equals_log_space(T, L, seed):
     n32, g32, spread32 = O.ctc_linear_rescaled(lp.numpy(), tgt.numpy(), dtype=np.float32)
     assert abs(n32 - n_log) < 1e-4 * max(1.0, abs(n_log))
     assert np.abs(g32 - g_log).max() < 1e-4 and spread32 < 1e-4
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
+@pytest.mark.parametrize("tfr", [1.0, 0.5])
+def test_oracle_train_step_port_matches_golden(path, tfr):
+    """oracle/train_step.CpuReferenceTrain (bench.py's CPU arm for the ref-shape block) reproduces the unmodified
+    reference's train() step: teacher forcing 1 from seq_<case>.npz, teacher forcing 0.5 — with the reference's RNG
+    consumption (rand(1) + one multinomial per label position) — from eval_<case>.npz."""
+    from oracle import train_step as TS
+    z, rnn_type, H, bi, attn = _load(path)
+    ze = np.load(path.replace("seq_", "eval_"))
+    c2i = O.build_char2idx()
+    pre, seed = ("enc.", 123456 + 1) if tfr == 1.0 else ("enc_after.", 123456 + 3)
+    dpre = "dec." if tfr == 1.0 else "dec_after."
+    enc_state = {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre)}
+    dec = O.OracleDecoder(H * (2 if bi else 1), rnn_type, 10, 64, c2i, attention_type=attn)
+    dec.load_state_dict({k[len(dpre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(dpre)})
+    batch = tuple(torch.from_numpy(z[k]) for k in ("frames", "frame_lens", "chars", "char_lens"))
+    ref = TS.CpuReferenceTrain(enc_state, dec, rnn_type, c2i, lr=1e-3, grad_norm=50)
+    torch.manual_seed(seed)
+    d_loss, c_loss = ref.step(batch, teacher_forcing_ratio=tfr)
+    want_d, want_c = (z["train_dec_loss"], z["train_ctc_loss"]) if tfr == 1.0 else (ze["tfr_dec_loss"], ze["tfr_ctc_loss"])
+    assert abs(d_loss - float(want_d)) < 1e-5 and abs(c_loss - float(want_c)) < 1e-4
+    after = (lambda k: z["enc_after." + k]) if tfr == 1.0 else (lambda k: ze["enc_tfr." + k])
+    for k, p in ref.enc.items():
+        assert np.abs(p.detach().numpy() - after(k)).max() < 2e-5, k
+    dafter = (lambda k: z["dec_after." + k]) if tfr == 1.0 else (lambda k: ze["dec_tfr." + k])
+    for k, p in dec.state_dict().items():
+        assert np.abs(p.numpy() - dafter(k)).max() < 2e-5, k
