@@ -244,6 +244,13 @@ int lr_attn_fwd(const float* q, const float* enc, const int32_t* lens, int B, in
 int lr_attn_bwd(const float* q, const float* enc, const int32_t* lens, const float* weights,
                 const float* zsum, const float* d_ctx, int B, int L, int T, int H, float* d_q,
                 float* d_enc, void* stream);
+/* The same core with caller-supplied scores (B,L,T): the '1_layer_nn' / 'concat' score functions of
+ * better_model.py:204-221 (the reference's default is attention_type='1_layer_nn', src/scripts/train.py:151).
+ * Forward: masked softmax + context.  Backward: d_scores (B,L,T) and the context part of d_enc (B,T,H).        */
+int lr_attn_scores_fwd(const float* scores, const float* enc, const int32_t* lens, int B, int L, int T, int H,
+                       float* weights, float* zsum, float* ctx, void* stream);
+int lr_attn_scores_bwd(const float* enc, const int32_t* lens, const float* weights, const float* zsum,
+                       const float* d_ctx, int B, int L, int T, int H, float* d_scores, float* d_enc, void* stream);
 
 /* Orientation 3 only (default 1).  0: every MMA-issuing warp stacks inside its own run of frames — each accumulator
  * is written by one thread in program order (bit-reproducible), at the price of narrow ramp-up/ramp-down MMAs at

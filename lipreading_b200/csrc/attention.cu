@@ -23,6 +23,8 @@ struct AttnParams {
   const int32_t* lens;  // (B)
   int B, L, T, H;
   int enc_in_smem;
+  const float* ext_scores;   // (B,L,T) or null: scores computed by the caller ('1_layer_nn', 'concat') instead of q . enc
+  float* d_scores;           // backward of the above: (B,L,T) gradient w.r.t. the scores
 };
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
@@ -84,12 +86,16 @@ attn_fwd_kernel(AttnParams p, float* __restrict__ weights, float* __restrict__ z
   __syncthreads();
   for (int l0 = 0; l0 < p.L; l0 += kLB) {
     const int nl = min(kLB, p.L - l0);
-    for (int i = tid; i < kLB * H; i += kAttnThreads) {
-      const int j = i / H;
-      qs[i] = j < nl ? p.q[((size_t)b * p.L + l0 + j) * H + (i - j * H)] : 0.f;
+    if (p.ext_scores) {
+      for (int i = tid; i < nl * T; i += kAttnThreads) sc[i] = p.ext_scores[((size_t)b * p.L + l0) * T + i];
+    } else {
+      for (int i = tid; i < kLB * H; i += kAttnThreads) {
+        const int j = i / H;
+        qs[i] = j < nl ? p.q[((size_t)b * p.L + l0 + j) * H + (i - j * H)] : 0.f;
+      }
+      __syncthreads();
+      dots(e, qs, sc, T, H, nl);
     }
-    __syncthreads();
-    dots(e, qs, sc, T, H, nl);
     __syncthreads();
     for (int j = 0; j < nl; ++j) {
       float* s = sc + j * T;
@@ -183,11 +189,12 @@ attn_bwd_kernel(AttnParams p, const float* __restrict__ weights, const float* __
         const float ds = t < len ? w[t] * z * (g[t] - s2) : 0.f;
         g[t] = ds;
         DS[(size_t)(l0 + j) * T + t] = ds;
+        if (p.d_scores) p.d_scores[((size_t)b * L + l0 + j) * T + t] = ds;
       }
     }
     __syncthreads();
     // d_q rows: thread = hidden unit
-    for (int h = tid; h < H; h += kAttnThreads) {
+    for (int h = tid; p.q && h < H; h += kAttnThreads) {
       float acc[kLB];
 #pragma unroll
       for (int j = 0; j < kLB; ++j) acc[j] = 0.f;
@@ -212,7 +219,7 @@ attn_bwd_kernel(AttnParams p, const float* __restrict__ weights, const float* __
       for (int j = 0; j < LC; ++j) {
         const bool on = lc + j < L;
         dc[j] = on ? d_ctx[((size_t)b * L + lc + j) * H + h] : 0.f;
-        qv[j] = on ? p.q[((size_t)b * L + lc + j) * H + h] : 0.f;
+        qv[j] = (on && p.q) ? p.q[((size_t)b * L + lc + j) * H + h] : 0.f;
       }
       for (int t = 0; t < T; ++t) {
         float acc = 0.f;
@@ -236,11 +243,11 @@ size_t attn_smem(int L, int T, int H, bool bwd, bool stage) {
 
 }  // namespace
 
-extern "C" int lr_attn_fwd(const float* q, const float* enc, const int32_t* lens, int B, int L, int T, int H,
-                           float* weights, float* zsum, float* ctx, void* stream) {
-  LR_CHECK_ARG(q && enc && lens && weights && zsum && ctx, "lr_attn_fwd: null pointer");
+static int attn_fwd_launch(const float* q, const float* ext_scores, const float* enc, const int32_t* lens, int B, int L,
+                           int T, int H, float* weights, float* zsum, float* ctx, void* stream) {
+  LR_CHECK_ARG((q || ext_scores) && enc && lens && weights && zsum && ctx, "lr_attn_fwd: null pointer");
   LR_CHECK_ARG(B > 0 && L > 0 && T > 0 && H > 0, "lr_attn_fwd: bad shape");
-  AttnParams p{q, enc, lens, B, L, T, H, 0};
+  AttnParams p{q, enc, lens, B, L, T, H, 0, ext_scores, nullptr};
   p.enc_in_smem = attn_smem(L, T, H, false, true) <= 220 * 1024;
   const size_t smem = attn_smem(L, T, H, false, p.enc_in_smem);
   LR_CHECK_ARG(smem <= 220 * 1024, "lr_attn_fwd: T/H too large for the staging buffers");
@@ -250,12 +257,12 @@ extern "C" int lr_attn_fwd(const float* q, const float* enc, const int32_t* lens
   return LR_OK;
 }
 
-extern "C" int lr_attn_bwd(const float* q, const float* enc, const int32_t* lens, const float* weights,
+static int attn_bwd_launch(const float* q, const float* enc, const int32_t* lens, const float* weights,
                            const float* zsum, const float* d_ctx, int B, int L, int T, int H, float* d_q,
-                           float* d_enc, void* stream) {
-  LR_CHECK_ARG(q && enc && lens && weights && zsum && d_ctx && d_q && d_enc, "lr_attn_bwd: null pointer");
+                           float* d_scores, float* d_enc, void* stream) {
+  LR_CHECK_ARG(enc && lens && weights && zsum && d_ctx && d_enc && ((q && d_q) || d_scores), "lr_attn_bwd: null pointer");
   LR_CHECK_ARG(B > 0 && L > 0 && T > 0 && H > 0, "lr_attn_bwd: bad shape");
-  AttnParams p{q, enc, lens, B, L, T, H, 0};
+  AttnParams p{q, enc, lens, B, L, T, H, 0, nullptr, d_scores};
   p.enc_in_smem = attn_smem(L, T, H, true, true) <= 220 * 1024;
   const size_t smem = attn_smem(L, T, H, true, p.enc_in_smem);
   LR_CHECK_ARG(smem <= 220 * 1024, "lr_attn_bwd: L*T too large for the coefficient tables");
@@ -263,4 +270,33 @@ extern "C" int lr_attn_bwd(const float* q, const float* enc, const int32_t* lens
   attn_bwd_kernel<<<B, kAttnThreads, smem, lr_stream(stream)>>>(p, weights, zsum, d_ctx, d_q, d_enc);
   LR_CHECK_LAUNCH();
   return LR_OK;
+}
+
+extern "C" int lr_attn_fwd(const float* q, const float* enc, const int32_t* lens, int B, int L, int T, int H,
+                           float* weights, float* zsum, float* ctx, void* stream) {
+  LR_CHECK_ARG(q, "lr_attn_fwd: null pointer");
+  return attn_fwd_launch(q, nullptr, enc, lens, B, L, T, H, weights, zsum, ctx, stream);
+}
+
+extern "C" int lr_attn_bwd(const float* q, const float* enc, const int32_t* lens, const float* weights,
+                           const float* zsum, const float* d_ctx, int B, int L, int T, int H, float* d_q,
+                           float* d_enc, void* stream) {
+  LR_CHECK_ARG(q && d_q, "lr_attn_bwd: null pointer");
+  return attn_bwd_launch(q, enc, lens, weights, zsum, d_ctx, B, L, T, H, d_q, nullptr, d_enc, stream);
+}
+
+// Same attention core with the scores supplied by the caller — the '1_layer_nn' and 'concat' score functions of
+// better_model.py:204-221 are small Linear layers over [enc ; q] and are evaluated outside; masked softmax and the
+// context sums (forward), d_scores and the context part of d_enc (backward) run here.
+extern "C" int lr_attn_scores_fwd(const float* scores, const float* enc, const int32_t* lens, int B, int L, int T,
+                                  int H, float* weights, float* zsum, float* ctx, void* stream) {
+  LR_CHECK_ARG(scores, "lr_attn_scores_fwd: null pointer");
+  return attn_fwd_launch(nullptr, scores, enc, lens, B, L, T, H, weights, zsum, ctx, stream);
+}
+
+extern "C" int lr_attn_scores_bwd(const float* enc, const int32_t* lens, const float* weights, const float* zsum,
+                                  const float* d_ctx, int B, int L, int T, int H, float* d_scores, float* d_enc,
+                                  void* stream) {
+  LR_CHECK_ARG(d_scores, "lr_attn_scores_bwd: null pointer");
+  return attn_bwd_launch(nullptr, enc, lens, weights, zsum, d_ctx, B, L, T, H, nullptr, d_scores, d_enc, stream);
 }

@@ -365,31 +365,112 @@ __global__ void mouth_roi_kernel(const double* __restrict__ lmk, const int32_t* 
   reinterpret_cast<int4*>(roi)[n] = o;
 }
 
+// One CTA = `rows_per_cta` output rows of one frame.  The 2 source rows every output row samples are staged in
+// shared memory with aligned 16-byte loads (a row's ROI span is contiguous bytes: HBM sees whole sectors once, instead
+// of 12 scattered byte loads per output pixel), the per-column geometry (byte offsets of the two taps inside a staged
+// row, the fp32 weight) is computed once per CTA, and every tap is an LDS.  Arithmetic is bit-for-bit the spec above.
+// Shared layout: col_x0[out_w] | col_x1[out_w] (int32 byte offsets) | col_ax[out_w] | row bytes [2*rows][pitch].
 __global__ void __launch_bounds__(256)
 mouth_crop_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi,
-                  uint8_t* __restrict__ out, int H, int W, int out_h, int out_w) {
+                  uint8_t* __restrict__ out, int H, int W, int out_h, int out_w, int rows_per_cta, int pitch,
+                  long long total_bytes) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  int* col_x0 = reinterpret_cast<int*>(msm);
+  int* col_x1 = col_x0 + out_w;
+  float* col_ax = reinterpret_cast<float*>(col_x1 + out_w);
+  uint8_t* rows = msm + (((size_t)out_w * 12 + 15) & ~(size_t)15);
   const int n = blockIdx.y;
+  const int oy0 = blockIdx.x * rows_per_cta;
+  const int n_rows = min(rows_per_cta, out_h - oy0);
   const int4 r = reinterpret_cast<const int4*>(roi)[n];
-  const uint8_t* img = frames + (size_t)n * H * W * 3;
-  uint8_t* o = out + (size_t)n * out_h * out_w * 3;
+  const long long img_off = (long long)n * H * W * 3;
   const float sxs = (float)r.z / (float)out_w, sys = (float)r.w / (float)out_h;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < out_h * out_w;
-       i += gridDim.x * blockDim.x) {
-    int oy = i / out_w, ox = i - oy * out_w;
+  const int tid = threadIdx.x;
+
+  // source column range touched by this ROI (clamped like the taps), as a byte span of a frame row
+  const float sx_first = __fadd_rn(__fadd_rn(__fmul_rn(0.5f, sxs), -0.5f), (float)r.x);
+  const float sx_last = __fadd_rn(__fadd_rn(__fmul_rn((float)(out_w - 1) + 0.5f, sxs), -0.5f), (float)r.x);
+  const int xa = min(max((int)floorf(sx_first), 0), W - 1);
+  const int xb = min(max((int)floorf(sx_last) + 1, 0), W - 1);
+  const int span = (xb - xa + 1) * 3;                       // bytes of a row that any tap can touch
+  if (span + 32 > pitch) {
+    // ROI wider than the staging rows were sized for (a face filling the frame): direct taps from global memory
+    const uint8_t* img = frames + img_off;
+    uint8_t* od = out + ((size_t)n * out_h + oy0) * out_w * 3;
+    for (int i = tid; i < n_rows * out_w; i += blockDim.x) {
+      const int j = i / out_w, ox = i - j * out_w;
+      float sx = __fadd_rn(__fadd_rn(__fmul_rn((float)ox + 0.5f, sxs), -0.5f), (float)r.x);
+      float sy = __fadd_rn(__fadd_rn(__fmul_rn((float)(oy0 + j) + 0.5f, sys), -0.5f), (float)r.y);
+      float fx = floorf(sx), fy = floorf(sy);
+      float ax = sx - fx, ay = sy - fy;
+      int x0 = min(max((int)fx, 0), W - 1), x1 = min(max((int)fx + 1, 0), W - 1);
+      int y0 = min(max((int)fy, 0), H - 1), y1 = min(max((int)fy + 1, 0), H - 1);
+      const uint8_t* p00 = img + ((size_t)y0 * W + x0) * 3;
+      const uint8_t* p01 = img + ((size_t)y0 * W + x1) * 3;
+      const uint8_t* p10 = img + ((size_t)y1 * W + x0) * 3;
+      const uint8_t* p11 = img + ((size_t)y1 * W + x1) * 3;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float top = __fadd_rn(__fmul_rn(1.f - ax, (float)p00[ch]), __fmul_rn(ax, (float)p01[ch]));
+        float bot = __fadd_rn(__fmul_rn(1.f - ax, (float)p10[ch]), __fmul_rn(ax, (float)p11[ch]));
+        float val = __fadd_rn(__fmul_rn(1.f - ay, top), __fmul_rn(ay, bot));
+        od[(size_t)i * 3 + ch] = (uint8_t)fminf(fmaxf(rintf(val), 0.f), 255.f);
+      }
+    }
+    return;
+  }
+
+  for (int ox = tid; ox < out_w; ox += blockDim.x) {
     float sx = __fadd_rn(__fadd_rn(__fmul_rn((float)ox + 0.5f, sxs), -0.5f), (float)r.x);
-    float sy = __fadd_rn(__fadd_rn(__fmul_rn((float)oy + 0.5f, sys), -0.5f), (float)r.y);
-    float fx = floorf(sx), fy = floorf(sy);
-    float ax = sx - fx, ay = sy - fy;
+    float fx = floorf(sx);
     int x0 = min(max((int)fx, 0), W - 1), x1 = min(max((int)fx + 1, 0), W - 1);
-    int y0 = min(max((int)fy, 0), H - 1), y1 = min(max((int)fy + 1, 0), H - 1);
-    const uint8_t* p00 = img + ((size_t)y0 * W + x0) * 3;
-    const uint8_t* p01 = img + ((size_t)y0 * W + x1) * 3;
-    const uint8_t* p10 = img + ((size_t)y1 * W + x0) * 3;
-    const uint8_t* p11 = img + ((size_t)y1 * W + x1) * 3;
+    col_x0[ox] = (x0 - xa) * 3;
+    col_x1[ox] = (x1 - xa) * 3;
+    col_ax[ox] = sx - fx;
+  }
+  // stage source rows: slot 2*j = y0 of output row oy0+j, slot 2*j+1 = y1.  Each slot starts at the 16-byte aligned
+  // address at or below the row's first byte; `lead` (same for all threads of a row) is added at read time.
+  for (int slot = tid >> 5; slot < 2 * n_rows; slot += (blockDim.x >> 5)) {
+    const int oy = oy0 + (slot >> 1);
+    float sy = __fadd_rn(__fadd_rn(__fmul_rn((float)oy + 0.5f, sys), -0.5f), (float)r.y);
+    int fy = (int)floorf(sy);
+    int y = min(max(fy + (slot & 1), 0), H - 1);
+    const long long first = img_off + ((long long)y * W + xa) * 3;
+    const long long base = first & ~15LL;
+    const int n_chunks = (int)((first - base + span + 15) >> 4);
+    uint4* dst = reinterpret_cast<uint4*>(rows + (size_t)slot * pitch);
+    for (int c = threadIdx.x & 31; c < n_chunks; c += 32) {
+      const long long a = base + 16LL * c;
+      if (a + 16 <= total_bytes) {
+        dst[c] = *reinterpret_cast<const uint4*>(frames + a);
+      } else {                                               // last partial chunk of the whole frames buffer
+        uint8_t* d8 = reinterpret_cast<uint8_t*>(dst + c);
+        for (int e = 0; e < 16; ++e) d8[e] = (a + e < total_bytes) ? frames[a + e] : (uint8_t)0;
+      }
+    }
+  }
+  __syncthreads();
+
+  uint8_t* o = out + ((size_t)n * out_h + oy0) * out_w * 3;
+  const int n_px = n_rows * out_w;
+  for (int i = tid; i < n_px; i += blockDim.x) {
+    const int j = i / out_w, ox = i - j * out_w;
+    const int oy = oy0 + j;
+    float sy = __fadd_rn(__fadd_rn(__fmul_rn((float)oy + 0.5f, sys), -0.5f), (float)r.y);
+    float fyf = floorf(sy);
+    const float ay = sy - fyf;
+    const int fy = (int)fyf;
+    const int y0 = min(max(fy, 0), H - 1), y1 = min(max(fy + 1, 0), H - 1);
+    const int lead0 = (int)((img_off + ((long long)y0 * W + xa) * 3) & 15);
+    const int lead1 = (int)((img_off + ((long long)y1 * W + xa) * 3) & 15);
+    const uint8_t* r0 = rows + (size_t)(2 * j) * pitch + lead0;
+    const uint8_t* r1 = rows + (size_t)(2 * j + 1) * pitch + lead1;
+    const int b0 = col_x0[ox], b1 = col_x1[ox];
+    const float ax = col_ax[ox];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      float top = __fadd_rn(__fmul_rn(1.f - ax, (float)p00[ch]), __fmul_rn(ax, (float)p01[ch]));
-      float bot = __fadd_rn(__fmul_rn(1.f - ax, (float)p10[ch]), __fmul_rn(ax, (float)p11[ch]));
+      float top = __fadd_rn(__fmul_rn(1.f - ax, (float)r0[b0 + ch]), __fmul_rn(ax, (float)r0[b1 + ch]));
+      float bot = __fadd_rn(__fmul_rn(1.f - ax, (float)r1[b0 + ch]), __fmul_rn(ax, (float)r1[b1 + ch]));
       float val = __fadd_rn(__fmul_rn(1.f - ay, top), __fmul_rn(ay, bot));
       val = fminf(fmaxf(rintf(val), 0.f), 255.f);
       o[(size_t)i * 3 + ch] = (uint8_t)val;
@@ -459,8 +540,17 @@ extern "C" int lr_mouth_crop(const uint8_t* frames, const double* lmk, const int
   cudaStream_t st = lr_stream(stream);
   mouth_roi_kernel<<<lr_div_up(N, 128), 128, 0, st>>>(lmk, rect_pad, roi, N, out_h, out_w);
   LR_CHECK_LAUNCH();
-  dim3 grid(lr_div_up(out_h * out_w, 256), N);
-  mouth_crop_kernel<<<grid, 256, 0, st>>>(frames, roi, out, H, W, out_h, out_w);
+  // staged-row geometry.  The ROI is data dependent (it lives on the device), so the rows are sized for mouths up to
+  // 512 source pixels wide (a mouth is ~1/3 of a face box); wider ROIs take the kernel's direct path.  16 bytes of
+  // alignment lead + 16 of tail per staged row; 10 output rows (20 staged rows, ~31 KB) per CTA -> 7 CTAs per SM.
+  const int pitch = (((W < 512 ? W : 512) * 3 + 15) & ~15) + 32;
+  const size_t head = ((size_t)out_w * 12 + 15) & ~(size_t)15;
+  const int rows_per_cta = 10;
+  const size_t smem = head + (size_t)2 * rows_per_cta * pitch;
+  LR_CHECK_ARG(smem <= 48 * 1024, "lr_mouth_crop: out_w = %d too wide for the column tables", out_w);
+  dim3 grid(lr_div_up(out_h, rows_per_cta), N);
+  mouth_crop_kernel<<<grid, 256, smem, st>>>(frames, roi, out, H, W, out_h, out_w, rows_per_cta, pitch,
+                                             (long long)N * H * W * 3);
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

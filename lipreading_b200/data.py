@@ -244,30 +244,41 @@ COPY_STREAMS = 1      # host->device copy streams of DevicePrefetcher (LR_H2D_ST
 
 
 class DevicePrefetcher:
-    """Iterate a loader of HOST batches one step ahead: the (large) frames tensor of batch i+1 is
-    copied host->device on a side stream while batch i computes.  Lengths and captions stay on the
+    """Iterate a loader of HOST batches `depth - 1` steps ahead: the (large) frames tensor of a later batch is
+    copied host->device on a side stream while earlier batches compute.  Lengths and captions stay on the
     host (the trainer wants them there).  Use pinned host tensors for truly asynchronous copies.
 
-    The device side is a ring of two persistent buffers (re-allocated only when a batch's shape
+    The device side is a ring of `depth` persistent buffers (re-allocated only when a batch's shape
     changes), so the steady state makes no allocator calls: the copy into slot k waits, on the side
     stream, for the event recorded when the consumer asked for the batch after the one that last
-    used slot k (i.e. all work reading the slot has been enqueued)."""
+    used slot k (i.e. all work reading the slot has been enqueued).
 
-    def __init__(self, loader, device, copy_streams=None):
+    depth = 3 (two batches in flight): a copy can only START once the work that last read its slot has finished
+    on the GPU, so with two slots its window is one step — enough on an idle host link (55 GB/s: 5 ms for a
+    288 MB batch of clips against a 13 ms step), not when eight ranks share the host (24 GB/s measured on the
+    four GPUs behind the busier root port: 12 ms plus contention stretched the step to 21.7 ms).  A third slot
+    doubles the window."""
+
+    def __init__(self, loader, device, copy_streams=None, depth=None):
         self.loader, self.device = loader, torch.device(device)
         # the big tensor is split along the batch axis over this many copy streams: one cudaMemcpyAsync keeps a single
         # copy engine busy, several in flight let the link's other engines work too
         if copy_streams is None:
             copy_streams = int(os.environ.get("LR_H2D_STREAMS", COPY_STREAMS))
         self.copy_streams = max(1, int(copy_streams))
+        if depth is None:
+            depth = int(os.environ.get("LR_PREFETCH_DEPTH", 3))
+        self.depth = max(2, int(depth))
 
     def __len__(self):
         return len(self.loader)
 
     def __iter__(self):
+        import collections
         sides = [torch.cuda.Stream(self.device) for _ in range(self.copy_streams)]
-        slots = [None, None]            # device buffers
-        released = [None, None]         # event: consumer is done enqueueing work on the slot
+        depth = self.depth
+        slots = [None] * depth          # device buffers
+        released = [None] * depth       # event: consumer is done enqueueing work on the slot
 
         def stage(batch, k):
             src = batch[0]
@@ -294,17 +305,23 @@ class DevicePrefetcher:
             return buf, evs, batch[1:]
 
         it = iter(self.loader)
-        try:
-            nxt = stage(next(it), 0)
-        except StopIteration:
-            return
-        i = 0
-        while nxt is not None:
-            frames, ev, rest = nxt
-            try:
-                nxt = stage(next(it), (i + 1) & 1)
-            except StopIteration:
-                nxt = None
+        queue = collections.deque()     # staged batches, oldest first
+        n_staged = 0
+
+        def fill():
+            nonlocal n_staged
+            while len(queue) < depth - 1:
+                try:
+                    batch = next(it)
+                except StopIteration:
+                    return
+                queue.append((n_staged % depth, stage(batch, n_staged % depth)))
+                n_staged += 1
+
+        fill()
+        while queue:
+            k, (frames, ev, rest) = queue.popleft()
+            fill()                       # keep depth-1 copies in flight behind the batch handed out now
             cur = torch.cuda.current_stream(self.device)
             for e in ev:
                 cur.wait_event(e)
@@ -312,5 +329,4 @@ class DevicePrefetcher:
             # the consumer came back for the next batch: everything that reads `frames` is enqueued
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(self.device))
-            released[i & 1] = done
-            i += 1
+            released[k] = done

@@ -24,9 +24,62 @@ def env_world():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def _gpu_numa_node(local_rank):
+    """NUMA node of the GPU `local_rank` drives (sysfs), or None when the platform does not say (one-node VMs)."""
+    try:
+        import subprocess
+        bdf = subprocess.check_output(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id",
+                                       "--format=csv,noheader"], text=True, timeout=20).strip().lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (its threads and its future allocations — the pinned staging buffers of the loader above all)
+    to the NUMA node of its GPU.  With eight ranks on a two-socket host the default first-touch placement puts half
+    of the pinned batches on the far socket, and their host->device copies then cross the socket interconnect.
+    Returns the node, or None when nothing was done (single node, no sysfs, LR_NUMA_BIND=0)."""
+    if os.environ.get("LR_NUMA_BIND", "1") == "0":
+        return None
+    node = _gpu_numa_node(local_rank)
+    if node is None:
+        return None
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = _parse_cpulist(fh.read()) & os.sched_getaffinity(0)
+        if not cpus or not os.path.isdir("/sys/devices/system/node/node1"):
+            return None
+        os.sched_setaffinity(0, cpus)
+        import ctypes
+        mask = ctypes.c_ulong(1 << node)
+        # set_mempolicy(MPOL_PREFERRED = 1): allocate on the GPU's node, fall back elsewhere when it is full
+        ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+        return node
+    except Exception:
+        return None
+
+
 def init(backend=None):
     """Initialise torch.distributed from the torchrun environment; returns (rank, local_rank, world)."""
     rank, local_rank, world = env_world()
+    if world > 1 and torch.cuda.is_available():
+        bind_to_gpu_numa(local_rank)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")

@@ -106,6 +106,43 @@ class _AttnContext(torch.autograd.Function):
         return d_q, d_enc, None
 
 
+class _AttnContextScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, enc, lens):
+        N.require_cuda(scores, enc, lens)
+        scores, enc = N.cont(scores, torch.float32), N.cont(enc, torch.float32)
+        lens32 = N.cont(lens, torch.int32)
+        B, L, T = scores.shape
+        H = enc.shape[2]
+        assert enc.shape[0] == B and enc.shape[1] == T
+        w = torch.empty((B, L, T), dtype=torch.float32, device=enc.device)
+        z = torch.empty((B, L), dtype=torch.float32, device=enc.device)
+        c = torch.empty((B, L, H), dtype=torch.float32, device=enc.device)
+        N.check(N.lib().lr_attn_scores_fwd(N.ptr(scores), N.ptr(enc), N.ptr(lens32), B, L, T, H, N.ptr(w), N.ptr(z),
+                                           N.ptr(c), N.stream()), "lr_attn_scores_fwd")
+        ctx.save_for_backward(enc, lens32, w, z)
+        ctx.mark_non_differentiable(w)
+        return c, w
+
+    @staticmethod
+    def backward(ctx, d_c, _d_w):
+        enc, lens32, w, z = ctx.saved_tensors
+        B, L, T = w.shape
+        H = enc.shape[2]
+        d_c = N.cont(d_c, torch.float32)
+        d_scores = torch.empty_like(w)
+        d_enc = torch.empty_like(enc)
+        N.check(N.lib().lr_attn_scores_bwd(N.ptr(enc), N.ptr(lens32), N.ptr(w), N.ptr(z), N.ptr(d_c), B, L, T, H,
+                                           N.ptr(d_scores), N.ptr(d_enc), N.stream()), "lr_attn_scores_bwd")
+        return d_scores, d_enc, None
+
+
+def attn_context_scores(scores, enc, lens):
+    """The attention core with caller-computed scores (B,L,T) — '1_layer_nn' / 'concat' (better_model.py:204-223):
+    allennlp masked softmax over t < len, context = weights @ enc.  -> (context (B,L,H), weights (B,L,T))."""
+    return _AttnContextScores.apply(scores, enc, lens)
+
+
 def attn_context(q, enc, lens):
     """Dot-product attention of L queries per clip over the clip's encoder states with allennlp's masked softmax
     (better_model.py:195-223): q (B,L,H), enc (B,T,H), lens (B) -> (context (B,L,H), weights (B,L,T))."""

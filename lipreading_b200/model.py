@@ -212,24 +212,25 @@ class CharDecodingStep(nn.Module):
         enc = encoder_hidden_states
         Te = enc.shape[1]
         if self.attention_type != "none":
-            if self.attention_type in ("dot", "general") and enc.is_cuda:
+            H = self.hidden_size
+            if self.attention_type in ("dot", "general"):
                 qq = q if self.attention_type == "dot" else self.attn_proj_general(q)
                 context, _ = LF.attn_context(qq, enc, encoder_lens)
             else:
-                if self.attention_type == "dot":
-                    scores = torch.einsum("bth,blh->blt", enc, q)
-                elif self.attention_type == "general":
-                    scores = torch.einsum("bth,blh->blt", enc, self.attn_proj_general(q))
+                # score functions over [enc ; q] (better_model.py:204-221): the Linear over the concatenation splits
+                # into an encoder part — evaluated ONCE per clip, not once per label position — and a query part
+                if self.attention_type == "1_layer_nn":
+                    w = self.attn_proj_1_layer_nn.weight                       # (1, 2H)
+                    s_enc = enc @ w[0, :H]                                       # (B,Te)
+                    s_q = q @ w[0, H:] + self.attn_proj_1_layer_nn.bias          # (B,L)
+                    scores = s_enc.unsqueeze(1) + s_q.unsqueeze(2)
                 else:
-                    both = torch.cat([enc.unsqueeze(1).expand(-1, L, -1, -1), q.unsqueeze(2).expand(-1, -1, Te, -1)], dim=3)
-                    if self.attention_type == "1_layer_nn":
-                        scores = self.attn_proj_1_layer_nn(both).squeeze(-1)
-                    else:
-                        scores = self.attn_proj_layer2(self.attn_proj_layer1(both).tanh()).squeeze(-1)
-                valid = (torch.arange(Te, device=inputs.device).unsqueeze(0) < encoder_lens.unsqueeze(1)).float().unsqueeze(1)
-                w = F.softmax(scores * valid, dim=-1) * valid            # allennlp masked_softmax
-                w = w / (w.sum(dim=-1, keepdim=True) + 1e-13)
-                context = torch.bmm(w, enc)
+                    w1 = self.attn_proj_layer1.weight                            # (A, 2H)
+                    p_enc = enc @ w1[:, :H].t()                                  # (B,Te,A)
+                    p_q = q @ w1[:, H:].t() + self.attn_proj_layer1.bias         # (B,L,A)
+                    hid = (p_enc.unsqueeze(1) + p_q.unsqueeze(2)).tanh()         # (B,L,Te,A)
+                    scores = (hid @ self.attn_proj_layer2.weight[0]) + self.attn_proj_layer2.bias
+                context, _ = LF.attn_context_scores(scores, enc, encoder_lens)
             q = self.concat_layer(torch.cat([context, q], dim=2)).tanh()
         log_mask = (self.output_mask.to(q.device) + 1e-45).log()
         return _proj_log_softmax(q, self.output_proj, log_mask), final_state

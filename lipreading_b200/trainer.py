@@ -81,17 +81,42 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
             enc_h, prev_state = encoder(frames, frame_lens_d)
         prev_output = torch.full((batch_size,), char2idx[BOS], dtype=torch.long, device=device)
 
-        if teacher_forcing_ratio >= 1 and SEQUENCE_DECODE and hasattr(decoding_step, "forward_sequence"):
-            log_probs, prev_state = decoding_step.forward_sequence(chars[:, :max_label_len], prev_state, frame_lens_d, enc_h)
+        if SEQUENCE_DECODE and hasattr(decoding_step, "forward_sequence"):
+            # Segmented decode.  Which positions are teacher forced is decided up front (one `torch.rand(1)` per
+            # position, as in the reference); a maximal run of positions whose INPUTS are known — a sampled
+            # character followed by teacher-forced ones — is one vectorised pass (`forward_sequence`: one RNN call,
+            # one attention launch, one projection launch), chained through the recurrent state.  With every step
+            # teacher forced that is a single pass; at the reference's default ratio of 0.9 about L/10 + 1 passes
+            # instead of L.  Same arithmetic as the step loop: the recurrent state never depends on the attention
+            # output (better_model.py:184,223-229), and a position's log-probs depend on earlier positions only
+            # through that state and the fed character.
+            forced, noise = [], []
+            for i in range(max_label_len):
+                forced.append(bool(torch.rand(1) < teacher_forcing_ratio))
+                if sampling == "cpu":
+                    # the reference's multinomial(1) of position i = argmax(p / q) with q ~ Exp(1) drawn here, in
+                    # the reference's order (ATen's single-sample path), so the host generator stays in step
+                    noise.append(torch.empty(batch_size, decoding_step.vocab_size).exponential_(1))
+            parts, i = [], 0
+            while i < max_label_len:
+                j = i + 1
+                while j < max_label_len and forced[j]:
+                    j += 1
+                inputs = chars[:, i:j]
+                if not forced[i]:
+                    inputs = torch.cat([prev_output.unsqueeze(1), inputs[:, 1:]], dim=1)
+                log_probs, prev_state = decoding_step.forward_sequence(inputs, prev_state, frame_lens_d, enc_h)
+                parts.append(log_probs)
+                if j < max_label_len:                              # position j is fed the character sampled at j-1
+                    last = log_probs[:, -1].detach()
+                    if sampling == "cpu":
+                        prev_output = (last.cpu().exp() / noise[j - 1]).argmax(-1).to(device)
+                    else:
+                        prev_output = last.exp().multinomial(1).squeeze(-1)
+                i = j
+            log_probs = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
             decoder_loss = F.nll_loss(log_probs.reshape(-1, log_probs.shape[-1]), labels[:, :max_label_len].reshape(-1),
                                       ignore_index=pad, reduction="sum")
-            if sampling == "cpu":
-                # leave the host generator where the reference leaves it: per position one rand(1) and one (B,V)
-                # multinomial draw (their values feed nothing when every step is teacher forced)
-                lp_h = log_probs.detach().cpu()
-                for i in range(max_label_len):
-                    torch.rand(1)
-                    lp_h[:, i].exp().multinomial(1)
         else:
             decoder_loss = 0
             for i in range(max_label_len):

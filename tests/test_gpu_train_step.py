@@ -112,12 +112,14 @@ def test_eval_cer_protocol_matches_reference_golden(native_lib, cuda, path, sequ
     assert cer == (int(ze["eval_count"]) - int(ze["eval_correct"])) / int(ze["eval_count"])
 
 
+@pytest.mark.parametrize("sequence_decode", [True, False])       # segmented vectorised decode / the reference's step loop
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[4:-4] for p in CASES])
-def test_teacher_forcing_half_train_step_matches_reference_golden(native_lib, cuda, path):
+def test_teacher_forcing_half_train_step_matches_reference_golden(native_lib, cuda, path, sequence_decode, monkeypatch):
     """train() with teacher_forcing_ratio=0.5 (the reference default is 0.9 decaying, train.py:161,275): which
     positions are teacher forced (`torch.rand(1)`) and which characters are fed back (multinomial) come from the
     host generator exactly as in the reference when `sampling="cpu"`."""
     from lipreading_b200 import trainer
+    monkeypatch.setattr(trainer, "SEQUENCE_DECODE", sequence_decode)
     z, ze = np.load(path), np.load(path.replace("seq_", "eval_"))
     enc, dec, c2i = _models_after(z, cuda)
     batch = tuple(torch.from_numpy(z[k]) for k in ("frames", "frame_lens", "chars", "char_lens"))

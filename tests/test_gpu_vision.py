@@ -97,20 +97,28 @@ def test_collate_pad(native_lib, cuda):
     assert torch.equal(out.reshape(ref.shape), ref)
 
 
-def test_mouth_crop_matches_spec(native_lib, cuda):
+@pytest.mark.parametrize("H,W,out_h,out_w,wide", [(360, 480, 50, 100, False), (181, 243, 100, 50, False),
+                                                  (720, 1280, 100, 50, True), (97, 131, 50, 100, False)])
+def test_mouth_crop_matches_spec(native_lib, cuda, H, W, out_h, out_w, wide):
+    """bit-exact against the numpy spec: staged-row path, odd frame sizes (unaligned rows, partial last chunk of the
+    buffer), ROIs hanging off every frame edge, and ROIs wider than the staging rows (direct path)."""
     from lipreading_b200 import functional as LF
     rng = np.random.default_rng(5)
-    H, W, n = 360, 480, 4
+    n = 6
     frames = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
     lmk = rng.random((n, 68, 3)) * 100.0
-    lmk[:, 48:68, 0] = 60 + rng.random((n, 20)) * 70
-    lmk[:, 48:68, 1] = 90 + rng.random((n, 20)) * 30
-    rp = np.array([[100, 300, 50, 250], [0, 200, 0, 200], [300, 479, 200, 359], [5, 100, 5, 100]], dtype=np.int32)
+    span = 0.55 * W if wide else 0.15 * W
+    lmk[:, 48:68, 0] = 0.12 * W + rng.random((n, 20)) * span
+    lmk[:, 48:68, 1] = 0.25 * H + rng.random((n, 20)) * 0.08 * H
+    rp = np.zeros((n, 4), dtype=np.int32)
+    rp[:, 0] = [int(0.2 * W), 0, int(0.62 * W), 5, -int(0.2 * W), int(0.3 * W)]       # left pad: ROI off the right / left edge
+    rp[:, 2] = [int(0.1 * H), 0, int(0.55 * H), 5, -int(0.3 * H), int(0.7 * H)]       # top pad: off the bottom / top edge
+    rp[:, 1], rp[:, 3] = rp[:, 0] + W // 2, rp[:, 2] + H // 2
     out, roi = LF.mouth_crop(torch.from_numpy(frames).to(cuda), torch.from_numpy(lmk).to(cuda),
-                             torch.from_numpy(rp).to(cuda), 50, 100)
+                             torch.from_numpy(rp).to(cuda), out_h, out_w)
     out, roi = out.cpu().numpy(), roi.cpu().numpy()
     for i in range(n):
-        r_ref = V.mouth_roi(lmk[i], rp[i], 50, 100)
+        r_ref = V.mouth_roi(lmk[i], rp[i], out_h, out_w)
         assert tuple(roi[i]) == r_ref
-        ref = V.mouth_crop(frames[i], r_ref, 50, 100)
-        assert np.array_equal(out[i], ref), int(np.abs(out[i].astype(int) - ref.astype(int)).max())
+        ref = V.mouth_crop(frames[i], r_ref, out_h, out_w)
+        assert np.array_equal(out[i], ref), (i, int(np.abs(out[i].astype(int) - ref.astype(int)).max()))
