@@ -15,13 +15,28 @@ def _to_host(t):
     return t.detach().to("cpu", torch.int64) if torch.is_tensor(t) else torch.as_tensor(t, dtype=torch.int64)
 
 
-def ctc_loss(encoder_outputs, labels, frame_lens, label_lens, reduction, device, host_lens=None):
+def feasible_on_host(labels_h, frame_lens_h, label_lens_h):
+    """Which samples have a finite CTC likelihood — decided from the lengths and labels alone: an alignment exists
+    iff T >= L + (number of adjacent equal labels), and with log-softmax inputs every existing alignment has a
+    finite log-probability.  This is exactly the set the reference finds by probing `torch.isinf(loss)` after the
+    fact (ctc_loss.py:87), known here BEFORE any kernel runs, so the wrapper needs no device->host read."""
+    L = labels_h.shape[1]
+    pos = torch.arange(L).unsqueeze(0)
+    same = (labels_h[:, 1:] == labels_h[:, :-1]) & (pos[:, 1:] < label_lens_h.unsqueeze(1)) if L > 1 else \
+        torch.zeros((labels_h.shape[0], 0), dtype=torch.bool)
+    return frame_lens_h >= label_lens_h + same.sum(1)
+
+
+def ctc_loss(encoder_outputs, labels, frame_lens, label_lens, reduction, device, host_lens=None, host_labels=None):
     """encoder_outputs (B,T,V+1) log-probs on the GPU, labels (B,Lmax) char ids WITHOUT the +1 shift
     (chars[:,1:]), frame_lens / label_lens (B,).  Returns a scalar tensor carrying grad, or None
     (whole batch unusable) exactly where the reference returns None.
 
     host_lens=(frame_lens_cpu, label_lens_cpu) lets the caller skip the device->host copy of the two
-    length vectors (the data loader has them on the host anyway)."""
+    length vectors (the data loader has them on the host anyway).  host_labels (the labels on the host, which the
+    loader has too) additionally removes the wrapper's only device->host read: feasibility — what the reference
+    probes with isinf after the fact — is then decided up front (`feasible_on_host`), so the host never waits for
+    the forward pass and keeps enqueueing a step ahead of the device."""
     assert reduction in ("mean", "sum")
     fl_h, ll_h = (host_lens if host_lens is not None else (_to_host(frame_lens), _to_host(label_lens)))
     fl_h, ll_h = fl_h.to(torch.int64), ll_h.to(torch.int64)
@@ -37,6 +52,8 @@ def ctc_loss(encoder_outputs, labels, frame_lens, label_lens, reduction, device,
         kd = keep.to(dev)
         encoder_outputs, labels = encoder_outputs.index_select(0, kd), labels.index_select(0, kd)
         fl_h, ll_h = fl_h.index_select(0, keep), ll_h.index_select(0, keep)
+        if host_labels is not None:
+            host_labels = host_labels.index_select(0, keep)
     n = fl_h.numel()
 
     # one launch for every sample of the batch; class 0 is the blank (labels + 1, ctc_loss.py:80)
@@ -75,6 +92,11 @@ def ctc_loss(encoder_outputs, labels, frame_lens, label_lens, reduction, device,
         coef_d = coef.to(dev, non_blocking=True)
         # infeasible samples carry coefficient 0; mask their +inf so 0*inf never appears
         return (torch.where(coef_d > 0, nll, torch.zeros_like(nll)) * coef_d).sum()
+
+    if host_labels is not None:
+        # feasibility known a priori: exact coefficients, no device->host read at all
+        ok = feasible_on_host(host_labels.to(torch.int64), fl_h, ll_h)
+        return reduce(None if bool(ok.all()) else ok)
 
     # fast path: assume every sample is feasible, verify with ONE small device->host read (the
     # reference's torch.isinf(loss) / total_loss == 0 probes, ctc_loss.py:87,110)

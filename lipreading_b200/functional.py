@@ -236,6 +236,8 @@ class _RNNLayer(torch.autograd.Function):
         b_ih = torch.cat([weights[4 * d + 2] for d in range(D)], 0)
         w_hh = torch.stack([weights[4 * d + 1] for d in range(D)], 0).contiguous()   # (D,G*H,H)
         b_hh = torch.stack([weights[4 * d + 3] for d in range(D)], 0).contiguous()
+        if GEMM_DTYPE != torch.float32:
+            w_ih = _lowp(w_ih)            # converted while contiguous (a .to() of the transposed view is a strided copy)
         gi = _mm(x2, w_ih.t(), bias=b_ih)                                       # plain GEMM -> cuBLAS
         lens32 = N.cont(lens, torch.int32)
         dev = x.device

@@ -65,7 +65,8 @@ def train(encoder, decoding_step, data_loader, opt, device, char2idx,
         encoder._t_max_hint = int(fl_h.max())
         if use_ctc:
             enc_out, enc_h, prev_state = encoder(frames, frame_lens_d)
-            cur_ctc = ctc_loss(enc_out, labels, frame_lens_d, ll_h, "mean", device, host_lens=(fl_h, ll_h))
+            cur_ctc = ctc_loss(enc_out, labels, frame_lens_d, ll_h, "mean", device, host_lens=(fl_h, ll_h),
+                               host_labels=chars_h[:, 1:])
             if cur_ctc is None:
                 # the reference skips the batch (train_better_model.py:41-42).  Under data parallelism the other
                 # ranks are about to all-reduce: join them with zero gradients so the collectives stay paired
@@ -241,14 +242,16 @@ def train_ctc(encoder, data_loader, opt, device, char2idx=None, grad_norm=None, 
     early = (list(encoder.rnn.parameters()) + list(encoder.output_proj.parameters())) \
         if (dist is not None and hasattr(dist, "arm") and getattr(encoder, "frame_processing", "") == "conv3d") else None
     for frames, frame_lens, chars, char_lens in data_loader:
-        fl_h, cl_h = frame_lens.cpu(), char_lens.cpu()
+        fl_h, cl_h, chars_h = frame_lens.cpu(), char_lens.cpu(), chars.cpu()
         ll_h = cl_h - 1
         frames = frames.to(device, non_blocking=True)
         labels = chars.to(device, non_blocking=True)[:, 1:]
         fl_d = fl_h.to(device, non_blocking=True)
         encoder._t_max_hint = int(fl_h.max())
         log_probs, _, _ = encoder(frames, fl_d)
-        loss = ctc_loss(log_probs, labels, fl_d, ll_h, "mean", device, host_lens=(fl_h, ll_h))
+        # (labels and lengths are on the host already: the wrapper decides feasibility there and never reads the
+        # device, so the host keeps enqueueing a step ahead of the GPU)
+        loss = ctc_loss(log_probs, labels, fl_d, ll_h, "mean", device, host_lens=(fl_h, ll_h), host_labels=chars_h[:, 1:])
         opt.zero_grad(set_to_none=True)
         if loss is None:
             if dist is None:
