@@ -49,16 +49,16 @@ uint64_t    lr_launch_count(void);
  * nll (B) f32 = -log p(target|input), +inf when infeasible.
  * grad (B,T,C) f32 or NULL: d nll_b / d log_probs with torch's native-CTC convention
  *   exp(lp) - exp(log(alpha*beta summed per class) + nll - lp), zero for t >= input_len.     */
-size_t lr_ctc_workspace(int B, int T, int C, int Lmax);
-/* 0 (default): warp-per-clip kernels for large batches (>= 1024 clips) whose lattice fits shared
+/* `kernel` (per call, same value for lr_ctc_workspace and lr_ctc_fwd_bwd):
+ * 0 (default): warp-per-clip kernels for large batches (>= 1024 clips) whose lattice fits shared
  * memory, else CTA-per-clip.  Among the warp kernels, labels of <= 31 symbols run the linear-space
  * (per-frame rescaled) recursion first and the log-space kernel only on the clips that one flags
  * (underflow / infeasible).  1: always CTA-per-clip; 2: log-space warp-per-clip whenever it fits;
  * 3: warp-per-clip whenever it fits, linear-space first (2, 3: test hooks).                          */
-void lr_ctc_select_kernel(int force_block);
+size_t lr_ctc_workspace(int B, int T, int C, int Lmax, int kernel);
 int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets, const int32_t* input_lens,
                    const int32_t* target_lens, int B, int T, int C, int Lmax,
-                   float* nll, float* grad, void* workspace, size_t ws_bytes, void* stream);
+                   float* nll, float* grad, void* workspace, size_t ws_bytes, int kernel, void* stream);
 /* Greedy CTC decode for the inference stream (semantics of src/models/lipreader/decoder.py:165-197):
  * arg-max per frame, collapse repeats, drop blank.  tokens (B,T) i32 zero padded, out_lens (B).   */
 int lr_ctc_greedy_decode(const float* log_probs, const int32_t* lens, int B, int T, int C,
@@ -71,19 +71,18 @@ int lr_scale_rows(const float* in, const float* scale, float* out, int B, int64_
 /* replaces: src/models/lipreader/better_model.py:92-93 (nn.Linear + allennlp masked_log_softmax).
  * hidden (M,K) f32, weight (C,K) f32, bias (C) f32, log_mask (C) f32 additive term
  * (log(mask+1e-45)); out log_probs (M,C) f32.                                                */
+/* `variant` (per call): 0 = fp32 SIMT kernel (the parity path); 1 = 3xTF32 tensor-core kernel (mma.sync, W resident
+ * in shared memory) whenever C <= 68, K % 16 == 0 and K <= 688 — 1.2x faster, 3e-5 instead of 1e-5 from the exact
+ * logits (legacy TF32 mma.sync on sm_100: slow, and its accumulator adds do not round to nearest).               */
 int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, const float* bias,
                            const float* log_mask, float* log_probs, int M, int K, int C,
-                           void* stream);
+                           int variant, void* stream);
 /* grad_lp (M,C) upstream; writes d_logits (M,C) = g - softmax*sum(g), d_bias (C) (zeroed by the
  * call), and d_hidden (M,K) = d_logits @ weight, d_weight (C,K) = d_logits^T @ hidden (zeroed by
  * the call).                                                                                 */
 int lr_proj_logsoftmax_bwd(const float* grad_lp, const float* log_probs, const float* hidden,
                            const float* weight, float* d_logits, float* d_hidden,
                            float* d_weight, float* d_bias, int M, int K, int C, void* stream);
-/* Forward kernel choice: 0 (default) = fp32 SIMT kernel; 1 = 3xTF32 tensor-core kernel (mma.sync, W resident in
- * shared memory) whenever C <= 68, K % 16 == 0 and K <= 688 — 1.2x faster, 3e-5 instead of 1e-5 from the exact
- * logits (legacy TF32 mma.sync on sm_100: slow, and its accumulator adds do not round to nearest).               */
-void lr_proj_select_kernel(int use_tc);
 
 /* -------- a12/a13: (bi)directional recurrent layer, packed-sequence semantics ------------ */
 /* replaces: src/models/lipreader/better_model.py:64-89 (sort -> pack -> nn.{LSTM,GRU,RNN} ->
@@ -252,36 +251,9 @@ int lr_attn_scores_fwd(const float* scores, const float* enc, const int32_t* len
 int lr_attn_scores_bwd(const float* enc, const int32_t* lens, const float* weights, const float* zsum,
                        const float* d_ctx, int B, int L, int T, int H, float* d_scores, float* d_enc, void* stream);
 
-/* Orientation 3 only (default 1).  0: every MMA-issuing warp stacks inside its own run of frames — each accumulator
- * is written by one thread in program order (bit-reproducible), at the price of narrow ramp-up/ramp-down MMAs at
- * both ends of every run.  1 (layers with >= 32 input channels per group): the chunks of a work item form one list shared out between the issuing warps, every
- * input plane is multiplied once with the widest window it has; the KT-1 frames at a hand-over point receive MMAs
- * from two threads, so their fp32 summation order (not the set of terms) depends on timing.                    */
-void lr_conv3d_set_seam(int on);
-
-/* -------- diagnostics ------------------------------------------------------------------------ */
-/* SM cycles for `iters` back-to-back tcgen05.mma of one shape with operands resident in shared memory
- * (tools/umma_table.py): the measured per-instruction cost that tile-orientation choices are based on.
- * Synchronous (the only entry point that is).                                                    */
-/* Device buffer (148*8 int64, or NULL to stop) that subsequent lr_conv3d_fwd launches fill with the
- * cycles each warp role spent waiting on its barriers (tools/conv_waits.py).                      */
-void lr_conv3d_set_debug(long long* device_buffer);
-/* Diagnostics only (results become wrong): bit 0 skips the epilogue work, bit 1 loads each weight stage once,
- * bit 2 loads each input chunk set once — shows which role limits a layer (tools/conv_waits.py --skip). */
-void lr_conv3d_set_debug_skip(int mask);
-long long lr_umma_microbench(int M, int N, int row_bytes_a, int row_bytes_b, int a_major, int b_major,
-                             int n_acc, int a_tiles, int iters, int a_shift_rows, void* stream);
-
-/* Same, for a trip of 8 MMAs (M = 128, K-major 64-byte rows) with individual N, accumulator column and B row-group
- * offsets: what differently shaped MMAs on overlapping accumulator ranges cost (tools/umma_pattern.py);
- * commit_every > 0 adds a tcgen05.commit after every that many MMAs (multiple of 8).             */
-long long lr_umma_pattern_bench(const int* n, const int* dcol, const int* bblk, int iters, int commit_every,
-                                void* stream);
-
-/* Cycles for tiles*n_ops*KS MMAs (M = 128, K-major 64-byte rows) issued by ONE thread of a `threads`-thread block
- * from a loop whose descriptors advance by loop-carried adds (variant 0) or stay constant (variant 1). */
-long long lr_umma_issue_bench(int N, int KS, int tiles, int n_ops, int a_step_bytes, int d_step, int threads,
-                              int variant, void* stream);
+/* No entry point of this header keeps state between calls: kernel variants are chosen per call (`kernel`, `variant`,
+ * the flag bits of `swap`).  The measurement hooks and micro-benchmarks live in include/lr_b200_diag.h and are
+ * compiled into a separate liblr_b200_diag.so.                                                                  */
 
 #ifdef __cplusplus
 }

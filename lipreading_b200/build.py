@@ -15,6 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "liblr_b200.so")
+DIAG_LIB = os.path.join(HERE, "liblr_b200_diag.so")      # product objects + csrc/diag/*.cu, hooks enabled (-DLR_DIAG)
+DIAG_HOOKED = ("conv3d_sm100.cu",)                         # sources that carry #ifdef LR_DIAG measurement hooks
 STAMP = os.path.join(HERE, ".liblr_b200.stamp")
 
 NVCC_FLAGS = [
@@ -36,10 +38,16 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def diag_sources():
+    d = os.path.join(CSRC, "diag")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu")) if os.path.isdir(d) else []
+
+
 def _digest():
     h = hashlib.sha256()
-    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    files = sources() + diag_sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files.append(os.path.join(INCLUDE, "lr_b200.h"))
+    files.append(os.path.join(INCLUDE, "lr_b200_diag.h"))
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:
@@ -51,7 +59,7 @@ def _digest():
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into liblr_b200.so; returns the library path."""
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+    if not force and os.path.exists(LIB) and os.path.exists(DIAG_LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
                 return LIB
@@ -59,20 +67,29 @@ def build(force=False, verbose=False):
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
-    for src in sources():
-        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc(), "-c", src, "-o", obj, "-I", INCLUDE] + [f for f in NVCC_FLAGS if f != "--shared"]
-        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+    jobs = [(src, os.path.join(build_dir, os.path.basename(src)[:-3] + ".o"), [], "product") for src in sources()]
+    jobs += [(src, os.path.join(build_dir, "diag_" + os.path.basename(src)[:-3] + ".o"), ["-DLR_DIAG"], "diag")
+             for src in sources() if os.path.basename(src) in DIAG_HOOKED] + \
+            [(src, os.path.join(build_dir, "diag_" + os.path.basename(src)[:-3] + ".o"), ["-DLR_DIAG"], "diag")
+             for src in diag_sources()]
+    for src, obj, extra, kind in jobs:
+        cmd = [_nvcc(), "-c", src, "-o", obj, "-I", INCLUDE] + flags + extra
+        procs.append((src, obj, kind, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
-    for src, obj, p in procs:
+    diag_objs = []
+    for src, obj, kind, p in procs:
         out, _ = p.communicate()
-        log.append("== %s\n%s" % (os.path.basename(src), out))
+        log.append("== %s (%s)\n%s" % (os.path.basename(src), kind, out))
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError("nvcc failed on %s" % src)
-        objs.append(obj)
-    cmd = [_nvcc(), "--shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
-    subprocess.run(cmd, check=True)
+        (objs if kind == "product" else diag_objs).append(obj)
+    arch = ["-gencode", "arch=compute_100a,code=sm_100a"]
+    subprocess.run([_nvcc(), "--shared", "-o", LIB] + objs + arch, check=True)
+    # the diagnostics library: the hooked sources recompiled with -DLR_DIAG replace their product objects
+    hooked = {os.path.join(build_dir, n[:-3] + ".o") for n in DIAG_HOOKED}
+    subprocess.run([_nvcc(), "--shared", "-o", DIAG_LIB] + [o for o in objs if o not in hooked] + diag_objs + arch, check=True)
     with open(os.path.join(build_dir, "ptxas.log"), "w") as fh:
         fh.write("\n".join(log))
     with open(STAMP, "w") as fh:

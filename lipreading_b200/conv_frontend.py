@@ -125,7 +125,7 @@ KERNEL_TIMING = None
 # conv orientation (see lr_b200.h): 0 = one MMA per tap, 1 = channels on the MMA M lanes, 3 = the KT kt-taps of a
 # spatial tap stacked on N (input plane c x [W(kt=KT-1);..;W(kt=0)] -> accumulators of frames c-KT+1..c)
 SWAP = 3
-# False (default): the MMA-issuing warps of the conv kernel share one chunk list per work item (lr_conv3d_set_seam(1),
+# False (default): the MMA-issuing warps of the conv kernel share one chunk list per work item (without the LR_CONV_SINGLE_WRITER flag,
 # ~15 % fewer tensor-pipe cycles on conv2's input gradient); the frames at a hand-over point are then summed in a
 # timing-dependent order.  True: every accumulator has a single writer -> bit-reproducible runs.
 DETERMINISTIC = False
@@ -155,7 +155,8 @@ def conv3d_native(x, w, bias, y, argmax, B, T, H, W, Hp, Wp, Cin, CG, Cout, K, e
     if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.lib().lr_conv3d_set_seam(0 if (DETERMINISTIC or torch.are_deterministic_algorithms_enabled()) else 1)
+    if DETERMINISTIC or torch.are_deterministic_algorithms_enabled():
+        mode |= 0x100                              # LR_CONV_SINGLE_WRITER: per-call flag bit of `swap`
     if epi_mode == 2:
         N.check(N.lib().lr_conv3d_dgrad_unpool(N.ptr(x), N.ptr(w), N.ptr(argmax), N.ptr(y), N.ptr(d_bias), B, T, H, W,
                                                Hp, Wp, Cin, CG, Cout, K[0], K[1], K[2], ovol[0], ovol[1], ovol[2],

@@ -876,14 +876,18 @@ unpool_kernel(const __nv_bfloat16* __restrict__ d_pooled, const uint8_t* __restr
 
 }  // namespace
 
+#ifdef LR_DIAG
+// liblr_b200_diag.so only (include/lr_b200_diag.h): measurement hooks with process-global state
 static long long* g_conv_dbg = nullptr;
 static int g_conv_skip = 0;
-static int g_conv_seam = 1;
-extern "C" void lr_conv3d_set_seam(int on) { g_conv_seam = on; }
 extern "C" void lr_conv3d_set_debug_skip(int mask) { g_conv_skip = mask; }
 // diagnostics: device buffer of 148*8 int64 that the next conv launches fill with per-role wait cycles
 // [producer a_empty, producer w_empty, mma acc_empty, mma a_full, mma w_full, epilogue acc_full, -, mma total]
 extern "C" void lr_conv3d_set_debug(long long* device_buffer) { g_conv_dbg = device_buffer; }
+#else
+static long long* const g_conv_dbg = nullptr;
+static const int g_conv_skip = 0;
+#endif
 
 extern "C" int lr_conv3d_supported(void) {
   int dev = 0;
@@ -979,6 +983,8 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
   LR_CHECK_ARG(p.CH <= 256, "lr_conv3d_fwd: halo too large for one TMA box (CH=%d)", p.CH);
   p.row_bytes = Cin * 2;
   p.chunk_bytes = (p.CH * p.row_bytes + 1023) / 1024 * 1024;
+  const int single_writer = (swap >> 8) & 1;   // LR_CONV_SINGLE_WRITER: every accumulator written by one thread
+  swap &= 0xff;
   const int mode = swap;                       // 0 positions on M, 1 swapped, 2 kx-stacked
   LR_CHECK_ARG(mode >= 0 && mode <= 3, "lr_conv3d_fwd: orientation must be 0, 1, 2 or 3");
   swap = mode == 1;
@@ -1042,7 +1048,7 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
     // (not for 32-byte rows: conv1's one-k-step MMAs are bound by shared-memory bandwidth, not by the pipe, and the
     // unequal chunk shares made it 5 % slower — measured)
     const bool seam_ok = G > 1 && (KT < J ? KT : J) * Cout <= 256;
-    p.seam = g_conv_seam && seam_ok && Cin >= 32;
+    p.seam = !single_writer && seam_ok && Cin >= 32;
     if (getenv("LR_CONV_SEAM")) p.seam = atoi(getenv("LR_CONV_SEAM")) != 0 && seam_ok && (Cin >= 32 || atoi(getenv("LR_CONV_SEAM")) > 1);
   }
   p.n_sets = n_sets;

@@ -17,8 +17,8 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-int lr_ctc_force_block_kernel = 0;   // 0 auto (by batch size), 1 always CTA-per-clip, 2 always log-space warp-per-clip,
-                                     // 3 always warp-per-clip with the linear-space kernel first (labels <= 31 symbols)
+// kernel choice is a per-call argument (`kernel`): 0 auto (by batch size), 1 always CTA-per-clip, 2 always log-space
+// warp-per-clip, 3 always warp-per-clip with the linear-space kernel first (labels <= 31 symbols)
 
 namespace {
 
@@ -744,7 +744,7 @@ int warp_kernel_pairs(int Lmax) {
   const int S = 2 * Lmax + 1;
   return S <= 64 ? 1 : (S <= 128 ? 2 : (S <= 256 ? 4 : 0));
 }
-bool warp_kernel_chosen(int B, int T, int C, int Lmax) {
+bool warp_kernel_chosen(int B, int T, int C, int Lmax, int lr_ctc_force_block_kernel) {
   const int P = warp_kernel_pairs(Lmax);
   // the linear-space kernel (labels <= 31 symbols, <= 96 classes) beats the CTA-per-clip kernel from a few dozen clips
   // on (50 vs 74 us at B = 256, measured); the log-space warp kernel only pays off once the SMs are full
@@ -811,12 +811,10 @@ extern "C" int lr_ctc_greedy_decode(const float* log_probs, const int32_t* lens,
   return LR_OK;
 }
 
-extern "C" void lr_ctc_select_kernel(int force_block) { lr_ctc_force_block_kernel = force_block; }
-
-extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
+extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax, int kernel) {
   if (B <= 0 || T <= 0 || C <= 0 || Lmax < 0) return 0;
   if (Lmax == 0) Lmax = 1;
-  if (warp_kernel_chosen(B, T, C, Lmax))               // alpha lattice of the warp-per-clip kernel: [B][T][64*P] f32
+  if (warp_kernel_chosen(B, T, C, Lmax, kernel))       // alpha lattice of the warp-per-clip kernel: [B][T][64*P] f32
     return (size_t)B * T * 64 * warp_kernel_pairs(Lmax) * sizeof(float) + (size_t)B * sizeof(int32_t);   // + redo flags
   CtcPlan p = make_plan(T, C, Lmax);
   if (p.lat_in_smem) return 16;
@@ -826,7 +824,8 @@ extern "C" size_t lr_ctc_workspace(int B, int T, int C, int Lmax) {
 extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
                               const int32_t* input_lens, const int32_t* target_lens, int B, int T,
                               int C, int Lmax, float* nll, float* grad, void* workspace,
-                              size_t ws_bytes, void* stream) {
+                              size_t ws_bytes, int kernel, void* stream) {
+  const int lr_ctc_force_block_kernel = kernel;      // per-call choice (0 auto), see lr_b200.h
   LR_CHECK_ARG(log_probs && targets && input_lens && target_lens && nll,
                "lr_ctc_fwd_bwd: null pointer");
   LR_CHECK_ARG(B > 0 && T > 0 && C > 1 && Lmax >= 0, "lr_ctc_fwd_bwd: bad shape B=%d T=%d C=%d L=%d",
@@ -836,7 +835,7 @@ extern "C" int lr_ctc_fwd_bwd(const float* log_probs, const int32_t* targets,
   // clip maximises clips in flight per SM (throughput); with few clips the CTA-per-clip kernel (alpha and beta on two
   // warps, 4-warp gradient) has the shorter critical path.  With a workspace for the lattice it runs the global-alpha
   // variant (32 clips per SM instead of 9).
-  if (warp_kernel_chosen(B, T, C, Lmax)) {
+  if (warp_kernel_chosen(B, T, C, Lmax, kernel)) {
     const int P = warp_kernel_pairs(Lmax);
     const size_t ws_need = (size_t)B * T * 64 * P * sizeof(float);
     const int ga = (grad && workspace && ws_bytes >= ws_need) ? 1 : 0;

@@ -1,7 +1,7 @@
 // umma_microbench.cu — measures the issue-to-retire cost of back-to-back tcgen05.mma of a given shape
 // on this GPU (operands resident in shared memory, one accumulator or a ring of accumulators).  Used to
 // choose tile orientation / N per layer from measurement instead of the nominal rate (tools/umma_table.py).
-#include "tcgen05.cuh"
+#include "../tcgen05.cuh"
 #include <string.h>
 
 using namespace lr_tc;

@@ -278,7 +278,6 @@ proj_logsoftmax_fwd_tc_kernel(const float* __restrict__ hidden, const float* __r
   }
 }
 
-int lr_proj_use_tc = 0;          // lr_proj_select_kernel: 1 = the 3xTF32 tensor-core forward where it applies (default: fp32 SIMT)
 
 // ---------------------------------------------------------------------------------------------
 // backward 1: d_logits = g - softmax * sum_c(g); d_bias partial sums (one warp per row)
@@ -393,7 +392,8 @@ proj_bwd_dweight_kernel(const float* __restrict__ d_logits, const float* __restr
 
 extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, const float* bias,
                                       const float* log_mask, float* log_probs, int M, int K, int C,
-                                      void* stream) {
+                                      int variant, void* stream) {
+  const int lr_proj_use_tc = variant == 1;
   LR_CHECK_ARG(hidden && weight && bias && log_mask && log_probs, "lr_proj_logsoftmax_fwd: null");
   LR_CHECK_ARG(M > 0 && K > 0 && C > 0 && C <= kMaxC, "lr_proj_logsoftmax_fwd: need 0<C<=%d (C=%d)",
                kMaxC, C);
@@ -418,7 +418,6 @@ extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, 
   return LR_OK;
 }
 
-extern "C" void lr_proj_select_kernel(int use_tc) { lr_proj_use_tc = use_tc; }
 
 extern "C" int lr_proj_logsoftmax_bwd(const float* grad_lp, const float* log_probs,
                                       const float* hidden, const float* weight, float* d_logits,

@@ -16,6 +16,11 @@ def _ws(nbytes, device):
 # ------------------------------------------------------------------------------------------------
 # a15: CTC
 # ------------------------------------------------------------------------------------------------
+# per-call kernel choices handed to the C-ABI (see include/lr_b200.h); 0 = the library's own choice / the parity path
+CTC_KERNEL = 0        # 1 CTA-per-clip, 2 log-space warp-per-clip, 3 linear-space warp kernel first (tests walk all of them)
+PROJ_VARIANT = 0      # 1 = 3xTF32 tensor-core forward
+
+
 class _CTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, log_probs, targets, input_lens, target_lens):
@@ -32,9 +37,9 @@ class _CTC(torch.autograd.Function):
         need_grad = log_probs.requires_grad
         grad = torch.empty_like(lp) if need_grad else None
         L = N.lib()
-        ws = _ws(L.lr_ctc_workspace(B, T, C, Lmax), lp.device)
+        ws = _ws(L.lr_ctc_workspace(B, T, C, Lmax, CTC_KERNEL), lp.device)
         N.check(L.lr_ctc_fwd_bwd(N.ptr(lp), N.ptr(tg), N.ptr(il), N.ptr(tl), B, T, C, Lmax,
-                                 N.ptr(nll), N.ptr(grad), N.ptr(ws), ws.numel(), N.stream()),
+                                 N.ptr(nll), N.ptr(grad), N.ptr(ws), ws.numel(), CTC_KERNEL, N.stream()),
                 "lr_ctc_fwd_bwd")
         ctx.unit_grad = grad
         return nll
@@ -163,7 +168,7 @@ class _ProjLogSoftmax(torch.autograd.Function):
         C = w.shape[0]
         out = torch.empty((M, C), dtype=torch.float32, device=h2.device)
         N.check(N.lib().lr_proj_logsoftmax_fwd(N.ptr(h2), N.ptr(w), N.ptr(b), N.ptr(lm), N.ptr(out),
-                                               M, K, C, N.stream()), "lr_proj_logsoftmax_fwd")
+                                               M, K, C, PROJ_VARIANT, N.stream()), "lr_proj_logsoftmax_fwd")
         ctx.save_for_backward(h2, w, out)
         ctx.in_shape = shp
         return out.reshape(shp[:-1] + (C,))

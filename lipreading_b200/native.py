@@ -28,20 +28,12 @@ SIGNATURES = {
     "lr_abi_version": (_i, []),
     "lr_last_error": (ctypes.c_char_p, []),
     "lr_launch_count": (_u64, []),
-    "lr_ctc_workspace": (_sz, [_i, _i, _i, _i]),
-    "lr_conv3d_set_debug": (None, [_vp]),
-    "lr_umma_microbench": (ctypes.c_longlong, [_i] * 10 + [_vp]),
-    "lr_umma_pattern_bench": (ctypes.c_longlong, [_vp, _vp, _vp, _i, _i, _vp]),
-    "lr_umma_issue_bench": (ctypes.c_longlong, [_i] * 8 + [_vp]),
-    "lr_conv3d_set_debug_skip": (None, [_i]),
-    "lr_conv3d_set_seam": (None, [_i]),
-    "lr_ctc_select_kernel": (None, [_i]),
-    "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "lr_ctc_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "lr_ctc_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "lr_ctc_greedy_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lr_scale_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
-    "lr_proj_logsoftmax_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lr_proj_logsoftmax_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "lr_proj_logsoftmax_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "lr_proj_select_kernel": (None, [_i]),
     "lr_rnn_saved_per_unit": (_i, [_i]),
     "lr_rnn_workspace": (_sz, [_i, _i, _i, _i, _i]),
     "lr_rnn_fwd": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -59,6 +51,25 @@ SIGNATURES = {
     "lr_attn_scores_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lr_attn_scores_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
+
+
+# include/lr_b200_diag.h — measurement hooks and micro-benchmarks, only in liblr_b200_diag.so (tools/ use them)
+DIAG_LIB_PATH = os.path.join(_HERE, "liblr_b200_diag.so")
+DIAG_SIGNATURES = {
+    "lr_conv3d_set_debug": (None, [_vp]),
+    "lr_conv3d_set_debug_skip": (None, [_i]),
+    "lr_umma_microbench": (ctypes.c_longlong, [_i] * 10 + [_vp]),
+    "lr_umma_pattern_bench": (ctypes.c_longlong, [_vp, _vp, _vp, _i, _i, _vp]),
+    "lr_umma_issue_bench": (ctypes.c_longlong, [_i] * 8 + [_vp]),
+}
+
+
+def use_diag_lib():
+    """tools/ only: make lib() load the diagnostics build (same entry points + the hooks of lr_b200_diag.h)."""
+    global LIB_PATH, _lib
+    assert _lib is None, "call use_diag_lib() before the first native.lib()"
+    LIB_PATH = DIAG_LIB_PATH
+    SIGNATURES.update(DIAG_SIGNATURES)
 
 
 def lib():

@@ -33,9 +33,10 @@ def _relerr(a, b):
 def ctc_kernel(request, native_lib):
     """All CTC kernels: log-space warp-per-clip, CTA-per-clip (any size), and the linear-space warp kernel (labels of
     <= 31 symbols; longer labels and flagged clips fall through to the log-space warp kernel)."""
-    native_lib.lr_ctc_select_kernel({"cta_per_clip": 1, "warp_per_clip": 2, "linear_warp": 3}[request.param])
+    from lipreading_b200 import functional as LF
+    LF.CTC_KERNEL = {"cta_per_clip": 1, "warp_per_clip": 2, "linear_warp": 3}[request.param]   # per-call `kernel` argument
     yield request.param
-    native_lib.lr_ctc_select_kernel(0)
+    LF.CTC_KERNEL = 0
 
 
 @pytest.mark.parametrize("B,T,C,Lmax", [(7, 20, 65, 8), (3, 75, 65, 30), (2, 300, 65, 120), (1, 5, 65, 1),
@@ -91,7 +92,7 @@ def test_ctc_infeasible_is_inf_and_zero_grad(native_lib, cuda, ctc_kernel):
 @pytest.mark.parametrize("M,K", [(300, 512), (75, 256), (1000, 1400), (33, 64), (2500, 512)])
 def test_proj_masked_log_softmax(native_lib, cuda, M, K, tc):
     from lipreading_b200 import functional as LF
-    native_lib.lr_proj_select_kernel(tc)
+    LF.PROJ_VARIANT = tc                           # per-call `variant` argument
     g = torch.Generator().manual_seed(7)
     c2i = O.build_char2idx()
     C = len(c2i) + 1
@@ -109,7 +110,7 @@ def test_proj_masked_log_softmax(native_lib, cuda, M, K, tc):
         (out * up.to(cuda)).sum().backward()
         torch.cuda.synchronize()
     finally:
-        native_lib.lr_proj_select_kernel(0)
+        LF.PROJ_VARIANT = 0
     assert float((out.cpu() - ref.detach()).abs().max()) < 1e-4
     # against float64: fp32 SIMT ~1e-5; 3xTF32 ~3e-5 (tensor-core accumulator adds do not round to nearest; a single
     # TF32 pass would be ~1e-3 here)

@@ -4,7 +4,9 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
-from lipreading_b200 import conv_frontend as CF, native as N  # noqa: E402
+from lipreading_b200 import native as N  # noqa: E402
+N.use_diag_lib()          # the hooks live in liblr_b200_diag.so only
+from lipreading_b200 import conv_frontend as CF  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 SKIPS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
@@ -36,7 +38,7 @@ def wrapped(*a, **k):
 
 CF.conv3d_native = wrapped
 import ctypes
-skipf = ctypes.CDLL(N.LIB_PATH).lr_conv3d_set_debug_skip
+skipf = ctypes.CDLL(N.DIAG_LIB_PATH).lr_conv3d_set_debug_skip
 for sk in SKIPS:
     print("== skip mask %d (1 epilogue, 2 weight reloads, 4 input reloads), orientation %s" % (sk, CF.SWAP))
     skipf(sk)

@@ -18,7 +18,7 @@ for B in [int(a) for a in sys.argv[1:]] or [256, 4096, 16384]:
     tl = torch.randint(10, 31, (B,), generator=g).to(dev).int()
     res = {}
     for name, sel in (("cta", 1), ("log_warp", 2), ("linear_warp", 3)):
-        N.lib().lr_ctc_select_kernel(sel)
+        LF.CTC_KERNEL = sel
         for _ in range(3):
             nll = LF.ctc_nll(lp, tg, il, tl)
         torch.cuda.synchronize()
@@ -33,7 +33,7 @@ for B in [int(a) for a in sys.argv[1:]] or [256, 4096, 16384]:
             ts.append(a.elapsed_time(b))
         ts.sort()
         res[name] = (ts[len(ts) // 2], nll.detach().clone())
-    N.lib().lr_ctc_select_kernel(0)
+    LF.CTC_KERNEL = 0
     byts = B * 2 * T * C * 4
     print("B=%d " % B + "  ".join("%s %.1f us (%.0f GB/s)" % (k, v[0] * 1e3, byts / v[0] / 1e6) for k, v in res.items()) +
           "  max|nll_lin - nll_log| = %.2e" % float((res["linear_warp"][1] - res["log_warp"][1]).abs().max()))

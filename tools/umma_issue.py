@@ -8,7 +8,7 @@ import torch  # noqa: E402
 from lipreading_b200 import native  # noqa: E402
 
 native.lib()
-f = ctypes.CDLL(native.LIB_PATH).lr_umma_issue_bench
+f = ctypes.CDLL(native.DIAG_LIB_PATH).lr_umma_issue_bench
 f.restype = ctypes.c_longlong
 f.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
 torch.zeros(1, device="cuda")

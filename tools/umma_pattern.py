@@ -11,7 +11,7 @@ import torch  # noqa: E402
 from lipreading_b200 import native  # noqa: E402
 
 native.lib()
-f = ctypes.CDLL(native.LIB_PATH).lr_umma_pattern_bench
+f = ctypes.CDLL(native.DIAG_LIB_PATH).lr_umma_pattern_bench
 f.restype = ctypes.c_longlong
 I8 = ctypes.c_int * 8
 f.argtypes = [I8, I8, I8, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
