@@ -73,10 +73,16 @@ int lr_scale_rows(const float* in, const float* scale, float* out, int B, int64_
  * (log(mask+1e-45)); out log_probs (M,C) f32.                                                */
 /* `variant` (per call): 0 = fp32 SIMT kernel (the parity path); 1 = 3xTF32 tensor-core kernel (mma.sync, W resident
  * in shared memory) whenever C <= 68, K % 16 == 0 and K <= 688 — 1.2x faster, 3e-5 instead of 1e-5 from the exact
- * logits (legacy TF32 mma.sync on sm_100: slow, and its accumulator adds do not round to nearest).               */
+ * logits (legacy TF32 mma.sync on sm_100: slow, and its accumulator adds do not round to nearest);
+ * 2 = tcgen05 kind::tf32 kernel (TMA ring, TMEM accumulator, register-local row softmax): the throughput path,
+ * TF32 products (1e-3 relative on the logits), needs lr_proj_tc5_supported(M, K, C).                             */
 int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, const float* bias,
                            const float* log_mask, float* log_probs, int M, int K, int C,
                            int variant, void* stream);
+int lr_proj_tc5_supported(int M, int K, int C);
+/* The log-softmax half of the backward alone: d_logits (M,C) = g - softmax*sum(g), d_bias (C) = its column sums. */
+int lr_logsoftmax_bwd(const float* grad_lp, const float* log_probs, float* d_logits, float* d_bias, int M, int C,
+                      void* stream);
 /* grad_lp (M,C) upstream; writes d_logits (M,C) = g - softmax*sum(g), d_bias (C) (zeroed by the
  * call), and d_hidden (M,K) = d_logits @ weight, d_weight (C,K) = d_logits^T @ hidden (zeroed by
  * the call).                                                                                 */

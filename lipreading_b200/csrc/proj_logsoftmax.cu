@@ -390,11 +390,16 @@ proj_bwd_dweight_kernel(const float* __restrict__ d_logits, const float* __restr
 
 }  // namespace
 
+// tf32 tensor-core variant (proj_tc5.cu)
+int lr_proj_logsoftmax_fwd_tc5(const float* hidden, const float* weight, const float* bias, const float* log_mask,
+                               float* log_probs, int M, int K, int C, void* stream);
+
 extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, const float* bias,
                                       const float* log_mask, float* log_probs, int M, int K, int C,
                                       int variant, void* stream) {
   const int lr_proj_use_tc = variant == 1;
   LR_CHECK_ARG(hidden && weight && bias && log_mask && log_probs, "lr_proj_logsoftmax_fwd: null");
+  if (variant == 2) return lr_proj_logsoftmax_fwd_tc5(hidden, weight, bias, log_mask, log_probs, M, K, C, stream);
   LR_CHECK_ARG(M > 0 && K > 0 && C > 0 && C <= kMaxC, "lr_proj_logsoftmax_fwd: need 0<C<=%d (C=%d)",
                kMaxC, C);
   {
@@ -418,6 +423,20 @@ extern "C" int lr_proj_logsoftmax_fwd(const float* hidden, const float* weight, 
   return LR_OK;
 }
 
+
+// d_logits = g - softmax * sum(g) and d_bias = column sums of d_logits, nothing else: the log-softmax half of the
+// backward for callers that run the two plain GEMMs (d_hidden, d_weight) elsewhere (throughput path)
+extern "C" int lr_logsoftmax_bwd(const float* grad_lp, const float* log_probs, float* d_logits, float* d_bias, int M,
+                                 int C, void* stream) {
+  LR_CHECK_ARG(grad_lp && log_probs && d_logits && d_bias && M > 0 && C > 0 && C <= kMaxC, "lr_logsoftmax_bwd: bad args");
+  cudaStream_t st = lr_stream(stream);
+  LR_CHECK_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * C, st));
+  int g1 = lr_div_up(M, 8);
+  if (g1 > kNumSMs * 4) g1 = kNumSMs * 4;
+  logsoftmax_bwd_kernel<<<g1, 256, 0, st>>>(grad_lp, log_probs, d_logits, d_bias, M, C);
+  LR_CHECK_LAUNCH();
+  return LR_OK;
+}
 
 extern "C" int lr_proj_logsoftmax_bwd(const float* grad_lp, const float* log_probs,
                                       const float* hidden, const float* weight, float* d_logits,

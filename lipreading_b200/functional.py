@@ -18,7 +18,8 @@ def _ws(nbytes, device):
 # ------------------------------------------------------------------------------------------------
 # per-call kernel choices handed to the C-ABI (see include/lr_b200.h); 0 = the library's own choice / the parity path
 CTC_KERNEL = 0        # 1 CTA-per-clip, 2 log-space warp-per-clip, 3 linear-space warp kernel first (tests walk all of them)
-PROJ_VARIANT = 0      # 1 = 3xTF32 tensor-core forward
+PROJ_VARIANT = 0      # 1 = 3xTF32 mma.sync forward; 2 = tcgen05 kind::tf32 forward + low-precision library GEMMs in the
+                      # backward (the throughput path; falls back to 0 for shapes the kernel does not take)
 
 
 class _CTC(torch.autograd.Function):
@@ -167,10 +168,14 @@ class _ProjLogSoftmax(torch.autograd.Function):
         M, K = h2.shape
         C = w.shape[0]
         out = torch.empty((M, C), dtype=torch.float32, device=h2.device)
+        variant = PROJ_VARIANT
+        if variant == 2 and not N.lib().lr_proj_tc5_supported(M, K, C):
+            variant = 0
         N.check(N.lib().lr_proj_logsoftmax_fwd(N.ptr(h2), N.ptr(w), N.ptr(b), N.ptr(lm), N.ptr(out),
-                                               M, K, C, PROJ_VARIANT, N.stream()), "lr_proj_logsoftmax_fwd")
+                                               M, K, C, variant, N.stream()), "lr_proj_logsoftmax_fwd")
         ctx.save_for_backward(h2, w, out)
         ctx.in_shape = shp
+        ctx.variant = variant
         return out.reshape(shp[:-1] + (C,))
 
     @staticmethod
@@ -180,6 +185,16 @@ class _ProjLogSoftmax(torch.autograd.Function):
         C = w.shape[0]
         g2 = N.cont(g.reshape(M, C), torch.float32)
         d_logits = torch.empty_like(out)
+        if ctx.variant == 2:
+            # throughput path: the log-softmax backward is the kernel, the two plain GEMMs go to the library with
+            # bf16 operands and fp32 accumulation / output (like the GEMMs around the recurrent kernel)
+            d_b = torch.empty(C, dtype=torch.float32, device=w.device)
+            N.check(N.lib().lr_logsoftmax_bwd(N.ptr(g2), N.ptr(out), N.ptr(d_logits), N.ptr(d_b), M, C, N.stream()),
+                    "lr_logsoftmax_bwd")
+            dl = d_logits.to(torch.bfloat16)
+            d_hidden = torch.mm(dl, w.to(torch.bfloat16), out_dtype=torch.float32)
+            d_w = torch.mm(dl.t(), h2.to(torch.bfloat16), out_dtype=torch.float32)
+            return d_hidden.reshape(ctx.in_shape), d_w, d_b, None
         d_hidden = torch.empty_like(h2)
         d_w = torch.empty_like(w)
         d_b = torch.empty(C, dtype=torch.float32, device=w.device)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "lr_ctc_greedy_decode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lr_scale_rows": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "lr_proj_logsoftmax_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "lr_proj_tc5_supported": (_i, [_i, _i, _i]),
+    "lr_logsoftmax_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "lr_proj_logsoftmax_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lr_rnn_saved_per_unit": (_i, [_i]),
     "lr_rnn_workspace": (_sz, [_i, _i, _i, _i, _i]),

@@ -172,9 +172,14 @@ class _Deconv(nn.Module):
         self.bn = nn.BatchNorm2d(cout, eps=_BN_EPS)
 
     def forward(self, x):
-        y = self.conv(x)
         if self.stride == 1:
-            y = y[:, :, 1:-2, 1:-2]               # gradient of a (1 before, 2 after) padded conv
+            # the stride-1 transposed conv, cropped by (1 before, 2 after), IS a plain conv with the kernel flipped
+            # and its channel axes swapped over the input padded (2 before, 1 after) — same sums, but the library
+            # then runs a forward-conv kernel instead of an input-gradient one (10 of the 17 decoder layers)
+            w = self.conv.weight.flip(2, 3).transpose(0, 1)
+            y = F.conv2d(F.pad(x, (2, 1, 2, 1)), w)
+        else:
+            y = self.conv(x)
         y = self.bn(y)
         return torch.sigmoid(y) if self.final else F.relu(y)
 

@@ -34,6 +34,9 @@ uv = np.loadtxt(os.path.join(gold, "uv_kpt_ind.txt")).astype(np.int64)
 kidx = torch.from_numpy((uv[1] * 256 + uv[0]).astype(np.int32)).to(dev)
 fidx = torch.from_numpy(np.load(os.path.join(gold, "face_ind.npy"))).to(dev)
 pos = (torch.rand(n, 256, 256, 3, generator=g) * 281.6).to(dev)
+vv, uu = torch.meshgrid(torch.arange(256.0), torch.arange(256.0), indexing="ij")
+pos_id = (torch.stack([uu, vv, torch.full_like(uu, 40.0)], -1)[None] + torch.randn(8, 256, 256, 3, generator=g)).to(dev)
+lmk_id = LF.posmap_gather(pos_id, crop[:8], rp[:8], kidx).repeat(n // 8, 1, 1)     # frontal-face landmarks: mouth ROI ~ 82x163 px
 lp256 = lp[:256].detach().clone().requires_grad_(True)
 for _ in range(reps):
     LF.warp256(frames, crop)
@@ -41,7 +44,6 @@ for _ in range(reps):
     LF.ctc_nll(lp, tg, il, tl)                       # linear-space warp kernel (+ the log-space pass on flagged clips)
     LF.ctc_nll(lp256, tg[:256], il[:256], tl[:256])   # the same at the training batch size
     LF.proj_masked_log_softmax(h, w, b, lm)
-    lmk = LF.posmap_gather(pos, crop, rp, kidx)
-    LF.mouth_crop(frames, lmk, rp)
+    LF.mouth_crop(frames, lmk_id, rp, 100, 50)
 torch.cuda.synchronize()
 print("done")
