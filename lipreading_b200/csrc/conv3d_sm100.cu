@@ -34,7 +34,10 @@ namespace {
 
 constexpr int kMmaWarps = 4;                      // MMA-issuing warps (accumulator j is issued by warp j % 4)
 constexpr int kEpiGroups = 2;                     // epilogue warp quartets (each covers the four TMEM lane quarters)
-constexpr int kThreads = 32 * (1 + kMmaWarps + 4 * kEpiGroups);   // producer + issuers + epilogue warps
+constexpr int kExtraWarps = 2;                    // warps 13, 14: with the issuing warps 3, 4 that orientation 3 leaves idle
+                                                  // they form a THIRD epilogue quartet (lane quarters 3, 0, 1, 2)
+constexpr int kThreads = 32 * (1 + kMmaWarps + 4 * kEpiGroups + kExtraWarps);   // producer + issuers + epilogue warps
+// (15 warps: no scheduler hosts more than four of them, so the 128-register cap per thread is unchanged)
 constexpr int kMaxChunks = 16;   // (J + KT - 1) * channel groups
 constexpr int kWStages = 4;
 constexpr int kMaxTaps = 80;
@@ -303,7 +306,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           __syncwarp();
         }
     }
-  } else if (MODE == 3 && warp <= kMmaWarps) {
+  } else if (MODE == 3 && warp <= kMmaWarps && (warp <= p.n_issuers || p.epi_groups < 3)) {
     // ===================== mode 3: ONE issuing warp, kt-stacked MMAs in program order ===================
     // A single thread feeds the tensor pipe, so the scalar work per MMA is a handful of uniform adds: no
     // tables, no divisions, no constant-bank loads in the inner loops.  Per spatial tap the chunks c = 0 ..
@@ -423,7 +426,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         __syncwarp();
       }
     }
-  } else if (warp <= kMmaWarps) {
+  } else if (MODE != 3 && warp <= kMmaWarps) {
     // ===================== MMA issuers: warp m issues accumulators j = m and m+4 ========================
     // (one thread cannot feed the tensor pipe for N < 128; the per-MMA scalar work is kept to one 64-bit
     // add: per-item descriptor bases + a per-tap offset table in constant memory)
@@ -476,11 +479,17 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
       __syncwarp();
     }
-  } else if ((warp - 1 - kMmaWarps) >> 2 < p.epi_groups) {
+  } else if (warp <= kMmaWarps ? (MODE == 3 && p.epi_groups == 3 && warp > 2)
+                               : ((warp - 1 - kMmaWarps) >> 2 < (p.epi_groups < 3 ? p.epi_groups : 2) ||
+                                  (p.epi_groups == 3 && warp > kMmaWarps + 4 * kEpiGroups))) {
     // ===================== epilogue (quartets of warps; quartet e owns accumulators j = e mod groups) ==========
+    // quartets 0, 1 = warps 5-8, 9-12; quartet 2 (orientation 3 with <= 2 issuing warps) = warps 3, 4, 13, 14
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int eg = (warp - 1 - kMmaWarps) >> 2;   // epilogue group (quartet)
-    const int etid = ((warp - 1 - kMmaWarps) & 3) * 32 + lane;      // 0..127 inside the quartet
+    const bool third = warp <= kMmaWarps || warp > kMmaWarps + 4 * kEpiGroups;
+    const int eg = third ? 2 : (warp - 1 - kMmaWarps) >> 2;        // epilogue group (quartet)
+    const int wq = third ? (warp <= kMmaWarps ? warp - 3 : warp - (kMmaWarps + 4 * kEpiGroups + 1) + 2)
+                         : (warp - 1 - kMmaWarps) & 3;             // this warp's slot 0..3 inside its quartet
+    const int etid = wq * 32 + lane;              // 0..127 inside the quartet
     const int bar_id = 1 + eg;                    // named barrier of this quartet
     stage += (size_t)eg * p.stage_bufs * (128 * p.stage_pitch);
     const int row = q * 32 + lane;                // accumulator row (tile position) held by this thread
@@ -1016,7 +1025,10 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
     const long long mma_cycles = (long long)KT * KH * KW * (Cin / 16) * CG * (32 + Cout / 4) * 2 / (mode == 3 ? 3 : 2);
     // (the un-pooling epilogue stores four rows per position and reads the arg-max map: ~2.5x the plain one)
     p.epi_groups = (mode == 0 || mode == 3) && mma_cycles < (epi_mode == 2 ? 9000 : 2500) ? 2 : 1;   // (conv2 dgrad: 2.29 -> 2.24 ms)
-    if (getenv("LR_CONV_EPI_GROUPS")) { const int v = atoi(getenv("LR_CONV_EPI_GROUPS")); if (v == 1 || (v == 2 && mode != 1 && mode != 2)) p.epi_groups = v; }
+    // a third quartet (the two issuing warps orientation 3 does not use + two extra warps) for the layers whose
+    // epilogue is still the limiter with two: conv1 (9 N = 96 MMAs per frame against a full pooling epilogue)
+    if (mode == 3 && p.epi_groups == 2 && mma_cycles < (epi_mode == 2 ? 0 : 1500)) p.epi_groups = 3;
+    if (getenv("LR_CONV_EPI_GROUPS")) { const int v = atoi(getenv("LR_CONV_EPI_GROUPS")); if (v == 1 || ((v == 2 || (v == 3 && mode == 3)) && mode != 1 && mode != 2)) p.epi_groups = v; }
   }
   int fixed = 2 * p.wtile_bytes + p.epi_groups * stage_bytes + 256;      // at least a 2-deep ring of single taps
   // accumulators per item: bounded by TMEM (512 columns), chunk slots and shared memory
@@ -1044,6 +1056,7 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
     LR_CHECK_ARG((KT < p.Jg ? KT : p.Jg) * Cout <= 256, "lr_conv3d_fwd: kt-stacked N exceeds 256");
     G = (J + p.Jg - 1) / p.Jg;
     p.n_issuers = G;
+    if (p.epi_groups == 3 && G > 2) p.epi_groups = 2;      // the third quartet borrows issuing warps 3 and 4
     // shared chunk list: a stacked MMA spans min(KT, J) weight blocks
     // (not for 32-byte rows: conv1's one-k-step MMAs are bound by shared-memory bandwidth, not by the pipe, and the
     // unequal chunk shares made it 5 % slower — measured)
@@ -1051,6 +1064,7 @@ static int conv3d_launch(const void* x, const void* w, const float* bias, void* 
     p.seam = !single_writer && seam_ok && Cin >= 32;
     if (getenv("LR_CONV_SEAM")) p.seam = atoi(getenv("LR_CONV_SEAM")) != 0 && seam_ok && (Cin >= 32 || atoi(getenv("LR_CONV_SEAM")) > 1);
   }
+  if (mode != 3 && p.epi_groups == 3) p.epi_groups = 2;
   p.n_sets = n_sets;
   p.n_ytiles = lr_div_up(H, p.R);
   p.n_tgroups = lr_div_up(T, J);
