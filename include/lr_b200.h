@@ -257,6 +257,42 @@ int lr_attn_scores_fwd(const float* scores, const float* enc, const int32_t* len
 int lr_attn_scores_bwd(const float* enc, const int32_t* lens, const float* weights, const float* zsum,
                        const float* d_ctx, int B, int L, int T, int H, float* d_scores, float* d_enc, void* stream);
 
+/* -------- a5 / f4: position-map CNN body (and plain GEMMs) as "tap GEMMs" on tcgen05 --------- */
+/* replaces: the tcl.conv2d / tcl.conv2d_transpose + batch_norm + relu/sigmoid calls of resfcn256
+ * (src/models/face/prnet.py:211-280, one TF session.run per frame at :305-309) and, in store mode 3, the
+ * input GEMM x @ W_ih^T + b_ih in front of nn.{GRU,LSTM,RNN} (src/models/lipreader/better_model.py:47-49,74).
+ *
+ *   acc[q, n] = sum over groups g, k < Kg of  A[q + tap_off[ph*n_groups+g]][k] * W[(ph*n_groups+g)*Cout_pad + n][k]
+ *
+ * a   : bf16 channels-last volume = matrix [rows][C] (row = one position of a zero-padded (B,Hp,Wp) grid; C*2 bytes
+ *       apart).  C >= Kt: a group's K runs over the channels of ONE position (Kg <= C).  C < Kt: the K = Kt
+ *       elements of row q are the channels of positions q .. q+Kt/C-1 (horizontally adjacent taps fused into one
+ *       K tile; Kg == Kt); the allocation must extend (Kt - C)*2 bytes past the last row.
+ * w   : bf16 [n_phases*n_groups*Cout_pad][w_pitch], K-major; tap_off (HOST pointer): row offset per (phase, group).
+ * epilogue per position: v = alpha[n]*acc + beta[n] (NULL: 1 / 0) [+ gamma[n]*res[same row as out][n]] ; act 0 none,
+ *       1 ReLU, 2 sigmoid; positions outside vy0 <= y < vy0+H, vx0 <= x < vx0+W of their grid are not stored.
+ * store modes (yy = y-vy0, xx = x-vx0):
+ *   0  bf16 -> out[(b*oHp + yy+opy)*oWp + xx+opx][n]                       (+ aux: even (yy,xx) also to
+ *      aux[(b*aHp + yy/2+apad)*aWp + xx/2+apad][n], the input of a stride-2 1x1 shortcut)
+ *   1  4 phases (py,px) = (ph>>1, ph&1) of a stride-2 transposed conv -> out[(b*oHp + 2yy+py+opy)*oWp + 2xx+px+opx][n]
+ *   2  space-to-depth for a following stride-2 4x4 conv: block ((yy+1)>>1, (xx+1)>>1), channel slot
+ *      (((yy+1)&1)*2 + ((xx+1)&1))*Cout_pad + n of rows oC = 4*Cout_pad wide
+ *   3  plain GEMM: fp32 out[q*oC + n] for n < Cout, q < rows (no grid)
+ *   4  fp32 compact out[((b*H + yy)*W + xx)*Cout + n] * out_scale for n < Cout (the final position map)
+ * Asynchronous on `stream`; the descriptor is read before the call returns.                                     */
+typedef struct lr_tapgemm_desc {
+  const void* a; long long rows; int C; int Hp, Wp, vy0, vx0, H, W;
+  const void* w; int w_pitch, Kg, Kt, n_phases, n_groups; const int32_t* tap_off;
+  int Cout_pad, Cout; const float* alpha; const float* beta; const float* gamma; int act, mode;
+  void* out; int oHp, oWp, oC, opy, opx;
+  const void* res; int resC;
+  void* aux; int aHp, aWp, aC, apad;
+  float out_scale;
+} lr_tapgemm_desc;
+int lr_tapgemm(const lr_tapgemm_desc* desc, void* stream);
+/* (N,H,W,3) f32 image -> interior (pad,pad) of the zero-padded bf16 volume (N,H+2*pad,W+2*pad,16), channels 3..15 zero */
+int lr_pack_image16(const float* img, void* out_bf16, int N, int H, int W, int pad, void* stream);
+
 /* No entry point of this header keeps state between calls: kernel variants are chosen per call (`kernel`, `variant`,
  * the flag bits of `swap`).  The measurement hooks and micro-benchmarks live in include/lr_b200_diag.h and are
  * compiled into a separate liblr_b200_diag.so.                                                                  */

@@ -240,6 +240,32 @@ def _mm(a, b, bias=None, out_dtype=torch.float32):
     return torch.addmm(bias.to(out_dtype), a, b, out_dtype=out_dtype)
 
 
+def tap_linear(a, w, bias=None):
+    """a (M,K) bf16 @ w (N,K) bf16 ^T [+ bias (N) f32] -> (M,N) f32 on the tcgen05 tap-GEMM kernel (lr_tapgemm, store
+    mode 3: one tap, fp32 accumulation, the bias added in the epilogue).  K a multiple of 8 and >= 64, N a multiple
+    of 16: the shapes of the recurrent layers' input GEMM x @ W_ih^T + b_ih (better_model.py:47-49,74)."""
+    import ctypes
+    N.require_cuda(a, w, bias)
+    M, K = a.shape
+    Nn = w.shape[0]
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
+    assert K >= 64 and K % 8 == 0 and Nn % 16 == 0, (K, Nn)
+    a, w = N.cont(a), N.cont(w)
+    out = torch.empty((M, Nn), dtype=torch.float32, device=a.device)
+    d = N.TapGemmDesc()
+    d.a, d.rows, d.C = a.data_ptr(), M, K
+    d.w, d.w_pitch, d.Kg, d.Kt, d.n_phases, d.n_groups = w.data_ptr(), K, K, 64, 1, 1
+    off = (ctypes.c_int32 * 1)(0)
+    d.tap_off = ctypes.cast(off, ctypes.POINTER(ctypes.c_int32))
+    d.Cout_pad, d.Cout = Nn, Nn
+    d.beta = N.cont(bias, torch.float32).data_ptr() if bias is not None else None
+    d.act, d.mode = 0, 3
+    d.out, d.oC = out.data_ptr(), Nn
+    d.out_scale = 1.0
+    N.check(N.lib().lr_tapgemm(ctypes.byref(d), N.stream()), "lr_tapgemm")
+    return out
+
+
 class _RNNLayer(torch.autograd.Function):
     """inputs: x (B,T,I), lens (B) int32, mode str, then per direction (w_ih, w_hh, b_ih, b_hh)."""
 

@@ -52,7 +52,26 @@ SIGNATURES = {
     "lr_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lr_attn_scores_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lr_attn_scores_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lr_tapgemm": (_i, [_vp, _vp]),                       # (const lr_tapgemm_desc*, stream): prnet_tc5._Desc
+    "lr_pack_image16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
+
+
+class TapGemmDesc(ctypes.Structure):
+    """lr_tapgemm_desc of include/lr_b200.h, field for field"""
+    _fields_ = [("a", ctypes.c_void_p), ("rows", ctypes.c_longlong), ("C", ctypes.c_int),
+                ("Hp", ctypes.c_int), ("Wp", ctypes.c_int), ("vy0", ctypes.c_int), ("vx0", ctypes.c_int),
+                ("H", ctypes.c_int), ("W", ctypes.c_int),
+                ("w", ctypes.c_void_p), ("w_pitch", ctypes.c_int), ("Kg", ctypes.c_int), ("Kt", ctypes.c_int),
+                ("n_phases", ctypes.c_int), ("n_groups", ctypes.c_int), ("tap_off", ctypes.POINTER(ctypes.c_int32)),
+                ("Cout_pad", ctypes.c_int), ("Cout", ctypes.c_int),
+                ("alpha", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("gamma", ctypes.c_void_p),
+                ("act", ctypes.c_int), ("mode", ctypes.c_int),
+                ("out", ctypes.c_void_p), ("oHp", ctypes.c_int), ("oWp", ctypes.c_int), ("oC", ctypes.c_int),
+                ("opy", ctypes.c_int), ("opx", ctypes.c_int),
+                ("res", ctypes.c_void_p), ("resC", ctypes.c_int),
+                ("aux", ctypes.c_void_p), ("aHp", ctypes.c_int), ("aWp", ctypes.c_int), ("aC", ctypes.c_int),
+                ("apad", ctypes.c_int), ("out_scale", ctypes.c_float)]
 
 
 # include/lr_b200_diag.h — measurement hooks and micro-benchmarks, only in liblr_b200_diag.so (tools/ use them)

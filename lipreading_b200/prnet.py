@@ -8,8 +8,10 @@ reference's own index file (every variable this module expects exists there with
 tests/test_prnet.py against tests/golden/prnet_index.json), the VALUES are unpinned until someone supplies the data
 shard.  With the shard present `PosPrediction.restore(prefix)` loads it directly (no TensorFlow).
 
-The convolutions run through torch (cuDNN): library code, like the plain GEMMs around the recurrent kernel — the
-hand-written kernels of this path are the ones on either side (lr_warp256 in front, lr_posmap_gather behind).
+Engines.  On a CUDA device `PosPrediction` runs the body on the hand-written tcgen05 "tap GEMM" kernel
+(`prnet_tc5.compile_plan` -> `lr_tapgemm`: every conv / transposed conv with its batch-norm, activation and residual
+add fused into the epilogue, bf16 volumes, fp32 accumulation).  `engine="torch"` keeps the `nn.Module` below on
+cuDNN — the fp32 statement of the architecture the kernel path is tested against (and the only engine on a CPU).
 
 TF-slim semantics restated here:
   * `tcl.conv2d(k=4, 'SAME')`: stride 1 pads (1 before, 2 after); stride 2 (even input) pads (1, 1);
@@ -285,15 +287,28 @@ class PosPrediction:
     """Drop-in for prnet.PosPrediction (:283-314): predict / predict_batch take NHWC float images in [0,1]
     (numpy or torch) and return the position map * MaxPos in the same layout."""
 
-    def __init__(self, resolution_inp=256, resolution_op=256, device="cuda", dtype=torch.float32):
+    def __init__(self, resolution_inp=256, resolution_op=256, device="cuda", dtype=torch.float32, engine=None):
         self.resolution_inp, self.resolution_op = resolution_inp, resolution_op
         self.MaxPos = resolution_inp * 1.1
         self.device, self.dtype = torch.device(device), dtype
+        self.engine = engine or ("tcgen05" if self.device.type == "cuda" else "torch")
+        assert self.engine in ("tcgen05", "torch")
         self.network = ResFcn256().eval().to(self.device)
+        self._plans = {}
         self._configure()
 
     def _configure(self):
-        self.network = self.network.to(dtype=self.dtype, memory_format=torch.channels_last)
+        self._plans = {}                 # compiled launch plans hold packed copies of the weights
+        if self.engine == "torch":
+            self.network = self.network.to(dtype=self.dtype, memory_format=torch.channels_last)
+
+    def plan(self, batch):
+        """The compiled tcgen05 launch plan for `batch` frames (built on first use, one per batch size)."""
+        if batch not in self._plans:
+            from . import prnet_tc5
+            self._plans[batch] = prnet_tc5.compile_plan(self.network.float(), batch, self.resolution_inp, self.device,
+                                                        max_pos=self.MaxPos)
+        return self._plans[batch]
 
     def restore(self, model_path):
         names = [n for n, _, _ in self.network.tf_variables()]
@@ -303,6 +318,9 @@ class PosPrediction:
     def predict_batch(self, images):
         as_numpy = isinstance(images, np.ndarray)
         x = torch.as_tensor(images, device=self.device)
+        if self.engine == "tcgen05":
+            y = self.plan(x.shape[0]).run(x.float().contiguous()).clone()
+            return y.cpu().numpy() if as_numpy else y
         with torch.no_grad():
             x = x.permute(0, 3, 1, 2).to(dtype=self.dtype, memory_format=torch.channels_last)
             y = self.network(x).permute(0, 2, 3, 1).float() * self.MaxPos

@@ -1,0 +1,94 @@
+"""CPU tests of the launch plan `prnet_tc5.compile_plan` builds for the position-map CNN (rows a5 / f4): every launch
+is replayed by oracle/tapgemm.py (the CPU statement of lr_tapgemm) and each stem / resBlock / transposed-conv output is
+held to `prnet.ResFcn256.forward` — the restatement of the reference's resfcn256 (src/models/face/prnet.py:211-280).
+Tolerance: bf16 storage of every activation (2^-8 relative per layer, accumulating over 53 launches): 2e-2 of the
+layer's largest value."""
+import pytest
+import torch
+
+from lipreading_b200 import prnet_tc5
+from lipreading_b200.prnet import ResFcn256
+from oracle import tapgemm as OT
+
+
+def randomized_net(seed=0):
+    torch.manual_seed(seed)
+    net = ResFcn256().eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):          # non-trivial inference statistics: the folding is exercised
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+                m.running_mean.uniform_(-0.2, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+                m.weight.mul_(2.0)                             # keep activations O(1) through 28 layers
+    return net
+
+
+def layer_outputs(net, x_nhwc):
+    acts = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            acts[name] = out.detach().permute(0, 2, 3, 1)
+        return f
+    hs = [net.stem.register_forward_hook(hook("stem"))]
+    hs += [b.register_forward_hook(hook("enc%d" % i)) for i, b in enumerate(net.enc)]
+    hs += [d.register_forward_hook(hook("dec%d" % i)) for i, d in enumerate(net.dec)]
+    with torch.no_grad():
+        y = net(x_nhwc.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    for h in hs:
+        h.remove()
+    return acts, y
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_plan_replayed_on_cpu_matches_resfcn256(fuse):
+    net = randomized_net()
+    B, R = 2, 32
+    x = torch.rand(B, R, R, 3, generator=torch.Generator().manual_seed(1))
+    saved = prnet_tc5.FUSE_TAPS
+    prnet_tc5.FUSE_TAPS = fuse
+    try:
+        plan = prnet_tc5.compile_plan(net, B, R, "cpu")
+    finally:
+        prnet_tc5.FUSE_TAPS = saved
+    assert len(plan.specs) == 53                       # 1 stem + 5*4 + 5*3 resBlock launches + 17 transposed convs
+    y = OT.run_plan(plan, x)
+    acts, ref = layer_outputs(net, x)
+    assert [n for n, _ in plan.marks] == list(acts)[:len(plan.marks)]
+    for name, vol in plan.marks:
+        r = acts[name]
+        got = vol.interior()[..., :r.shape[-1]].float()
+        assert float((got - r).abs().max()) <= 2e-2 * float(r.abs().max()), name
+        assert float(vol.interior()[..., r.shape[-1]:].abs().max() if vol.C > r.shape[-1] else 0.0) == 0.0     # padded channels
+    assert float((y - ref * R * 1.1).abs().max()) <= 2e-2 * R * 1.1
+    # borders of every volume stay zero (they ARE the conv padding)
+    for _, vol in plan.marks:
+        v = vol.t[:vol.rows].view(vol.B, vol.Hp, vol.Wp, vol.C).float()
+        inner = torch.zeros_like(v, dtype=torch.bool)
+        inner[:, prnet_tc5.P:prnet_tc5.P + vol.H, prnet_tc5.P:prnet_tc5.P + vol.W] = True
+        assert float(v[~inner].abs().max()) == 0.0
+
+
+def test_fused_tap_groups_cover_each_tap_once():
+    """C = 16: the four x-taps of a filter row share one K = 64 tile; C = 32: two tiles per row; C >= 64: one per tap."""
+    w = torch.randn(16, 16, 4, 4)
+    taps = prnet_tc5._conv_taps(w, 4, False)
+    offs, mats, Kg, Kt = prnet_tc5._groups(taps, 16, 100, 16)
+    assert (Kg, Kt, len(offs)) == (64, 64, 4) and offs == [(ky - 1) * 100 - 1 for ky in range(4)]
+    for ky in range(4):
+        for kx in range(4):
+            assert torch.equal(mats[ky][:, kx * 16:(kx + 1) * 16], w[:, :, ky, kx])
+    w = torch.randn(32, 32, 4, 4)
+    offs, mats, Kg, Kt = prnet_tc5._groups(prnet_tc5._conv_taps(w, 4, False), 32, 100, 32)
+    assert len(offs) == 8 and Kg == 64
+    offs, mats, Kg, Kt = prnet_tc5._groups(prnet_tc5._conv_taps(torch.randn(64, 64, 4, 4), 4, False), 64, 100, 64)
+    assert len(offs) == 16 and Kg == 64 and Kt == 64
+    # transposed stride-2 conv: 4 phases x 4 taps, each kernel element used exactly once
+    wt = torch.randn(32, 16, 4, 4)
+    phases = prnet_tc5._deconv_phases(wt, 2)
+    assert len(phases) == 4 and all(len(p) == 4 for p in phases)
+    total = sum(float(m.abs().sum()) for p in phases for _, _, m in p)
+    assert abs(total - float(wt.abs().sum())) < 1e-3 * total
