@@ -298,8 +298,8 @@ def ref_shape_block(dev, char2idx, steps=3):
 
 def frame_stream_block(dev, enc, char2idx, n_clips=8):
     """Raw 720p frames + boxes -> characters in one pass (infer.FrameRecognizer): rect geometry -> warp256 -> position
-    map CNN (cuDNN bf16, random weights: the reference ships none) -> 68 landmarks -> mouth crop -> conv front-end ->
-    BiGRU -> greedy CTC.  The CNN (8.26 GFLOP/frame, library code) dominates; the per-stage kernels are in `kernels`."""
+    map CNN (tcgen05 tap-GEMM plan, random weights: the reference ships none) -> 68 landmarks -> mouth crop -> conv
+    front-end -> BiGRU -> greedy CTC.  The CNN (8.26 GFLOP/frame) dominates; the per-stage kernels are in `kernels`."""
     import numpy as np
     from lipreading_b200.face import PRN
     from lipreading_b200.infer import FrameRecognizer
@@ -307,7 +307,7 @@ def frame_stream_block(dev, enc, char2idx, n_clips=8):
     gold = os.path.join(ROOT, "tests", "golden")
     uv = np.loadtxt(os.path.join(gold, "uv_kpt_ind.txt")).astype(np.int32)
     face = np.load(os.path.join(gold, "face_ind.npy"))
-    pred = PosPrediction(device=dev, dtype=torch.bfloat16)
+    pred = PosPrediction(device=dev)
     prn = PRN(predict_batch=pred.predict_batch, uv_kpt_ind=uv, face_ind=face, device=dev)
     stream = FrameRecognizer(enc, char2idx, prn, batch=64)
     n = n_clips * T_FRAMES
@@ -408,12 +408,21 @@ def kernel_rooflines(dev, pk, char2idx):
                 "shape": "n=%d 720p, ROI %dx%d px read + 15 kB written per frame" % (nm, int(roi_h[0, 2]), int(roi_h[0, 3])),
                 "ms": s * 1e3})
     del frames_m, lmk_m, rp_m
-    # whole per-frame vision path (BASELINE config 2): rect geometry -> warp256 -> PRNet CNN (cuDNN, bf16, random
-    # weights: the reference ships none) -> restore + 68-landmark gather.  4.13 GMAC/frame in the CNN.
+    # position-map CNN body alone (rows a5 / f4): 53 lr_tapgemm launches + the image packing per batch of 64 frames,
+    # 4.13 GMAC/frame of model work (the plan's own count, padding and zero-weight fused taps excluded)
     try:
         from lipreading_b200.prnet import PosPrediction
-        pred = PosPrediction(device=dev, dtype=torch.bfloat16)
+        pred = PosPrediction(device=dev)
         nb = 64
+        plan = pred.plan(nb)
+        img = torch.rand(nb, 256, 256, 3, generator=g).to(dev)
+        s = time_cuda(lambda: plan.run(img), iters=10, warm=3, flush=flush)
+        out.append({"kernel": "prnet_body (tapgemm_kernel x53, tcgen05 bf16)", "bound": "tensor", "unit": "TFLOP/s",
+                    "achieved": plan.model_flops / s / 1e12, "frac": plan.model_flops / s / 1e12 / pk["bf16_tflops"],
+                    "issued_tflops": plan.flops / s / 1e12, "frames_per_s": nb / s, "shape": "batch %d x 256x256x3" % nb,
+                    "ms": s * 1e3})
+        # whole per-frame vision path (BASELINE config 2): rect geometry -> warp256 -> position-map CNN -> restore +
+        # 68-landmark gather, every stage a kernel of this repo (random CNN weights: the reference ships none)
 
         def vision():
             for i in range(0, n, nb):
@@ -421,10 +430,15 @@ def kernel_rooflines(dev, pk, char2idx):
                 pm = pred.predict_batch(LF.warp256(frames[i:i + nb], c2))
                 LF.posmap_gather(pm, c2, r2, kidx)
         s = time_cuda(vision, iters=3, warm=2)
-        out.append({"kernel": "vision_stream(frames->68 landmarks, incl. PRNet CNN via cuDNN bf16)", "bound": "tensor",
-                    "unit": "frames/s", "achieved": n / s, "frac": n * 2 * 4.13e9 / s / 1e12 / pk["bf16_tflops"],
+        out.append({"kernel": "vision_stream(frames->68 landmarks, incl. the position-map CNN on tcgen05)", "bound": "tensor",
+                    "unit": "frames/s", "achieved": n / s, "frac": n * plan.model_flops / nb / s / 1e12 / pk["bf16_tflops"],
                     "shape": "n=%d,720p, batches of %d" % (n, nb), "ms": s * 1e3})
-        del pred
+        ref = PosPrediction(device=dev, dtype=torch.bfloat16, engine="torch")
+        s = time_cuda(lambda: ref.predict_batch(img), iters=3, warm=2)
+        out.append({"kernel": "prnet_body via torch/cuDNN bf16 channels-last (library baseline)", "bound": "tensor",
+                    "unit": "TFLOP/s", "achieved": plan.model_flops / s / 1e12, "frac": plan.model_flops / s / 1e12 / pk["bf16_tflops"],
+                    "frames_per_s": nb / s, "shape": "batch %d" % nb, "ms": s * 1e3})
+        del pred, ref, plan
     except Exception as e:
         out.append({"kernel": "vision_stream", "error": repr(e)})
     # recurrent layer fwd (BiGRU-256, B=256, T=75): latency-bound; report FLOP/s of the recurrent GEMMs

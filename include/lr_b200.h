@@ -288,6 +288,9 @@ typedef struct lr_tapgemm_desc {
   const void* res; int resC;
   void* aux; int aHp, aWp, aC, apad;
   float out_scale;
+  int pack;             /* 0/1, or 2 / 4: a matrix row holds `pack` horizontally adjacent positions (pack*C == Kt = 64):
+                         * `rows` counts matrix rows, tap_off is in matrix rows, w has pack*Cout_pad rows per
+                         * (phase, group) — accumulator columns [j*Cout_pad, (j+1)*Cout_pad) are position q*pack + j */
 } lr_tapgemm_desc;
 int lr_tapgemm(const lr_tapgemm_desc* desc, void* stream);
 /* (N,H,W,3) f32 image -> interior (pad,pad) of the zero-padded bf16 volume (N,H+2*pad,W+2*pad,16), channels 3..15 zero */

@@ -29,17 +29,22 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kMaxBK = 64;                    // bf16 per K tile: 64 (128-byte swizzled rows), or 32 / 16 (64- / 32-byte rows)
-constexpr int kMaxStages = 6;
-constexpr int kThreads = 32 * 6;
+constexpr int kMaxStages = 24;                // small-K layers: many small stages keep enough bytes in flight
+constexpr int kMaxAcc = 8;                    // TMEM accumulator buffers (Ntile <= 64: 8, 128: 4, 256: 2)
+constexpr int kEpiGroups = 2;                 // epilogue warp quartets (alternate work items)
+constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
+constexpr int kMaxN = 256;                    // widest N tile
 constexpr int kMaxTapGroups = 64;             // phases * groups
-constexpr int kSmemCap = 200 * 1024;
+constexpr int kSmemCap = 192 * 1024;
 
 struct TgParams {
   int n_mtiles, n_ntiles, n_phases, n_groups, n_chunks, n_items;
   int Ntile, Cout_pad, Cout;
+  int Nrow;                      // weight rows per (phase, group) = pack * Cout_pad
   int a_chunked;                 // 1: A column coordinate = chunk*Kt (C >= Kt); 0: always 0 (fused-tap rows)
   int Kt, a_tile_bytes;          // K tile (elements) and bytes of the A tile
   int stages, stage_bytes;
+  int n_acc;                     // accumulator buffers in use (power of two)
   int rows, HpWp, Wp, vy0, vx0, H, W;
   int mode, act;
   int oHp, oWp, oC, opy, opx;
@@ -53,6 +58,7 @@ struct TgParams {
   const __nv_bfloat16* res;
   __nv_bfloat16* aux;
   uint32_t idesc, desc_hi;
+  struct { uint32_t m, s; } d_mtiles, d_ntiles, d_hpwp, d_wp;   // magic numbers: exact division of values < 2^31
   int tap_off[kMaxTapGroups];
 };
 
@@ -74,6 +80,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// exact q / d for q < 2^31: (q * m) >> s with m = ceil(2^s / d), s = 31 + ceil(log2 d)
+template <typename F>
+__device__ __forceinline__ uint32_t fdiv(uint32_t q, F f) {
+  return (uint32_t)(((uint64_t)q * f.m) >> f.s);
+}
+
+template <int MODE, int PACK>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -82,18 +95,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + kMaxStages;
   uint64_t* bar_acc_full = bars + 2 * kMaxStages;
-  uint64_t* bar_acc_empty = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* bar_acc_empty = bars + 2 * kMaxStages + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc);
+  float* vecs = reinterpret_cast<float*>(tmem_slot + 4);       // [kEpiGroups][3][kMaxN]: alpha, beta, gamma of the current N tile
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.Ntile) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.n_acc * p.Ntile) tmem_cols <<= 1;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       lr_mbar_init(&bar_full[s], 1);
       lr_mbar_init(&bar_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kMaxAcc; ++b) {
       lr_mbar_init(&bar_acc_full[b], 1);
       lr_mbar_init(&bar_acc_empty[b], 128);
     }
@@ -110,13 +124,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== TMA producer =====
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int m = item % p.n_mtiles, r = item / p.n_mtiles;
-      const int nt = r % p.n_ntiles, ph = r / p.n_ntiles;
+      const int r = (int)fdiv((uint32_t)item, p.d_mtiles), m = item - r * p.n_mtiles;
+      const int ph = (int)fdiv((uint32_t)r, p.d_ntiles), nt = r - ph * p.n_ntiles;
       const int q0 = m * kBM;
       for (int g = 0; g < p.n_groups; ++g) {
         const int pg = ph * p.n_groups + g;
         const int arow = q0 + p.tap_off[pg];
-        const int wrow = pg * p.Cout_pad + nt * p.Ntile;
+        const int wrow = pg * p.Nrow + nt * p.Ntile;
         for (int kc = 0; kc < p.n_chunks; ++kc, ++it) {
           const int s = it % p.stages;
           lr_mbar_wait(&bar_empty[s], ((it / p.stages) & 1) ^ 1);     // (tiles are short: no back-off sleeps)
@@ -134,8 +148,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== MMA issuer =====
     uint32_t it = 0, n = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-      const uint32_t buf = n & 1;
-      lr_mbar_wait(&bar_acc_empty[buf], ((n >> 1) & 1) ^ 1);
+      const uint32_t buf = n & (uint32_t)(p.n_acc - 1);
+      lr_mbar_wait(&bar_acc_empty[buf], ((n / (uint32_t)p.n_acc) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d = tmem_base + buf * (uint32_t)p.Ntile;
       for (int k = 0; k < n_k; ++k, ++it) {
@@ -156,118 +170,171 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
     }
   } else {
-    // ===== epilogue: thread = one position (TMEM lane) =====
+    // ===== epilogue: two warp quartets take alternate work items; thread = one position (TMEM lane) =====
+    // (a tile's epilogue is a dependent chain of a few hundred instructions on ONE warp per scheduler: with 16- or
+    //  32-column tiles it, not the tensor pipe or HBM, bounds the kernel — hence magic-number divisions, the
+    //  per-channel vectors in shared memory, a compile-time store mode and two quartets)
     const int quarter = warp & 3;
+    const int eg = (warp - 2) >> 2;                             // quartet 0: warps 2-5, quartet 1: warps 6-9
+    float* v_alpha = vecs + eg * 3 * kMaxN;
+    float* v_beta = v_alpha + kMaxN;
+    float* v_gamma = v_beta + kMaxN;
+    const int etid = ((warp - 2) & 3) * 32 + lane;
+    int cur_nt = -1;
     uint32_t n = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
-      const int m = item % p.n_mtiles, r = item / p.n_mtiles;
-      const int nt = r % p.n_ntiles, ph = r / p.n_ntiles;
-      const uint32_t buf = n & 1;
-      const int q = m * kBM + quarter * 32 + lane;
-      bool valid = q < p.rows;
-      long long orow = q;                      // mode 3: the GEMM's own row
-      long long arow = -1;
-      int coff = nt * p.Ntile;                 // channel offset inside the output row
-      int yy = 0, xx = 0, b = 0;
-      if (p.mode != 3) {
-        b = q / p.HpWp;
-        const int rr = q - b * p.HpWp;
-        const int y = rr / p.Wp;
-        yy = y - p.vy0;
-        xx = rr - y * p.Wp - p.vx0;
-        valid = valid && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
-        if (p.mode == 0) {
-          orow = ((long long)b * p.oHp + yy + p.opy) * p.oWp + xx + p.opx;
-        } else if (p.mode == 1) {
-          orow = ((long long)b * p.oHp + 2 * yy + (ph >> 1) + p.opy) * p.oWp + 2 * xx + (ph & 1) + p.opx;
-        } else if (p.mode == 2) {
-          orow = ((long long)b * p.oHp + ((yy + 1) >> 1) + p.opy) * p.oWp + ((xx + 1) >> 1) + p.opx;
-          coff += ((((yy + 1) & 1) << 1) | ((xx + 1) & 1)) * p.Cout_pad;
-        } else {                               // mode 4: compact fp32 (B,H,W,Cout)
-          orow = ((long long)b * p.H + yy) * p.W + xx;
+      if ((int)(n & 1) != eg) continue;
+      const int r = (int)fdiv((uint32_t)item, p.d_mtiles), m = item - r * p.n_mtiles;
+      const int ph = (int)fdiv((uint32_t)r, p.d_ntiles), nt = r - ph * p.n_ntiles;
+      if (nt != cur_nt) {                                       // (rare: items run over the M tiles first)
+        named_bar_sync(1 + eg, 128);
+        const int nv = PACK > 1 ? p.Cout_pad : p.Ntile, v0 = PACK > 1 ? 0 : nt * p.Ntile;
+        for (int c = etid; c < nv; c += 128) {
+          v_alpha[c] = p.alpha ? p.alpha[v0 + c] : 1.f;
+          v_beta[c] = p.beta ? p.beta[v0 + c] : 0.f;
+          v_gamma[c] = p.gamma ? p.gamma[v0 + c] : 1.f;
         }
-        if (p.aux != nullptr && valid && !((yy | xx) & 1))
-          arow = ((long long)b * p.aHp + (yy >> 1) + p.apad) * p.aWp + (xx >> 1) + p.apad;
+        named_bar_sync(1 + eg, 128);
+        cur_nt = nt;
       }
-      lr_mbar_wait(&bar_acc_full[buf], (n >> 1) & 1);
+      const uint32_t buf = n & (uint32_t)(p.n_acc - 1);
+      const int q = m * kBM + quarter * 32 + lane;           // matrix row of this thread = PACK consecutive positions
+      // ---- where the PACK positions of this row go -------------------------------------------------------------
+      bool valid[PACK];
+      long long orow[PACK], arow[PACK];
+      int coff[PACK];
+#pragma unroll
+      for (int j = 0; j < PACK; ++j) {
+        const int qp = q * PACK + j;
+        valid[j] = q < p.rows;
+        orow[j] = qp;                            // mode 3: the GEMM's own row
+        arow[j] = -1;
+        coff[j] = nt * p.Ntile;                  // channel offset inside the output row (PACK > 1: one N tile)
+        if (MODE != 3) {
+          const int b = (int)fdiv((uint32_t)qp, p.d_hpwp);
+          const int rr = qp - b * p.HpWp;
+          const int y = (int)fdiv((uint32_t)rr, p.d_wp);
+          const int yy = y - p.vy0;
+          const int xx = rr - y * p.Wp - p.vx0;
+          valid[j] = valid[j] && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+          if (MODE == 0) {
+            orow[j] = ((long long)b * p.oHp + yy + p.opy) * p.oWp + xx + p.opx;
+            if (p.aux != nullptr && valid[j] && !((yy | xx) & 1))
+              arow[j] = ((long long)b * p.aHp + (yy >> 1) + p.apad) * p.aWp + (xx >> 1) + p.apad;
+          } else if (MODE == 1) {
+            orow[j] = ((long long)b * p.oHp + 2 * yy + (ph >> 1) + p.opy) * p.oWp + 2 * xx + (ph & 1) + p.opx;
+          } else if (MODE == 2) {
+            orow[j] = ((long long)b * p.oHp + ((yy + 1) >> 1) + p.opy) * p.oWp + ((xx + 1) >> 1) + p.opx;
+            coff[j] += ((((yy + 1) & 1) << 1) | ((xx + 1) & 1)) * p.Cout_pad;
+          } else {                               // mode 4: compact fp32 (B,H,W,Cout)
+            orow[j] = ((long long)b * p.H + yy) * p.W + xx;
+          }
+        }
+      }
+      // columns of the accumulator per position: PACK > 1 -> Cout_pad each (position j at j*Cout_pad); else the N tile
+      const int n_cols = PACK > 1 ? p.Cout_pad : p.Ntile;
+      // the residual of the first 16 channels is requested BEFORE the accumulator wait, every later chunk's while the one
+      // before it is processed: its L2 / HBM latency is off the tile-to-tile chain
+      const bool has_res = MODE == 0 && p.res != nullptr;
+      uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+      if (has_res && valid[0]) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow[0] * p.resC + coff[0]);
+        r0 = __ldg(rp);
+        r1 = __ldg(rp + 1);
+      }
+      lr_mbar_wait(&bar_acc_full[buf], (n / (uint32_t)p.n_acc) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + buf * (uint32_t)p.Ntile + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+      for (int j = 0; j < PACK; ++j) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
-        if (valid) {
-        const int cn = nt * p.Ntile + c0;      // channel index in [0, Cout_pad)
-        float f[16];
-        {
-          // per-channel scale / shift: 16 consecutive floats, 64-byte aligned (cn is a multiple of 16)
-          float al[16], be[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 a4 = p.alpha ? __ldg(reinterpret_cast<const float4*>(p.alpha + cn) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-            const float4 b4 = p.beta ? __ldg(reinterpret_cast<const float4*>(p.beta + cn) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            al[4 * i] = a4.x; al[4 * i + 1] = a4.y; al[4 * i + 2] = a4.z; al[4 * i + 3] = a4.w;
-            be[4 * i] = b4.x; be[4 * i + 1] = b4.y; be[4 * i + 2] = b4.z; be[4 * i + 3] = b4.w;
+        for (int c0 = 0; c0 < n_cols; c0 += 16) {
+          uint32_t v[16];
+          uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+          if (has_res) {                         // next chunk of this position, or the first chunk of the next one
+            if (c0 + 16 < n_cols) {
+              if (valid[j]) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow[j] * p.resC + coff[j] + c0 + 16);
+                n0 = __ldg(rp);
+                n1 = __ldg(rp + 1);
+              }
+            } else if (j + 1 < PACK) {
+              if (valid[j + 1 < PACK ? j + 1 : j]) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow[j + 1 < PACK ? j + 1 : j] * p.resC +
+                                                                 coff[j + 1 < PACK ? j + 1 : j]);
+                n0 = __ldg(rp);
+                n1 = __ldg(rp + 1);
+              }
+            }
           }
+          tmem_ld16(trow + (uint32_t)(j * n_cols + c0), v);
+          if (valid[j]) {
+            const int cn = (PACK > 1 ? 0 : nt * p.Ntile) + c0;      // channel index in [0, Cout_pad)
+            float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(v[i]), al[i], be[i]);
-        }
-        if (p.res != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow * p.resC + coff + c0);
-          const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-          const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          float ga[16];
+            for (int i = 0; i < 4; ++i) {
+              const float4 a4 = *reinterpret_cast<const float4*>(v_alpha + c0 + 4 * i);
+              const float4 b4 = *reinterpret_cast<const float4*>(v_beta + c0 + 4 * i);
+              f[4 * i] = fmaf(__uint_as_float(v[4 * i]), a4.x, b4.x);
+              f[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), a4.y, b4.y);
+              f[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), a4.z, b4.z);
+              f[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), a4.w, b4.w);
+            }
+            if (has_res) {
+              const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 g4 = p.gamma ? __ldg(reinterpret_cast<const float4*>(p.gamma + cn) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-            ga[4 * i] = g4.x; ga[4 * i + 1] = g4.y; ga[4 * i + 2] = g4.z; ga[4 * i + 3] = g4.w;
+              for (int i = 0; i < 4; ++i) {
+                const float4 g4 = *reinterpret_cast<const float4*>(v_gamma + c0 + 4 * i);
+                f[4 * i] = fmaf(bf16_lo(ru[2 * i]), g4.x, f[4 * i]);
+                f[4 * i + 1] = fmaf(bf16_hi(ru[2 * i]), g4.y, f[4 * i + 1]);
+                f[4 * i + 2] = fmaf(bf16_lo(ru[2 * i + 1]), g4.z, f[4 * i + 2]);
+                f[4 * i + 3] = fmaf(bf16_hi(ru[2 * i + 1]), g4.w, f[4 * i + 3]);
+              }
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (MODE != 4 || cn + i < p.Cout) f[i] = 1.f / (1.f + __expf(-f[i]));
+            }
+            if (MODE == 3) {
+              float* o = reinterpret_cast<float*>(p.out) + orow[j] * p.oC + coff[j] + c0;
+              if (cn + 16 <= p.Cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (cn + i < p.Cout) o[i] = f[i];
+              }
+            } else if (MODE == 4) {
+              float* o = reinterpret_cast<float*>(p.out) + orow[j] * p.Cout;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (cn + i < p.Cout) o[cn + i] = f[i] * p.out_scale;
+            } else {
+              uint4 s0, s1;
+              s0.x = pack_bf16x2(f[0], f[1]);   s0.y = pack_bf16x2(f[2], f[3]);
+              s0.z = pack_bf16x2(f[4], f[5]);   s0.w = pack_bf16x2(f[6], f[7]);
+              s1.x = pack_bf16x2(f[8], f[9]);   s1.y = pack_bf16x2(f[10], f[11]);
+              s1.z = pack_bf16x2(f[12], f[13]); s1.w = pack_bf16x2(f[14], f[15]);
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow[j] * p.oC + coff[j] + c0);
+              o[0] = s0;
+              o[1] = s1;
+              if (MODE == 0 && arow[j] >= 0) {
+                uint4* a2 = reinterpret_cast<uint4*>(p.aux + arow[j] * p.aC + cn);
+                a2[0] = s0;
+                a2[1] = s1;
+              }
+            }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[2 * i] = fmaf(bf16_lo(ru[i]), ga[2 * i], f[2 * i]);
-            f[2 * i + 1] = fmaf(bf16_hi(ru[i]), ga[2 * i + 1], f[2 * i + 1]);
-          }
+          r0 = n0;
+          r1 = n1;
+          __syncwarp();                          // tcgen05.ld is warp-collective: reconverge before the next one
         }
-        if (p.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = 1.f / (1.f + expf(-f[i]));
-        }
-        if (p.mode == 3) {
-          float* o = reinterpret_cast<float*>(p.out) + orow * p.oC + coff + c0;
-          if (cn + 16 <= p.Cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (cn + i < p.Cout) o[i] = f[i];
-          }
-        } else if (p.mode == 4) {
-          float* o = reinterpret_cast<float*>(p.out) + orow * p.Cout;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (cn + i < p.Cout) o[cn + i] = f[i] * p.out_scale;
-        } else {
-          uint4 s0, s1;
-          s0.x = pack_bf16x2(f[0], f[1]);   s0.y = pack_bf16x2(f[2], f[3]);
-          s0.z = pack_bf16x2(f[4], f[5]);   s0.w = pack_bf16x2(f[6], f[7]);
-          s1.x = pack_bf16x2(f[8], f[9]);   s1.y = pack_bf16x2(f[10], f[11]);
-          s1.z = pack_bf16x2(f[12], f[13]); s1.w = pack_bf16x2(f[14], f[15]);
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.oC + coff + c0);
-          o[0] = s0;
-          o[1] = s1;
-          if (arow >= 0) {
-            uint4* a2 = reinterpret_cast<uint4*>(p.aux + arow * p.aC + nt * p.Ntile + c0);
-            a2[0] = s0;
-            a2[1] = s1;
-          }
-        }
-        }
-        __syncwarp();                          // tcgen05.ld is warp-collective: reconverge before the next one
       }
       tc_fence_before();
       lr_mbar_arrive(&bar_acc_empty[buf]);
@@ -312,8 +379,8 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
                "lr_tapgemm: 1..%d tap groups over all phases", kMaxTapGroups);
   const int Kt = d->Kt;
   LR_CHECK_ARG(Kt == 16 || Kt == 32 || Kt == kMaxBK, "lr_tapgemm: K tile must be 16, 32 or 64");
-  LR_CHECK_ARG(d->Kg >= 1 && (d->C >= Kt ? d->Kg <= d->C : d->Kg == Kt),
-               "lr_tapgemm: Kg = Kt (fused taps, C < Kt) or <= C (C >= Kt)");
+  LR_CHECK_ARG(d->Kg >= 1 && (d->C * (d->pack > 1 ? d->pack : 1) >= Kt ? d->Kg <= d->C * (d->pack > 1 ? d->pack : 1) : d->Kg == Kt),
+               "lr_tapgemm: Kg = Kt (fused taps, C < Kt) or <= the channels of a matrix row");
   LR_CHECK_ARG(d->Cout_pad >= 16 && d->Cout_pad % 16 == 0 && d->Cout >= 1 && d->Cout <= d->Cout_pad,
                "lr_tapgemm: Cout_pad must be a multiple of 16 >= Cout");
   LR_CHECK_ARG(d->mode >= 0 && d->mode <= 4 && d->act >= 0 && d->act <= 2, "lr_tapgemm: mode 0..4, act 0..2");
@@ -323,22 +390,28 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
   LR_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "lr_tapgemm: operands must be 16-byte aligned");
   if (d->mode != 3)
-    LR_CHECK_ARG(d->Hp > 0 && d->Wp > 0 && d->H > 0 && d->W > 0 && d->rows % ((long long)d->Hp * d->Wp) == 0,
+    LR_CHECK_ARG(d->Hp > 0 && d->Wp > 0 && d->H > 0 && d->W > 0 && (d->rows * (d->pack > 1 ? d->pack : 1)) % ((long long)d->Hp * d->Wp) == 0,
                  "lr_tapgemm: rows must be whole Hp x Wp grids");
   if (d->mode <= 2) LR_CHECK_ARG(d->oC % 8 == 0 && d->oC >= (d->mode == 2 ? 4 : 1) * d->Cout_pad, "lr_tapgemm: output row too narrow");
 
+  const int PK = d->pack > 0 ? d->pack : 1;
+  LR_CHECK_ARG(PK == 1 || ((PK == 2 || PK == 4) && d->mode != 3 && PK * d->C == d->Kt && PK * d->Cout_pad <= kMaxN &&
+                           d->Wp % PK == 0),
+               "lr_tapgemm: pack 2 / 4 needs pack*C == Kt, pack*Cout_pad <= %d, Wp %% pack == 0 and a grid store mode", kMaxN);
+  const int Crow = d->C * PK;        // channels per matrix row
   TgParams p;
   memset(&p, 0, sizeof(p));
-  // N tile: the largest divisor of Cout_pad that is a multiple of 16 and <= 256
-  int ntile = d->Cout_pad <= 256 ? d->Cout_pad : 256;
-  while (d->Cout_pad % ntile) ntile -= 16;
+  // N tile: the largest divisor of the row block that is a multiple of 16 and <= 256
+  p.Nrow = PK * d->Cout_pad;
+  int ntile = p.Nrow <= 256 ? p.Nrow : 256;
+  while (p.Nrow % ntile) ntile -= 16;
   p.Ntile = ntile;
-  p.n_ntiles = d->Cout_pad / ntile;
+  p.n_ntiles = p.Nrow / ntile;
   p.n_mtiles = lr_div_up(d->rows, kBM);
   p.n_phases = d->n_phases;
   p.n_groups = d->n_groups;
   p.n_chunks = lr_div_up(d->Kg, Kt);
-  p.a_chunked = d->C >= Kt;
+  p.a_chunked = Crow >= Kt;
   p.Kt = Kt;
   p.a_tile_bytes = kBM * Kt * 2;
   const long long items = (long long)p.n_mtiles * p.n_ntiles * p.n_phases;
@@ -349,6 +422,7 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
   p.stage_bytes = p.a_tile_bytes + ntile * Kt * 2;
   p.stages = kSmemCap / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.n_acc = ntile <= 64 ? 8 : (ntile <= 128 ? 4 : 2);
   p.rows = (int)d->rows;
   p.HpWp = d->Hp * d->Wp; p.Wp = d->Wp; p.vy0 = d->vy0; p.vx0 = d->vx0; p.H = d->H; p.W = d->W;
   p.mode = d->mode; p.act = d->act;
@@ -364,21 +438,42 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
   p.desc_hi = desc_hi_for(Kt * 2, 8 * Kt * 2);
   for (int i = 0; i < d->n_phases * d->n_groups; ++i) p.tap_off[i] = d->tap_off[i];
+  auto magic = [](uint32_t dv, uint32_t& m, uint32_t& sh) {
+    if (dv == 0) dv = 1;
+    uint32_t l = 0;
+    while ((1ull << l) < dv) ++l;
+    sh = 31 + l;
+    m = (uint32_t)(((1ull << sh) + dv - 1) / dv);
+  };
+  magic((uint32_t)p.n_mtiles, p.d_mtiles.m, p.d_mtiles.s);
+  magic((uint32_t)p.n_ntiles, p.d_ntiles.m, p.d_ntiles.s);
+  magic((uint32_t)p.HpWp, p.d_hpwp.m, p.d_hpwp.s);
+  magic((uint32_t)p.Wp, p.d_wp.m, p.d_wp.s);
 
   CUtensorMap map_a, map_w;
   // A: [rows][C] with the position pitch as row stride; the inner extent is C (>= Kt: chunks of Kt, columns past C
   // are zero-filled) or Kt (C < Kt: the row runs over the next positions — fused horizontal taps)
-  int rc = make_map_bf16_strided(&map_a, d->a, (uint64_t)(d->C >= Kt ? d->C : Kt), (uint64_t)d->rows,
-                                 (uint64_t)d->C * 2, Kt, kBM, Kt * 2);
+  int rc = make_map_bf16_strided(&map_a, d->a, (uint64_t)(Crow >= Kt ? Crow : Kt), (uint64_t)d->rows,
+                                 (uint64_t)Crow * 2, Kt, kBM, Kt * 2);
   if (rc != LR_OK) return rc;
-  const uint64_t w_rows = (uint64_t)d->n_phases * d->n_groups * d->Cout_pad;
+  const uint64_t w_rows = (uint64_t)d->n_phases * d->n_groups * p.Nrow;
   LR_CHECK_ARG(d->w_pitch >= d->Kg && d->w_pitch % 8 == 0, "lr_tapgemm: weight row pitch must be >= Kg and a multiple of 8");
   rc = make_map_bf16_strided(&map_w, d->w, (uint64_t)d->Kg, w_rows, (uint64_t)d->w_pitch * 2, Kt, (uint32_t)ntile, Kt * 2);
   if (rc != LR_OK) return rc;
-  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * kMaxStages + 4) * 8 + 16 + 1024;
-  LR_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * kMaxStages + 2 * kMaxAcc) * 8 + 16 +
+                            kEpiGroups * 3 * kMaxN * sizeof(float) + 1024;
   const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-  tapgemm_kernel<<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_a, map_w, p);
+#define LR_TG_LAUNCH(M, P)                                                                                             \
+  case M * 8 + P:                                                                                                      \
+    LR_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+    tapgemm_kernel<M, P><<<grid, kThreads, smem_bytes, lr_stream(stream)>>>(map_a, map_w, p);                          \
+    break;
+  switch (d->mode * 8 + PK) {
+    LR_TG_LAUNCH(0, 1) LR_TG_LAUNCH(1, 1) LR_TG_LAUNCH(2, 1) LR_TG_LAUNCH(3, 1) LR_TG_LAUNCH(4, 1)
+    LR_TG_LAUNCH(0, 2) LR_TG_LAUNCH(1, 2) LR_TG_LAUNCH(2, 2) LR_TG_LAUNCH(4, 2)
+    LR_TG_LAUNCH(0, 4) LR_TG_LAUNCH(1, 4) LR_TG_LAUNCH(2, 4) LR_TG_LAUNCH(4, 4)
+  }
+#undef LR_TG_LAUNCH
   LR_CHECK_LAUNCH();
   return LR_OK;
 }

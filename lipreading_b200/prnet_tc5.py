@@ -28,6 +28,7 @@ from . import native
 
 P = 2                                    # border of every normal volume
 FUSE_TAPS = True                         # C < 64: fuse 64/C adjacent x-taps into one 128-byte K tile
+PACK_POSITIONS = True                    # C < 64: a matrix row = 64/C adjacent positions (block-Toeplitz weights), see _groups
 
 
 _Desc = native.TapGemmDesc
@@ -56,16 +57,40 @@ class Volume:
 
 
 def _groups(taps, C, Wp, cout_pad):
-    """taps: [(dy, dx, W[cout, cin<=C] f32)] -> (offsets, weight [n_groups, cout_pad, Kg] f32, Kg, Kt)"""
+    """taps: [(dy, dx, W[cout, cin<=C] f32)] -> (row offsets, weight [n_groups, pack*cout_pad, Kg] f32, Kg, Kt, pack).
+
+    C >= 64: one group per tap, K over the channels of one position.
+    C < 64, packed (default): a matrix row holds pack = 64/C horizontally adjacent positions p*pack .. p*pack+pack-1 and the
+    accumulator row their pack*cout_pad outputs.  Output j of a row needs input position p*pack + j + dx, which lives in
+    row p + go at slot i with go*pack + i = j + dx: per filter row one group per needed `go`, whose weight block
+    [(j, n), (i, c)] is W[dx = go*pack + i - j] (zero when that is no tap) — every K tile is an ALIGNED 128-byte row
+    (one TMA request per row; the overlapping-row fusion below costs two), and a tile covers 128*pack positions.
+    C < 64, fused: the 128-byte row of position q runs over positions q .. q+64/C-1 (row pitch = position pitch).
+    """
     def padded(w):
         out = torch.zeros(cout_pad, C)
         out[:w.shape[0], :w.shape[1]] = w
         return out
+    pk = 64 // C if C < 64 else 1
+    if C < 64 and PACK_POSITIONS and Wp % pk == 0 and pk * cout_pad <= 256:
+        offs, mats = [], []
+        for dy in sorted({t[0] for t in taps}):
+            row = {dx: padded(w) for y, dx, w in taps if y == dy}
+            for go in sorted({(dx + j) // pk for dx in row for j in range(pk)}):
+                m = torch.zeros(pk * cout_pad, 64)
+                for j in range(pk):
+                    for i in range(pk):
+                        dx = go * pk + i - j
+                        if dx in row:
+                            m[j * cout_pad:(j + 1) * cout_pad, i * C:(i + 1) * C] = row[dx]
+                offs.append(dy * (Wp // pk) + go)
+                mats.append(m)
+        return offs, torch.stack(mats), 64, 64, pk
     single = len({(t[0]) for t in taps}) == len(taps)          # one tap per row (1x1 convs): nothing to fuse, and a
     if C >= 64 or not FUSE_TAPS or single:                    # K = 64 tile would fetch 64/C times the bytes it needs
         Kt = 64 if C >= 64 else C
         offs = [dy * Wp + dx for dy, dx, _ in taps]
-        return offs, torch.stack([padded(w) for _, _, w in taps]), C, Kt
+        return offs, torch.stack([padded(w) for _, _, w in taps]), C, Kt, 1
     f = 64 // C
     offs, mats = [], []
     for dy in sorted({t[0] for t in taps}):
@@ -80,7 +105,7 @@ def _groups(taps, C, Wp, cout_pad):
             todo = [d for d in todo if d >= dx0 + f]
             offs.append(dy * Wp + dx0)
             mats.append(m)
-    return offs, torch.stack(mats), 64, 64
+    return offs, torch.stack(mats), 64, 64, 1
 
 
 class Plan:
@@ -91,6 +116,7 @@ class Plan:
         self.vin = Volume(B, R, R, 16, device)
         self.out = torch.zeros(B, R, R, 3, dtype=torch.float32, device=device)
         self.marks = []                  # (name, Volume) of the stem / resBlock / transposed-conv outputs, in network order
+        self.model_flops = 0             # 2 * MACs of the network itself (no padding, no zero-weight fused taps), per batch
         self.flops = 0                   # MMA work actually issued (2 * rows_valid * Kg * groups * Cout_pad), per batch
 
     # ---- building -------------------------------------------------------------------------------
@@ -100,11 +126,11 @@ class Plan:
         dev = self.device
         cp = _pad16(cout)
         packed = [_groups(t, vin.C, vin.Wp, cp) for t in phases]
-        n_groups = max(len(o) for o, _, _, _ in packed)
-        Kg, Kt = packed[0][2], packed[0][3]
-        w = torch.zeros(len(phases), n_groups, cp, Kg)
+        n_groups = max(len(pk[0]) for pk in packed)
+        Kg, Kt, pack = packed[0][2], packed[0][3], packed[0][4]
+        w = torch.zeros(len(phases), n_groups, pack * cp, Kg)
         offs = []
-        for i, (o, m, _, _) in enumerate(packed):
+        for i, (o, m, _, _, _) in enumerate(packed):
             w[i, :len(o)] = m
             offs += o + [0] * (n_groups - len(o))
 
@@ -115,20 +141,22 @@ class Plan:
             o[:cout] = v.detach().float().cpu()
             return o.to(dev)
         spec = {"a": vin, "w": w.reshape(-1, Kg).to(torch.bfloat16).to(dev), "Kg": Kg, "Kt": Kt, "n_phases": len(phases),
-                "n_groups": n_groups, "tap_off": offs, "Cout_pad": cp, "Cout": cout, "alpha": vec(alpha, 0.0),
+                "n_groups": n_groups, "tap_off": offs, "pack": pack, "Cout_pad": cp, "Cout": cout, "alpha": vec(alpha, 0.0),
                 "beta": vec(beta, 0.0), "gamma": vec(gamma, 0.0), "act": act, "mode": mode, "out": out, "res": res,
                 "aux": aux, "out_scale": out_scale,
                 "valid": (0, 0, vin.H // 2, vin.W // 2) if vin.s2d else (P, P, vin.H, vin.W)}
         # (padded channels: zero weights, alpha = beta = 0 -> ReLU gives 0; the sigmoid layer stores only Cout channels)
         self.specs.append(spec)
-        self.flops += 2 * vin.B * spec["valid"][2] * spec["valid"][3] * Kg * n_groups * len(phases) * cp
+        self.model_flops += 2 * vin.B * spec["valid"][2] * spec["valid"][3] * sum(int((m != 0).sum()) for t in phases for _, _, m in t)
+        self.flops += 2 * vin.B * spec["valid"][2] * spec["valid"][3] * Kg * n_groups * len(phases) * cp     # (pack cancels)
         return out
 
     # ---- running on the GPU ---------------------------------------------------------------------
     def _desc(self, s):
         d = _Desc()
         a = s["a"]
-        d.a, d.rows, d.C, d.Hp, d.Wp = a.t.data_ptr(), a.rows, a.C, a.Hp, a.Wp
+        d.a, d.rows, d.C, d.Hp, d.Wp = a.t.data_ptr(), a.rows // s["pack"], a.C, a.Hp, a.Wp
+        d.pack = s["pack"]
         d.vy0, d.vx0, d.H, d.W = s["valid"]
         d.w, d.w_pitch, d.Kg, d.Kt = s["w"].data_ptr(), s["Kg"], s["Kg"], s["Kt"]
         d.n_phases, d.n_groups = s["n_phases"], s["n_groups"]

@@ -10,11 +10,14 @@ epilogue, bf16 rounding where the kernel stores bf16.
 import torch
 
 
-def _windows(vol, Kg):
+def _windows(vol, Kg, pack=1):
     """A matrix the kernel's TMA boxes see: row q = the Kg values starting at position q's channel 0 (runs over the
-    following positions when C < Kg; rows outside the volume read as zero)."""
+    following positions when C < Kg; rows outside the volume read as zero).  pack > 1: row q = positions q*pack ..
+    q*pack+pack-1 (aligned, pack*C == Kg)."""
     flat = vol.t.reshape(-1).float()
     C = vol.C
+    if pack > 1:
+        return flat[:vol.rows * C].reshape(vol.rows // pack, pack * C)
     if C >= Kg:
         return vol.t[:vol.rows, :Kg].float()
     idx = torch.arange(vol.rows)[:, None] * C + torch.arange(Kg)[None, :]
@@ -24,8 +27,11 @@ def _windows(vol, Kg):
 def run_launch(s):
     a = s["a"]
     rows, Kg, cp, G, NP = a.rows, s["Kg"], s["Cout_pad"], s["n_groups"], s["n_phases"]
-    A = _windows(a, Kg)                                                  # (rows, Kg)
-    W = s["w"].float().reshape(NP, G, cp, Kg)
+    pack = s.get("pack", 1)
+    mrows = rows // pack                                                 # matrix rows
+    A = _windows(a, Kg, pack)                                            # (mrows, Kg)
+    W = s["w"].float().reshape(NP, G, pack * cp, Kg)
+    qm = torch.arange(mrows)
     q = torch.arange(rows)
     b = q // (a.Hp * a.Wp)
     r = q % (a.Hp * a.Wp)
@@ -35,15 +41,15 @@ def run_launch(s):
     valid = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < Wd)
     out = s["out"]
     for ph in range(NP):
-        acc = torch.zeros(rows, cp)
+        acc = torch.zeros(mrows, pack * cp)
         for g in range(G):
             off = s["tap_off"][ph * G + g]
-            src = q + off
-            ok = (src >= 0) & (src < rows)
-            Ag = torch.zeros(rows, Kg)
+            src = qm + off
+            ok = (src >= 0) & (src < mrows)
+            Ag = torch.zeros(mrows, Kg)
             Ag[ok] = A[src[ok]]
             acc += Ag @ W[ph, g].t()
-        v = acc
+        v = acc.reshape(rows, cp)                                         # columns [j*cp, (j+1)*cp) -> position q*pack + j
         if s["alpha"] is not None:
             v = v * s["alpha"].float().cpu()
         if s["beta"] is not None:

@@ -24,21 +24,15 @@ def test_plain_gemm_against_fp32(native_lib, cuda, M, K, N):
     assert float((out - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))     # fp32 accumulation order only
 
 
-@pytest.mark.parametrize("fuse", [True, False])
-def test_cnn_plan_launch_by_launch_against_cpu_statement(native_lib, cuda, fuse):
-    from lipreading_b200 import prnet_tc5
+@pytest.mark.parametrize("layout", ["packed", "fused", "plain"])
+def test_cnn_plan_launch_by_launch_against_cpu_statement(native_lib, cuda, layout):
     from oracle import tapgemm as OT
-    from test_prnet_plan import randomized_net
+    from test_prnet_plan import compile_with_layout, randomized_net
     net = randomized_net(3)
     B, R = 3, 64
     x = torch.rand(B, R, R, 3, generator=torch.Generator().manual_seed(5))
-    saved = prnet_tc5.FUSE_TAPS
-    prnet_tc5.FUSE_TAPS = fuse
-    try:
-        cpu = prnet_tc5.compile_plan(net, B, R, "cpu")
-        dev = prnet_tc5.compile_plan(net, B, R, cuda)
-    finally:
-        prnet_tc5.FUSE_TAPS = saved
+    cpu = compile_with_layout(layout, net, B, R, "cpu")
+    dev = compile_with_layout(layout, net, B, R, cuda)
     want = OT.run_plan(cpu, x)
     got = dev.run(x.to(cuda))
     torch.cuda.synchronize()

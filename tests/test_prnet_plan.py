@@ -43,17 +43,26 @@ def layer_outputs(net, x_nhwc):
     return acts, y
 
 
-@pytest.mark.parametrize("fuse", [True, False])
-def test_plan_replayed_on_cpu_matches_resfcn256(fuse):
+LAYOUTS = {"packed": (True, True), "fused": (False, True), "plain": (False, False)}     # (PACK_POSITIONS, FUSE_TAPS)
+
+
+def compile_with_layout(layout, net, B, R, device):
+    """the three ways a C < 64 layer can be laid out for the kernel (prnet_tc5._groups); packed is the default"""
+    saved = prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS
+    prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS = LAYOUTS[layout]
+    try:
+        return prnet_tc5.compile_plan(net, B, R, device)
+    finally:
+        prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS = saved
+
+
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+def test_plan_replayed_on_cpu_matches_resfcn256(layout):
     net = randomized_net()
     B, R = 2, 32
     x = torch.rand(B, R, R, 3, generator=torch.Generator().manual_seed(1))
-    saved = prnet_tc5.FUSE_TAPS
-    prnet_tc5.FUSE_TAPS = fuse
-    try:
-        plan = prnet_tc5.compile_plan(net, B, R, "cpu")
-    finally:
-        prnet_tc5.FUSE_TAPS = saved
+    plan = compile_with_layout(layout, net, B, R, "cpu")
+    assert any(s["pack"] > 1 for s in plan.specs) == (layout == "packed")
     assert len(plan.specs) == 53                       # 1 stem + 5*4 + 5*3 resBlock launches + 17 transposed convs
     y = OT.run_plan(plan, x)
     acts, ref = layer_outputs(net, x)
@@ -76,16 +85,33 @@ def test_fused_tap_groups_cover_each_tap_once():
     """C = 16: the four x-taps of a filter row share one K = 64 tile; C = 32: two tiles per row; C >= 64: one per tap."""
     w = torch.randn(16, 16, 4, 4)
     taps = prnet_tc5._conv_taps(w, 4, False)
-    offs, mats, Kg, Kt = prnet_tc5._groups(taps, 16, 100, 16)
-    assert (Kg, Kt, len(offs)) == (64, 64, 4) and offs == [(ky - 1) * 100 - 1 for ky in range(4)]
+    saved = prnet_tc5.PACK_POSITIONS
+    prnet_tc5.PACK_POSITIONS = False
+    try:
+        offs, mats, Kg, Kt, pack = prnet_tc5._groups(taps, 16, 100, 16)
+        assert (Kg, Kt, len(offs), pack) == (64, 64, 4, 1) and offs == [(ky - 1) * 100 - 1 for ky in range(4)]
+        for ky in range(4):
+            for kx in range(4):
+                assert torch.equal(mats[ky][:, kx * 16:(kx + 1) * 16], w[:, :, ky, kx])
+        w32 = torch.randn(32, 32, 4, 4)
+        offs, mats, Kg, Kt, pack = prnet_tc5._groups(prnet_tc5._conv_taps(w32, 4, False), 32, 100, 32)
+        assert len(offs) == 8 and Kg == 64
+    finally:
+        prnet_tc5.PACK_POSITIONS = saved
+    # packed: rows of 4 positions; taps dx = -1..2 reach the row groups -1, 0, +1 -> 3 aligned K tiles per filter row, and
+    # block (j, i) of group go holds W[dx = 4*go + i - j]
+    offs, mats, Kg, Kt, pack = prnet_tc5._groups(taps, 16, 100, 16)
+    assert (Kg, Kt, pack, len(offs)) == (64, 64, 4, 12) and offs[:3] == [-25 - 1, -25, -25 + 1]
     for ky in range(4):
-        for kx in range(4):
-            assert torch.equal(mats[ky][:, kx * 16:(kx + 1) * 16], w[:, :, ky, kx])
-    w = torch.randn(32, 32, 4, 4)
-    offs, mats, Kg, Kt = prnet_tc5._groups(prnet_tc5._conv_taps(w, 4, False), 32, 100, 32)
-    assert len(offs) == 8 and Kg == 64
-    offs, mats, Kg, Kt = prnet_tc5._groups(prnet_tc5._conv_taps(torch.randn(64, 64, 4, 4), 4, False), 64, 100, 64)
-    assert len(offs) == 16 and Kg == 64 and Kt == 64
+        for g, go in enumerate((-1, 0, 1)):
+            m = mats[3 * ky + g]
+            for j in range(4):
+                for i in range(4):
+                    dx = 4 * go + i - j
+                    blk = m[j * 16:(j + 1) * 16, i * 16:(i + 1) * 16]
+                    assert torch.equal(blk, w[:, :, ky, dx + 1]) if -1 <= dx <= 2 else float(blk.abs().max()) == 0.0
+    offs, mats, Kg, Kt, pack = prnet_tc5._groups(prnet_tc5._conv_taps(torch.randn(64, 64, 4, 4), 4, False), 64, 100, 64)
+    assert len(offs) == 16 and Kg == 64 and Kt == 64 and pack == 1
     # transposed stride-2 conv: 4 phases x 4 taps, each kernel element used exactly once
     wt = torch.randn(32, 16, 4, 4)
     phases = prnet_tc5._deconv_phases(wt, 2)
