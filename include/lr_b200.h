@@ -288,6 +288,7 @@ typedef struct lr_tapgemm_desc {
   const void* res; int resC;
   void* aux; int aHp, aWp, aC, apad;
   float out_scale;
+  int flags;            /* bit 0: never keep the weights / input chunk resident (test hook: stream every tap's tiles) */
   int pack;             /* 0/1, or 2 / 4: a matrix row holds `pack` horizontally adjacent positions (pack*C == Kt = 64):
                          * `rows` counts matrix rows, tap_off is in matrix rows, w has pack*Cout_pad rows per
                          * (phase, group) — accumulator columns [j*Cout_pad, (j+1)*Cout_pad) are position q*pack + j */

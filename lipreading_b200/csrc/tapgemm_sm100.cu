@@ -45,6 +45,9 @@ struct TgParams {
   int Kt, a_tile_bytes;          // K tile (elements) and bytes of the A tile
   int stages, stage_bytes;
   int n_acc;                     // accumulator buffers in use (power of two)
+  // resident mode (small K, many taps): ALL weight tiles stay in shared memory, and per work item ONE chunk of
+  // 128 + (max_off - min_off) rows is loaded; every tap's A operand is a descriptor into that chunk
+  int resident, n_wtiles, w_tile_bytes, w_bytes, chunk_boxes, min_off;
   int rows, HpWp, Wp, vy0, vx0, H, W;
   int mode, act;
   int oHp, oWp, oC, opy, opx;
@@ -91,13 +94,15 @@ __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TgParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)p.stages * p.stage_bytes);
+  uint8_t* wbase = base + (size_t)p.stages * p.stage_bytes;               // resident weight tiles (resident mode)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + p.w_bytes);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + kMaxStages;
   uint64_t* bar_acc_full = bars + 2 * kMaxStages;
   uint64_t* bar_acc_empty = bars + 2 * kMaxStages + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc);
-  float* vecs = reinterpret_cast<float*>(tmem_slot + 4);       // [kEpiGroups][3][kMaxN]: alpha, beta, gamma of the current N tile
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(tmem_slot + 4);
+  float* vecs = reinterpret_cast<float*>(bar_w + 2);       // [kEpiGroups][3][kMaxN]: alpha, beta, gamma of the current N tile
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   uint32_t tmem_cols = 32;
@@ -111,6 +116,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       lr_mbar_init(&bar_acc_full[b], 1);
       lr_mbar_init(&bar_acc_empty[b], 128);
     }
+    lr_mbar_init(bar_w, 1);
     lr_fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -123,6 +129,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     uint32_t it = 0;
+    if (p.resident) {
+      if (elect_one()) {
+        lr_mbar_expect_tx(bar_w, p.w_bytes);
+        for (int t = 0; t < p.n_wtiles; ++t)
+          tma_load_2d(wbase + (size_t)t * p.w_tile_bytes, &map_w, 0, t * p.Nrow, bar_w);
+      }
+      __syncwarp();
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int r = (int)fdiv((uint32_t)item, p.d_mtiles), m = item - r * p.n_mtiles;
+        const int s = it % p.stages;
+        lr_mbar_wait(&bar_empty[s], ((it / p.stages) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* st = base + (size_t)s * p.stage_bytes;
+          lr_mbar_expect_tx(&bar_full[s], p.stage_bytes);
+          for (int bx = 0; bx < p.chunk_boxes; ++bx)
+            tma_load_2d(st + (size_t)bx * p.a_tile_bytes, &map_a, 0, m * kBM + p.min_off + bx * kBM, &bar_full[s]);
+        }
+        __syncwarp();
+      }
+    } else
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int r = (int)fdiv((uint32_t)item, p.d_mtiles), m = item - r * p.n_mtiles;
       const int ph = (int)fdiv((uint32_t)r, p.d_ntiles), nt = r - ph * p.n_ntiles;
@@ -152,6 +178,30 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       lr_mbar_wait(&bar_acc_empty[buf], ((n / (uint32_t)p.n_acc) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d = tmem_base + buf * (uint32_t)p.Ntile;
+      if (p.resident) {
+        if (n == 0) lr_mbar_wait(bar_w, 0);
+        const int ph = (int)fdiv(fdiv((uint32_t)item, p.d_mtiles), p.d_ntiles);
+        const int s = it % p.stages;
+        lr_mbar_wait(&bar_full[s], (it / p.stages) & 1);
+        if (elect_one()) {
+          const uint32_t c_addr = lr_smem_u32(base + (size_t)s * p.stage_bytes);
+          const uint32_t w_addr = lr_smem_u32(wbase);
+          for (int g = 0; g < p.n_groups; ++g) {
+            const int pg = ph * p.n_groups + g;
+            // tap = row offset into the resident chunk (rows are Kt*2 bytes; the swizzle follows absolute addresses)
+            const uint64_t ad = make_desc(c_addr + (uint32_t)(p.tap_off[pg] - p.min_off) * (uint32_t)(p.Kt * 2), p.desc_hi);
+            const uint64_t bd = make_desc(w_addr + (uint32_t)pg * (uint32_t)p.w_tile_bytes, p.desc_hi);
+            const int n_kk = p.Kt >> 4;
+#pragma unroll 4
+            for (int kk = 0; kk < n_kk; ++kk) umma_bf16(d, ad + 2 * kk, bd + 2 * kk, p.idesc, (g > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[s]);
+          umma_commit(&bar_acc_full[buf]);
+        }
+        __syncwarp();
+        ++it;
+        continue;
+      }
       for (int k = 0; k < n_k; ++k, ++it) {
         const int s = it % p.stages;
         lr_mbar_wait(&bar_full[s], (it / p.stages) & 1);
@@ -422,6 +472,28 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
   p.stage_bytes = p.a_tile_bytes + ntile * Kt * 2;
   p.stages = kSmemCap / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  {
+    // resident mode: one K tile per group, several groups, one N tile, and everything fits: weights + >= 2 chunks
+    int mn = d->tap_off[0], mx = d->tap_off[0];
+    for (int i = 1; i < d->n_phases * d->n_groups; ++i) {
+      mn = d->tap_off[i] < mn ? d->tap_off[i] : mn;
+      mx = d->tap_off[i] > mx ? d->tap_off[i] : mx;
+    }
+    const int boxes = lr_div_up(kBM + mx - mn, kBM);
+    const int wt = p.Nrow * Kt * 2, nw = d->n_phases * d->n_groups;
+    const long long need = (long long)nw * wt + 2ll * boxes * p.a_tile_bytes;
+    if (!(d->flags & 1) && p.n_chunks == 1 && p.n_ntiles == 1 && d->n_groups >= 3 && Crow >= Kt && need <= kSmemCap) {
+      p.resident = 1;
+      p.n_wtiles = nw;
+      p.w_tile_bytes = wt;
+      p.w_bytes = nw * wt;
+      p.chunk_boxes = boxes;
+      p.min_off = mn;
+      p.stage_bytes = boxes * p.a_tile_bytes;
+      p.stages = (kSmemCap - p.w_bytes) / p.stage_bytes;
+      if (p.stages > 4) p.stages = 4;
+    }
+  }
   p.n_acc = ntile <= 64 ? 8 : (ntile <= 128 ? 4 : 2);
   p.rows = (int)d->rows;
   p.HpWp = d->Hp * d->Wp; p.Wp = d->Wp; p.vy0 = d->vy0; p.vx0 = d->vx0; p.H = d->H; p.W = d->W;
@@ -460,7 +532,7 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
   LR_CHECK_ARG(d->w_pitch >= d->Kg && d->w_pitch % 8 == 0, "lr_tapgemm: weight row pitch must be >= Kg and a multiple of 8");
   rc = make_map_bf16_strided(&map_w, d->w, (uint64_t)d->Kg, w_rows, (uint64_t)d->w_pitch * 2, Kt, (uint32_t)ntile, Kt * 2);
   if (rc != LR_OK) return rc;
-  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + (2 * kMaxStages + 2 * kMaxAcc) * 8 + 16 +
+  const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + p.w_bytes + (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16 +
                             kEpiGroups * 3 * kMaxN * sizeof(float) + 1024;
   const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
 #define LR_TG_LAUNCH(M, P)                                                                                             \

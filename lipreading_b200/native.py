@@ -71,7 +71,7 @@ class TapGemmDesc(ctypes.Structure):
                 ("opy", ctypes.c_int), ("opx", ctypes.c_int),
                 ("res", ctypes.c_void_p), ("resC", ctypes.c_int),
                 ("aux", ctypes.c_void_p), ("aHp", ctypes.c_int), ("aWp", ctypes.c_int), ("aC", ctypes.c_int),
-                ("apad", ctypes.c_int), ("out_scale", ctypes.c_float), ("pack", ctypes.c_int)]
+                ("apad", ctypes.c_int), ("out_scale", ctypes.c_float), ("flags", ctypes.c_int), ("pack", ctypes.c_int)]
 
 
 # include/lr_b200_diag.h — measurement hooks and micro-benchmarks, only in liblr_b200_diag.so (tools/ use them)

@@ -28,6 +28,7 @@ from . import native
 
 P = 2                                    # border of every normal volume
 FUSE_TAPS = True                         # C < 64: fuse 64/C adjacent x-taps into one 128-byte K tile
+RESIDENT = True                          # let the kernel keep a layer's weights + one input chunk per tile in shared memory
 PACK_POSITIONS = True                    # C < 64: a matrix row = 64/C adjacent positions (block-Toeplitz weights), see _groups
 
 
@@ -141,7 +142,7 @@ class Plan:
             o[:cout] = v.detach().float().cpu()
             return o.to(dev)
         spec = {"a": vin, "w": w.reshape(-1, Kg).to(torch.bfloat16).to(dev), "Kg": Kg, "Kt": Kt, "n_phases": len(phases),
-                "n_groups": n_groups, "tap_off": offs, "pack": pack, "Cout_pad": cp, "Cout": cout, "alpha": vec(alpha, 0.0),
+                "n_groups": n_groups, "tap_off": offs, "pack": pack, "flags": 0 if RESIDENT else 1, "Cout_pad": cp, "Cout": cout, "alpha": vec(alpha, 0.0),
                 "beta": vec(beta, 0.0), "gamma": vec(gamma, 0.0), "act": act, "mode": mode, "out": out, "res": res,
                 "aux": aux, "out_scale": out_scale,
                 "valid": (0, 0, vin.H // 2, vin.W // 2) if vin.s2d else (P, P, vin.H, vin.W)}
@@ -156,7 +157,7 @@ class Plan:
         d = _Desc()
         a = s["a"]
         d.a, d.rows, d.C, d.Hp, d.Wp = a.t.data_ptr(), a.rows // s["pack"], a.C, a.Hp, a.Wp
-        d.pack = s["pack"]
+        d.pack, d.flags = s["pack"], s["flags"]
         d.vy0, d.vx0, d.H, d.W = s["valid"]
         d.w, d.w_pitch, d.Kg, d.Kt = s["w"].data_ptr(), s["Kg"], s["Kg"], s["Kt"]
         d.n_phases, d.n_groups = s["n_phases"], s["n_groups"]

@@ -24,7 +24,7 @@ def test_plain_gemm_against_fp32(native_lib, cuda, M, K, N):
     assert float((out - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))     # fp32 accumulation order only
 
 
-@pytest.mark.parametrize("layout", ["packed", "fused", "plain"])
+@pytest.mark.parametrize("layout", ["packed", "fused", "plain", "streamed"])
 def test_cnn_plan_launch_by_launch_against_cpu_statement(native_lib, cuda, layout):
     from oracle import tapgemm as OT
     from test_prnet_plan import compile_with_layout, randomized_net

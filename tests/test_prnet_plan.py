@@ -43,20 +43,22 @@ def layer_outputs(net, x_nhwc):
     return acts, y
 
 
-LAYOUTS = {"packed": (True, True), "fused": (False, True), "plain": (False, False)}     # (PACK_POSITIONS, FUSE_TAPS)
+# (PACK_POSITIONS, FUSE_TAPS, RESIDENT); "streamed": the packed layout with every tap's tiles streamed through the ring
+LAYOUTS = {"packed": (True, True, True), "fused": (False, True, True), "plain": (False, False, True),
+           "streamed": (True, True, False)}
 
 
 def compile_with_layout(layout, net, B, R, device):
     """the three ways a C < 64 layer can be laid out for the kernel (prnet_tc5._groups); packed is the default"""
-    saved = prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS
-    prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS = LAYOUTS[layout]
+    saved = prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS, prnet_tc5.RESIDENT
+    prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS, prnet_tc5.RESIDENT = LAYOUTS[layout]
     try:
         return prnet_tc5.compile_plan(net, B, R, device)
     finally:
-        prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS = saved
+        prnet_tc5.PACK_POSITIONS, prnet_tc5.FUSE_TAPS, prnet_tc5.RESIDENT = saved
 
 
-@pytest.mark.parametrize("layout", list(LAYOUTS))
+@pytest.mark.parametrize("layout", ["packed", "fused", "plain"])
 def test_plan_replayed_on_cpu_matches_resfcn256(layout):
     net = randomized_net()
     B, R = 2, 32
