@@ -131,14 +131,18 @@ def configure_throughput_path():
     that restores the parity-path defaults.  tests/test_gpu_bench_config.py holds exactly this configuration to the
     fp32 CPU port."""
     from lipreading_b200 import conv_frontend, functional as LF
-    saved = (LF.GEMM_DTYPE, LF.RNN_CLUSTER, conv_frontend.OUT_DTYPE, LF.PROJ_VARIANT)
+    saved = (LF.GEMM_DTYPE, LF.RNN_CLUSTER, conv_frontend.OUT_DTYPE, LF.PROJ_VARIANT, LF.GEMM_TCGEN05)
     LF.GEMM_DTYPE = torch.bfloat16              # plain GEMMs: bf16 operands, fp32 accumulate
     LF.RNN_CLUSTER = True                       # persistent cluster recurrence (bf16 operands, fp32 state)
     conv_frontend.OUT_DTYPE = torch.bfloat16    # the conv3 epilogue's bf16 features feed the bf16 input GEMM directly
     LF.PROJ_VARIANT = 2                         # projection + log-softmax on tcgen05 kind::tf32
+    # the four plain GEMMs around the recurrent kernel stay on cuBLAS (measured: 12.81 ms/step against 13.46 with them on
+    # lr_tapgemm — their K-major transposes and a one-CTA tile without multicast cost more than the library call);
+    # LR_GEMM_TCGEN05=1 routes them through this repo's kernel
+    LF.GEMM_TCGEN05 = os.environ.get("LR_GEMM_TCGEN05", "0") == "1"
 
     def restore():
-        LF.GEMM_DTYPE, LF.RNN_CLUSTER, conv_frontend.OUT_DTYPE, LF.PROJ_VARIANT = saved
+        LF.GEMM_DTYPE, LF.RNN_CLUSTER, conv_frontend.OUT_DTYPE, LF.PROJ_VARIANT, LF.GEMM_TCGEN05 = saved
     return restore
 
 

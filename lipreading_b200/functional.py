@@ -217,6 +217,21 @@ def proj_masked_log_softmax(hidden, weight, bias, log_mask):
 GEMM_DTYPE = torch.float32
 # True: run the recurrence on the persistent cluster kernels (bf16 operands) when the shape allows it
 RNN_CLUSTER = False
+# True (with GEMM_DTYPE = bfloat16): the four plain GEMMs around the recurrent kernel (x @ W_ih^T + b_ih, dX, dW_ih, dW_hh)
+# run on this repo's tcgen05 tap-GEMM kernel (lr_tapgemm, store mode 3) instead of cuBLAS
+GEMM_TCGEN05 = False
+
+
+def _tc_ok(K, Nn):
+    return GEMM_TCGEN05 and GEMM_DTYPE == torch.bfloat16 and K >= 64 and K % 8 == 0 and Nn % 16 == 0
+
+
+def _mm_nt(a, w, bias=None, out_dtype=torch.float32):
+    """a (M,K) @ w (N,K)^T [+ bias]: both operands K-major, the orientation the tensor-core kernel reads."""
+    if _tc_ok(a.shape[1], w.shape[0]):
+        r = tap_linear(N.cont(_lowp(a)), N.cont(_lowp(w)), bias)
+        return r if out_dtype == torch.float32 else r.to(out_dtype)
+    return _mm(a, w.t(), bias=bias, out_dtype=out_dtype)
 
 
 def _lowp(t):
@@ -284,7 +299,7 @@ class _RNNLayer(torch.autograd.Function):
         b_hh = torch.stack([weights[4 * d + 3] for d in range(D)], 0).contiguous()
         if GEMM_DTYPE != torch.float32:
             w_ih = _lowp(w_ih)            # converted while contiguous (a .to() of the transposed view is a strided copy)
-        gi = _mm(x2, w_ih.t(), bias=b_ih)                                       # plain GEMM -> cuBLAS
+        gi = _mm_nt(x2, w_ih, bias=b_ih)                                        # plain GEMM: lr_tapgemm or cuBLAS
         lens32 = N.cont(lens, torch.int32)
         dev = x.device
         hidden = torch.empty((B, T, D * H), dtype=torch.float32, device=dev)
@@ -345,14 +360,20 @@ class _RNNLayer(torch.autograd.Function):
         d_b_hh = d_gh2.sum(0)
         if GEMM_DTYPE != torch.float32:                                         # one conversion per operand
             d_gi2, d_gh2, h_prev3 = _lowp(d_gi2), _lowp(d_gh2), _lowp(h_prev3)
-        d_w_ih = _mm(d_gi2.t(), x2)                                             # (D*G*H, I)
+        tc = _tc_ok(B * T, I) and _tc_ok(B * T, H)
+        # (the K-major operands the tensor-core kernel wants are the transposes: one bf16 copy each)
+        d_w_ih = _mm_nt(d_gi2.t().contiguous(), x2.t().contiguous()) if tc else _mm(d_gi2.t(), x2)       # (D*G*H, I)
         d_gh3 = d_gh2.reshape(B * T, D, G * H)
         grads = []
         for d in range(D):
-            d_w_hh = _mm(d_gh3[:, d].t(), h_prev3[:, d])                        # (G*H, H)
+            d_w_hh = _mm_nt(d_gh3[:, d].t().contiguous(), h_prev3[:, d].t().contiguous()) if tc \
+                else _mm(d_gh3[:, d].t(), h_prev3[:, d])                        # (G*H, H)
             grads += [d_w_ih[d * G * H:(d + 1) * G * H], d_w_hh, d_b_ih[d * G * H:(d + 1) * G * H],
                       d_b_hh[d * G * H:(d + 1) * G * H]]
-        d_x = _mm(d_gi2, w_ih, out_dtype=ctx.x_dtype).reshape(B, T, I) if ctx.x_needs_grad else None
+        d_x = None
+        if ctx.x_needs_grad:
+            d_x = (_mm_nt(d_gi2, w_ih.t().contiguous(), out_dtype=ctx.x_dtype) if _tc_ok(D * G * H, I)
+                   else _mm(d_gi2, w_ih, out_dtype=ctx.x_dtype)).reshape(B, T, I)
         return (d_x, None, None) + tuple(grads)
 
 

@@ -62,3 +62,34 @@ def test_cnn_at_256_against_fp32_module(native_lib, cuda):
     # a second batch size compiles its own plan; numpy in -> numpy out like the reference's predict()
     one = pred.predict(x[0].cpu().numpy())
     assert float(abs(one - got[0].cpu().numpy()).max()) <= 1e-3 * pred.MaxPos
+
+
+def test_recurrent_layer_gemms_on_tapgemm_match_library(native_lib, cuda):
+    """functional.GEMM_TCGEN05: x @ W_ih^T + b_ih, dX, dW_ih, dW_hh of the recurrent layer (better_model.py:47-49,74) on
+    lr_tapgemm give what the library GEMMs give on the same bf16 operands (fp32 accumulation order only)."""
+    from lipreading_b200 import functional as LF
+    g = torch.Generator().manual_seed(9)
+    B, T, I, H = 32, 20, 192, 128
+    x = torch.randn(B, T, I, generator=g).to(cuda).to(torch.bfloat16)
+    lens = torch.full((B,), T, dtype=torch.int32, device=cuda)
+    ws = []
+    for _ in range(2):
+        ws += [(torch.randn(3 * H, I, generator=g) / I ** 0.5).to(cuda), (torch.randn(3 * H, H, generator=g) / H ** 0.5).to(cuda),
+               torch.randn(3 * H, generator=g).to(cuda) * 0.1, torch.randn(3 * H, generator=g).to(cuda) * 0.1]
+    saved = LF.GEMM_DTYPE, LF.GEMM_TCGEN05
+    out = {}
+    try:
+        for tc in (False, True):
+            LF.GEMM_DTYPE, LF.GEMM_TCGEN05 = torch.bfloat16, tc
+            xs = x.clone().requires_grad_(True)
+            wl = [w.clone().requires_grad_(True) for w in ws]
+            n0 = native_lib.lr_launch_count()
+            hidden, h_n = LF.rnn_layer(xs, lens, "GRU", wl)
+            (hidden.square().sum() + h_n.sum()).backward()
+            out[tc] = [hidden.detach(), xs.grad.float()] + [w.grad for w in wl]
+            out[(tc, "launches")] = native_lib.lr_launch_count() - n0
+    finally:
+        LF.GEMM_DTYPE, LF.GEMM_TCGEN05 = saved
+    assert out[(True, "launches")] == out[(False, "launches")] + 5          # gi, dX, dW_ih, 2 x dW_hh
+    for a, b in zip(out[False], out[True]):
+        assert float((a - b).abs().max()) <= 1e-2 * max(1e-3, float(a.abs().max()))
