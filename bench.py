@@ -551,8 +551,13 @@ def main():
 
     # ---- end to end: pinned host batches, H2D inside the timed region, loss read back each step ----
     from lipreading_b200.data import DevicePrefetcher
+    trace = [] if os.environ.get("LR_E2E_TRACE") else None
+    copy_trace = [] if trace is not None else None
+
     def host_loader(n):
-        return DevicePrefetcher([host[i % 2] for i in range(n)], dev)
+        pf = DevicePrefetcher([host[i % 2] for i in range(n)], dev)
+        pf.trace = copy_trace
+        return pf
     # every step's loss is read back to the host inside the timed region, through a pinned staging
     # slot and an event (the value is collected one step later, so the read does not stall the queue)
     losses, pending = [], []
@@ -560,15 +565,20 @@ def main():
 
     def read_back(loss):
         i = len(pending)
+        t_in = time.perf_counter()
         slots[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = torch.cuda.Event(enable_timing=trace is not None)
         ev.record()
         pending.append(ev)
         if i > 0:
             pending[i - 1].synchronize()
             losses.append(float(slots[i - 1]))
+        if trace is not None:
+            trace.append((t_in, time.perf_counter()))
     run(host_loader, 3)
     pending.clear()
+    if trace is not None:
+        del trace[:], copy_trace[:]
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -578,6 +588,19 @@ def main():
     losses.append(float(slots[len(pending) - 1]))
     t1.record()
     barrier()
+    if trace is not None:
+        # per step: host time from one read_back entry to the next (enqueue of a whole step), time blocked in the
+        # read-back synchronize, GPU completion time of the step and duration of each H2D copy (ms)
+        torch.cuda.synchronize()
+        t_host0 = trace[0][0]
+        rec = {"rank": rank, "host_enter_ms": [(a - t_host0) * 1e3 for a, _ in trace],
+               "host_blocked_ms": [(b - a) * 1e3 for a, b in trace],
+               "gpu_step_end_ms": [t0.elapsed_time(e) for e in pending],
+               "copy_ms": [a.elapsed_time(b) for a, b in copy_trace],
+               "copy_start_ms": [t0.elapsed_time(a) for a, _ in copy_trace],
+               "total_ms": t0.elapsed_time(t1)}
+        with open(os.path.join(ROOT, "gpurun_out", "e2e_trace_rank%d.json" % rank), "w") as fh:
+            json.dump(rec, fh)
     te = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)

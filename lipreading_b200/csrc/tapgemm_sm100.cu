@@ -32,7 +32,7 @@ constexpr int kMaxBK = 64;                    // bf16 per K tile: 64 (128-byte s
 constexpr int kMaxStages = 24;                // small-K layers: many small stages keep enough bytes in flight
 constexpr int kMaxAcc = 8;                    // TMEM accumulator buffers (Ntile <= 64: 8, 128: 4, 256: 2)
 constexpr int kEpiGroups = 2;                 // epilogue warp quartets (alternate work items)
-constexpr int kThreads = 32 * (2 + 4 * kEpiGroups);
+constexpr int kThreads = 32 * (2 + 4 * kEpiGroups + 1);   // + a second MMA-issuing warp (warp 10)
 constexpr int kMaxN = 256;                    // widest N tile
 constexpr int kMaxTapGroups = 64;             // phases * groups
 constexpr int kSmemCap = 192 * 1024;
@@ -170,16 +170,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    uint32_t it = 0, n = 0;
+  } else if (warp == 1 || warp == 2 + 4 * kEpiGroups) {
+    // ===== MMA issuers: two warps take alternate work items (disjoint accumulators and ring stages) =====
+    // (one thread sustains about one tcgen05.mma per ~100 cycles from this loop; an N <= 64 MMA occupies the pipe for
+    //  <= 48 — a second issuing thread keeps the pipe fed on the narrow layers)
+    // Only in resident mode (one ring stage per work item, an EVEN number of stages: each issuer then meets "its" stages
+    // and accumulators in order, one mbarrier phase at a time).  With several stages per item the second issuer would
+    // wait on phases two laps ahead of the barrier — a parity wait cannot tell those apart — so the streamed mode keeps
+    // one issuer.
+    const uint32_t iw = warp == 1 ? 0u : 1u;
+    const bool two = p.resident != 0;
+    uint32_t n = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n) {
+      if (two ? (n & 1u) != iw : iw != 0u) continue;
+      uint32_t it = p.resident ? n : n * (uint32_t)n_k;
       const uint32_t buf = n & (uint32_t)(p.n_acc - 1);
       lr_mbar_wait(&bar_acc_empty[buf], ((n / (uint32_t)p.n_acc) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d = tmem_base + buf * (uint32_t)p.Ntile;
       if (p.resident) {
-        if (n == 0) lr_mbar_wait(bar_w, 0);
+        lr_mbar_wait(bar_w, 0);                       // (completes once; later waits return at the first poll)
         const int ph = (int)fdiv(fdiv((uint32_t)item, p.d_mtiles), p.d_ntiles);
         const int s = it % p.stages;
         lr_mbar_wait(&bar_full[s], (it / p.stages) & 1);
@@ -199,7 +209,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           umma_commit(&bar_acc_full[buf]);
         }
         __syncwarp();
-        ++it;
         continue;
       }
       for (int k = 0; k < n_k; ++k, ++it) {
@@ -492,6 +501,7 @@ extern "C" int lr_tapgemm(const lr_tapgemm_desc* d, void* stream) {
       p.stage_bytes = boxes * p.a_tile_bytes;
       p.stages = (kSmemCap - p.w_bytes) / p.stage_bytes;
       if (p.stages > 4) p.stages = 4;
+      if (p.stages == 3) p.stages = 2;      // even: the two MMA-issuing warps alternate stages
     }
   }
   p.n_acc = ntile <= 64 ? 8 : (ntile <= 128 ? 4 : 2);

@@ -269,6 +269,7 @@ class DevicePrefetcher:
         if depth is None:
             depth = int(os.environ.get("LR_PREFETCH_DEPTH", 3))
         self.depth = max(2, int(depth))
+        self.trace = None               # a list: (start, end) timing events of every copy are appended (diagnostics)
 
     def __len__(self):
         return len(self.loader)
@@ -297,10 +298,16 @@ class DevicePrefetcher:
                 side = sides[p_i]
                 if released[k] is not None:
                     side.wait_event(released[k])
+                trace = self.trace
+                if trace is not None:
+                    t_a = torch.cuda.Event(enable_timing=True)
+                    t_a.record(side)
                 with torch.cuda.stream(side):
                     (buf[lo:hi] if src.dim() > 0 else buf).copy_(src[lo:hi] if src.dim() > 0 else src, non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=trace is not None)
                 ev.record(side)
+                if trace is not None:
+                    trace.append((t_a, ev))
                 evs.append(ev)
             return buf, evs, batch[1:]
 
