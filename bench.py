@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="clips per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="clips per GPU (weak scaling) / in total (--scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --batch is the GLOBAL batch, split evenly over the ranks (BASELINE config 4 reads 'batch=256 clips at 1/2/4/8')")
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--rnn", default="GRU")
     ap.add_argument("--cpu-batch", type=int, default=8, help="clips per step of the CPU baseline sample")
@@ -469,6 +471,9 @@ def main():
     char2idx = build_char2idx()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.scaling == "strong":
+        assert args.batch % world == 0, "--scaling strong: the global batch must divide over the ranks"
+        args.batch //= world
     cfg = {"workload": "stcnn+bi%s%d+ctc train step, synthetic u8 clips (B,75,100,50,3), B=%d clips/GPU, L in [10,30]"
                        % (args.rnn.lower(), args.hidden, args.batch),
            "clips_per_gpu": args.batch, "clip_shape": [T_FRAMES, H_FRAME, W_FRAME, 3], "optimizer": "adam lr=1e-4, clip 50",
@@ -559,20 +564,24 @@ def main():
         pf.trace = copy_trace
         return pf
     # every step's loss is read back to the host inside the timed region, through a pinned staging
-    # slot and an event (the value is collected one step later, so the read does not stall the queue)
+    # slot and an event (the value is collected two steps later, so the read does not stall the queue)
     losses, pending = [], []
     slots = torch.zeros(args.steps + 4, dtype=torch.float32).pin_memory()
+
+    LAG = 2         # the loss of step i is collected while step i + 2 is being enqueued
 
     def read_back(loss):
         i = len(pending)
         t_in = time.perf_counter()
         slots[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event(enable_timing=trace is not None)
+        # blocking event: the waiting host thread sleeps instead of spinning (eight ranks share the host's cores with
+        # their autograd and NCCL threads)
+        ev = torch.cuda.Event(enable_timing=trace is not None, blocking=True)
         ev.record()
         pending.append(ev)
-        if i > 0:
-            pending[i - 1].synchronize()
-            losses.append(float(slots[i - 1]))
+        if i >= LAG:
+            pending[i - LAG].synchronize()
+            losses.append(float(slots[i - LAG]))
         if trace is not None:
             trace.append((t_in, time.perf_counter()))
     run(host_loader, 3)
@@ -584,8 +593,9 @@ def main():
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     run(host_loader, args.steps, on_step=read_back)
-    pending[-1].synchronize()
-    losses.append(float(slots[len(pending) - 1]))
+    for j in range(max(0, len(pending) - LAG), len(pending)):       # the last LAG losses: still inside the timed region
+        pending[j].synchronize()
+        losses.append(float(slots[j]))
     t1.record()
     barrier()
     if trace is not None:
@@ -681,7 +691,7 @@ def main():
                                    "frac": v[1] / v[0] / 1e12 / peak} for k, v in per.items()}}
     line = {"metric": "frames/sec end-to-end (3Dconv+BiGRU+CTC train step)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": cfg, "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "final_loss": losses[-1] if losses else None},
