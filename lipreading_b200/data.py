@@ -270,6 +270,22 @@ class DevicePrefetcher:
             depth = int(os.environ.get("LR_PREFETCH_DEPTH", 3))
         self.depth = max(2, int(depth))
         self.trace = None               # a list: (start, end) timing events of every copy are appended (diagnostics)
+        self.kick_mode = os.environ.get("LR_H2D_KICK", "0") == "1"
+        self._kick = None
+
+    def kick(self, wait_current=True):
+        """Consumer hook (kick mode): enqueue the pending host->device copies now; with `wait_current` they start only
+        after the work enqueued so far on the current stream (e.g. the forward pass) has run."""
+        f, self._kick = self._kick, None
+        if f is None:
+            return
+        if wait_current:
+            self._after = torch.cuda.Event()
+            self._after.record(torch.cuda.current_stream(self.device))
+        else:
+            self._after = None
+        f()
+        self._after = None
 
     def __len__(self):
         return len(self.loader)
@@ -298,6 +314,8 @@ class DevicePrefetcher:
                 side = sides[p_i]
                 if released[k] is not None:
                     side.wait_event(released[k])
+                if getattr(self, "_after", None) is not None:
+                    side.wait_event(self._after)
                 trace = self.trace
                 if trace is not None:
                     t_a = torch.cuda.Event(enable_timing=True)
@@ -328,7 +346,12 @@ class DevicePrefetcher:
         fill()
         while queue:
             k, (frames, ev, rest) = queue.popleft()
-            fill()                       # keep depth-1 copies in flight behind the batch handed out now
+            if self.kick_mode:
+                # the next copy is enqueued when the consumer calls kick() (e.g. after its forward pass): it then starts
+                # behind the work enqueued so far instead of at the start of the step
+                self._kick = fill
+            else:
+                fill()                   # keep depth-1 copies in flight behind the batch handed out now
             cur = torch.cuda.current_stream(self.device)
             for e in ev:
                 cur.wait_event(e)
@@ -337,3 +360,5 @@ class DevicePrefetcher:
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(self.device))
             released[k] = done
+            if self._kick is not None:   # the consumer never kicked during the step
+                self.kick(wait_current=False)

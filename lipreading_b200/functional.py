@@ -191,9 +191,15 @@ class _ProjLogSoftmax(torch.autograd.Function):
             d_b = torch.empty(C, dtype=torch.float32, device=w.device)
             N.check(N.lib().lr_logsoftmax_bwd(N.ptr(g2), N.ptr(out), N.ptr(d_logits), N.ptr(d_b), M, C, N.stream()),
                     "lr_logsoftmax_bwd")
-            dl = d_logits.to(torch.bfloat16)
-            d_hidden = torch.mm(dl, w.to(torch.bfloat16), out_dtype=torch.float32)
-            d_w = torch.mm(dl.t(), h2.to(torch.bfloat16), out_dtype=torch.float32)
+            # (the class dimension is padded to a multiple of 16: with C = 65 the library otherwise falls back to a legacy
+            #  unaligned kernel — cutlass_75 s1688 align1, 119 + 26 us per step in the launch list against ~15 us aligned)
+            Cp = (C + 15) // 16 * 16
+            dl = torch.zeros((M, Cp), dtype=torch.bfloat16, device=w.device)
+            dl[:, :C] = d_logits
+            wp = torch.zeros((Cp, K), dtype=torch.bfloat16, device=w.device)
+            wp[:C] = w
+            d_hidden = torch.mm(dl, wp, out_dtype=torch.float32)
+            d_w = torch.mm(dl.t(), h2.to(torch.bfloat16), out_dtype=torch.float32)[:C]
             return d_hidden.reshape(ctx.in_shape), d_w, d_b, None
         d_hidden = torch.empty_like(h2)
         d_w = torch.empty_like(w)

@@ -249,6 +249,8 @@ def train_ctc(encoder, data_loader, opt, device, char2idx=None, grad_norm=None, 
         fl_d = fl_h.to(device, non_blocking=True)
         encoder._t_max_hint = int(fl_h.max())
         log_probs, _, _ = encoder(frames, fl_d)
+        if hasattr(data_loader, "kick"):
+            data_loader.kick()                               # prefetcher in kick mode: next copy starts behind the forward pass
         # (labels and lengths are on the host already: the wrapper decides feasibility there and never reads the
         # device, so the host keeps enqueueing a step ahead of the GPU)
         loss = ctc_loss(log_probs, labels, fl_d, ll_h, "mean", device, host_lens=(fl_h, ll_h), host_labels=chars_h[:, 1:])
