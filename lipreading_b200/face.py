@@ -6,7 +6,8 @@ What runs where
     not in this image) -> the box is an INPUT here: pass `rects`, or plug any detector through
     `set_detector(callable(frames)->(N,4) left,right,top,bottom)`;
   * position-map CNN (PRNet resfcn256): `lipreading_b200.prnet.PosPrediction` (architecture pinned by the
-    reference's checkpoint index; convolutions through cuDNN).  The reference ships no weights (`.gitignore:5`):
+    reference's checkpoint index; on CUDA the body runs as 53 launches of the tcgen05 tap-GEMM kernel, prnet_tc5.py).
+    The reference ships no weights (`.gitignore:5`):
     the default predictor restores `data/weights/prnet/net/256_256_resfcn256_weight` when the data shard is
     there (prnet.py:42-45) and asserts like the reference when it is not; any other predictor plugs in through
     `set_posmap_predictor`.  SURVEY §8 row a5 / f4;
