@@ -124,6 +124,23 @@ int lr_rnn_cluster_bwd(int mode, const float* d_hidden, const float* d_h_n, cons
                        const int32_t* lens, int B, int T, int H, int D, float* d_gi, float* d_gh,
                        float* h_prev_all, void* stream);
 
+/* Hidden sizes whose W_hh does not fit a cluster's shared memory (the reference's BiLSTM-768,
+ * config/archive/experiments/ecd/*): the same layer as ONE cooperative launch per pass — a direction's units are
+ * spread over H/16 co-resident CTAs (W_hh slices resident as bf16), the per-step operand (state / gate gradients) is
+ * exchanged through a double-buffered bf16 buffer in `workspace` (L2-resident) with one barrier per step among the
+ * CTAs of a direction; 64 clips per pass (csrc/rnn_grid.cu).  Same tensors and semantics as lr_rnn_cluster_*;
+ * workspace of lr_rnn_grid_workspace bytes (contents need not be initialised).
+ * lr_rnn_grid_supported: H % 256 == 0, D*H/16 <= 148 CTAs, slices fit shared memory.                  */
+int    lr_rnn_grid_supported(int mode, int H, int D);
+size_t lr_rnn_grid_workspace(int mode, int H, int D);
+int lr_rnn_grid_fwd(int mode, const float* gi, const float* w_hh, const float* b_hh,
+                    const int32_t* lens, int B, int T, int H, int D, float* hidden, float* h_n,
+                    float* c_n, float* saved, void* workspace, size_t ws_bytes, void* stream);
+int lr_rnn_grid_bwd(int mode, const float* d_hidden, const float* d_h_n, const float* d_c_n,
+                    const float* saved, const float* hidden, const float* w_hh,
+                    const int32_t* lens, int B, int T, int H, int D, float* d_gi, float* d_gh,
+                    float* h_prev_all, void* workspace, size_t ws_bytes, void* stream);
+
 /* -------- a11: collate / pad -------------------------------------------------------------- */
 /* replaces: src/data/data_loader.py:124-137 (_pad of ragged (T_i,68,3) f64 rows to (B,Tmax,F) f32).
  * src_concat f64 rows back to back, offsets (B+1) i64 in rows, dst (B,Tmax,F) f32 zero padded.  */

@@ -315,15 +315,23 @@ class _RNNLayer(torch.autograd.Function):
         S = L.lr_rnn_saved_per_unit(N.RNN_MODES[mode])
         saved = torch.empty((B, T, D, S * H), dtype=torch.float32, device=dev) if S > 0 else None
         use_cluster = bool(RNN_CLUSTER and L.lr_rnn_cluster_supported(N.RNN_MODES[mode], H))
+        # hidden sizes whose W_hh does not fit one cluster (BiLSTM-768): grid-persistent kernels (csrc/rnn_grid.cu)
+        use_grid = bool(RNN_CLUSTER and not use_cluster and L.lr_rnn_grid_supported(N.RNN_MODES[mode], H, D))
         if use_cluster:
             N.check(L.lr_rnn_cluster_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T,
                                          H, D, N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.stream()),
                     "lr_rnn_cluster_fwd")
+        elif use_grid:
+            ws = _ws(L.lr_rnn_grid_workspace(N.RNN_MODES[mode], H, D), dev)
+            N.check(L.lr_rnn_grid_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T, H, D,
+                                      N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.ptr(ws), ws.numel(),
+                                      N.stream()), "lr_rnn_grid_fwd")
         else:
             ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)
             N.check(L.lr_rnn_fwd(N.RNN_MODES[mode], N.ptr(gi), N.ptr(w_hh), N.ptr(b_hh), N.ptr(lens32), B, T, H, D,
                                  N.ptr(hidden), N.ptr(h_n), N.ptr(c_n), N.ptr(saved), N.ptr(ws), ws.numel(),
                                  N.stream()), "lr_rnn_fwd")
+        ctx.use_grid = use_grid
         ctx.use_cluster = use_cluster
         ctx.mode, ctx.dims = mode, (B, T, I, H, D, G)
         ctx.save_for_backward(x2, lens32, w_ih, w_hh, hidden, saved if saved is not None else torch.empty(0, device=dev))
@@ -351,6 +359,12 @@ class _RNNLayer(torch.autograd.Function):
                                          N.ptr(saved) if saved.numel() else None, N.ptr(hidden), N.ptr(w_hh),
                                          N.ptr(lens32), B, T, H, D, N.ptr(d_gi), N.ptr(d_gh), N.ptr(h_prev),
                                          N.stream()), "lr_rnn_cluster_bwd")
+        elif ctx.use_grid:
+            ws = _ws(L.lr_rnn_grid_workspace(N.RNN_MODES[mode], H, D), dev)
+            N.check(L.lr_rnn_grid_bwd(N.RNN_MODES[mode], N.ptr(d_hidden), N.ptr(d_h_n), N.ptr(d_c_n),
+                                      N.ptr(saved) if saved.numel() else None, N.ptr(hidden), N.ptr(w_hh),
+                                      N.ptr(lens32), B, T, H, D, N.ptr(d_gi), N.ptr(d_gh), N.ptr(h_prev), N.ptr(ws),
+                                      ws.numel(), N.stream()), "lr_rnn_grid_bwd")
         else:
             w_hh_t = w_hh.transpose(1, 2).contiguous()                          # (D,H,G*H)
             ws = _ws(L.lr_rnn_workspace(N.RNN_MODES[mode], B, T, H, D), dev)

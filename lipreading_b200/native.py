@@ -43,6 +43,10 @@ SIGNATURES = {
     "lr_rnn_cluster_supported": (_i, [_i, _i]),
     "lr_rnn_cluster_fwd": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "lr_rnn_cluster_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "lr_rnn_grid_supported": (_i, [_i, _i, _i]),
+    "lr_rnn_grid_workspace": (_sz, [_i, _i, _i]),
+    "lr_rnn_grid_fwd": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lr_rnn_grid_bwd": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lr_collate_pad_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "lr_rect_geometry": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "lr_warp256": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -237,9 +237,28 @@ def test_ctc_wrapper_quirk_matches_oracle(native_lib, cuda, reduction):
 def test_rnn_cluster_kernels_match_oracle_bf16(native_lib, cuda, rnn_type, bidirectional, B, T, H):
     """Throughput path (persistent 8-CTA cluster kernels, bf16 operands / fp32 accumulate+state) vs the
     fp32 packed-sequence reference.  Tolerance = bf16 operand rounding through T recurrent steps."""
-    from lipreading_b200 import functional as LF
     if not native_lib.lr_rnn_cluster_supported({"RNN": 0, "GRU": 1, "LSTM": 2}[rnn_type], H):
         pytest.skip("shape not supported by the cluster kernels")
+    _persistent_rnn_vs_packed_torch(native_lib, cuda, rnn_type, bidirectional, B, T, H)
+
+
+@pytest.mark.parametrize("rnn_type,bidirectional,B,T,H", [("LSTM", True, 70, 12, 768), ("GRU", True, 37, 9, 768),
+                                                          ("LSTM", False, 64, 7, 512), ("RNN", True, 20, 5, 1024),
+                                                          ("LSTM", True, 128, 75, 768)])
+def test_rnn_grid_kernels_match_oracle_bf16(native_lib, cuda, rnn_type, bidirectional, B, T, H):
+    """Hidden sizes whose W_hh does not fit a cluster (the reference's BiLSTM-768, config/archive/experiments/ecd/*,
+    better_model.py:47-49): the grid-persistent kernels (csrc/rnn_grid.cu, one cooperative launch per pass) vs the fp32
+    packed-sequence reference, incl. batches of more than one 64-clip pass and ragged lengths."""
+    mode = {"RNN": 0, "GRU": 1, "LSTM": 2}[rnn_type]
+    D = 2 if bidirectional else 1
+    assert not native_lib.lr_rnn_cluster_supported(mode, H) and native_lib.lr_rnn_grid_supported(mode, H, D)
+    n0 = native_lib.lr_launch_count()
+    _persistent_rnn_vs_packed_torch(native_lib, cuda, rnn_type, bidirectional, B, T, H, tol=4e-2 if T > 20 else 3e-2)
+    assert native_lib.lr_launch_count() - n0 == 2                  # one forward + one backward launch, not 2*T*D
+
+
+def _persistent_rnn_vs_packed_torch(native_lib, cuda, rnn_type, bidirectional, B, T, H, tol=3e-2):
+    from lipreading_b200 import functional as LF
     I = 40
     g = torch.Generator().manual_seed(2024)
     ref = getattr(torch.nn, rnn_type)(I, H, bidirectional=bidirectional, batch_first=True)
@@ -277,8 +296,8 @@ def test_rnn_cluster_kernels_match_oracle_bf16(native_lib, cuda, rnn_type, bidir
         torch.cuda.synchronize()
     finally:
         LF.RNN_CLUSTER = False
-    assert float((res[0].cpu() - out_r.detach()).abs().max()) < 3e-2
-    assert float((res[1].cpu() - hn_r.detach()).abs().max()) < 3e-2
+    assert float((res[0].cpu() - out_r.detach()).abs().max()) < tol
+    assert float((res[1].cpu() - hn_r.detach()).abs().max()) < tol
     # exact zeros beyond each clip's length, like pad_packed_sequence
     for b in range(B):
         assert float(res[0][b, int(lens[b]):].abs().max() if int(lens[b]) < T else 0.0) == 0.0
