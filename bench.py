@@ -279,6 +279,21 @@ def ref_shape_block(dev, char2idx, steps=3):
                                  % (rnn.lower(), H, B, "40..75 mixed" if mixed else "75"),
                        "gpu_frames_per_s": n_frames / s_gpu, "gpu_ms_per_step": s_gpu * 1e3, "gpu_path": "fp32 parity path",
                        "decoder_loss": dl, "ctc_loss": cl}
+                # the same call on the throughput path: persistent recurrent kernels (8-CTA cluster for H = 256, the
+                # grid-persistent kernels for H = 768) with bf16 operands, bf16 library GEMMs around them
+                LF.GEMM_DTYPE, LF.RNN_CLUSTER = torch.bfloat16, True
+                with contextlib.redirect_stdout(io.StringIO()):
+                    trainer.train(enc, dec, [batch], opt, dev, char2idx, teacher_forcing_ratio=1, grad_norm=50)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    trainer.train(enc, dec, [batch] * steps, opt, dev, char2idx, teacher_forcing_ratio=1, grad_norm=50)
+                    e1.record()
+                    torch.cuda.synchronize()
+                s_thr = e0.elapsed_time(e1) * 1e-3 / steps
+                row["gpu_frames_per_s_persistent_bf16"] = n_frames / s_thr
+                row["gpu_ms_per_step_persistent_bf16"] = s_thr * 1e3
+                LF.GEMM_DTYPE, LF.RNN_CLUSTER = torch.float32, False
                 if not mixed:
                     # CPU arm on a bounded sample (first cpu_B clips of the same batch), all usable host threads
                     sample = tuple(t[:cpu_B].clone() for t in batch)
