@@ -18,6 +18,9 @@ Parity status:
     (estimate_transform, warp), dlib 19.16 (HOG box) and the PRNet weights are absent from the
     reference tree and from this image -> "parity unpinned" for those; tolerances are stated in
     the tests.
+  * position-map CNN (rows a5 / f4): oracle/tapgemm.py states what one lr_tapgemm launch computes; tests replay the
+    compiled launch plan through it and hold it to prnet.ResFcn256 (the restatement of src/models/face/prnet.py:211-280,
+    itself held to the reference's checkpoint index).  No weights exist -> values "parity unpinned".
   * conv3d front-end and mouth crop are north-star extensions with no reference code; their oracle
     is torch.nn.functional.conv3d fp32 / the numpy spec in oracle/vision.py.
 """
