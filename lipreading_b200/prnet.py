@@ -286,6 +286,7 @@ class ResFcn256(nn.Module):
 class PosPrediction:
     """Drop-in for prnet.PosPrediction (:283-314): predict / predict_batch take NHWC float images in [0,1]
     (numpy or torch) and return the position map * MaxPos in the same layout."""
+    MAX_PLAN_BATCH = 64                 # largest batch a tcgen05 launch plan is compiled for (a power of two)
 
     def __init__(self, resolution_inp=256, resolution_op=256, device="cuda", dtype=torch.float32, engine=None):
         self.resolution_inp, self.resolution_op = resolution_inp, resolution_op
@@ -319,7 +320,20 @@ class PosPrediction:
         as_numpy = isinstance(images, np.ndarray)
         x = torch.as_tensor(images, device=self.device)
         if self.engine == "tcgen05":
-            y = self.plan(x.shape[0]).run(x.float().contiguous()).clone()
+            # a compiled plan owns ~33 MB of activation volumes per frame: only power-of-two batch sizes up to
+            # MAX_PLAN_BATCH are compiled (at most 7 plans), any other batch runs as its binary decomposition
+            # (37 frames = 32 + 4 + 1) — the ragged tail batches of generate_dataview would otherwise compile, and
+            # keep, one plan per distinct size
+            x = x.float().contiguous()
+            n, outs, i = x.shape[0], [], 0
+            if n == 0:
+                y = x.new_zeros((0, self.resolution_op, self.resolution_op, 3))
+                return y.cpu().numpy() if as_numpy else y
+            while i < n:
+                b = 1 << min((n - i).bit_length() - 1, self.MAX_PLAN_BATCH.bit_length() - 1)
+                outs.append(self.plan(b).run(x[i:i + b]).clone())
+                i += b
+            y = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
             return y.cpu().numpy() if as_numpy else y
         with torch.no_grad():
             x = x.permute(0, 3, 1, 2).to(dtype=self.dtype, memory_format=torch.channels_last)

@@ -120,3 +120,30 @@ def test_fused_tap_groups_cover_each_tap_once():
     assert len(phases) == 4 and all(len(p) == 4 for p in phases)
     total = sum(float(m.abs().sum()) for p in phases for _, _, m in p)
     assert abs(total - float(wt.abs().sum())) < 1e-3 * total
+
+
+def test_predict_batch_runs_any_batch_on_power_of_two_plans():
+    """PosPrediction (tcgen05 engine) compiles plans for power-of-two batches only and runs any other batch as its binary
+    decomposition, so ragged tail batches do not each compile (and keep) a plan of their own."""
+    from lipreading_b200 import prnet as P
+    pred = P.PosPrediction(device="cpu", engine="tcgen05", resolution_inp=32, resolution_op=32)
+    seen = []
+
+    class FakePlan:
+        def __init__(self, b):
+            self.b = b
+
+        def run(self, x):
+            assert x.shape[0] == self.b and x.is_contiguous()
+            seen.append(self.b)
+            return x[..., :3] * 2.0
+
+    pred.plan = lambda b: FakePlan(b)
+    for n, want in ((1, [1]), (64, [64]), (37, [32, 4, 1]), (24, [16, 8]), (100, [64, 32, 4]), (63, [32, 16, 8, 4, 2, 1])):
+        del seen[:]
+        x = torch.rand(n, 32, 32, 3)
+        y = pred.predict_batch(x)
+        assert seen == want and torch.equal(y, x * 2.0)
+    assert pred.predict_batch(torch.zeros(0, 32, 32, 3)).shape == (0, 32, 32, 3)
+    out = pred.predict(torch.rand(32, 32, 3).numpy())                  # numpy in -> numpy out, like the reference
+    assert out.shape == (32, 32, 3) and out.dtype.name == "float32"
